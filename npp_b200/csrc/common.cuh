@@ -1,0 +1,96 @@
+// Shared device / host helpers for libnpp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/npp_b200.h"
+
+namespace npp {
+
+void set_error(const char* what, cudaError_t e);
+void set_error_str(const char* what);
+
+#define NPP_CHECK_LAUNCH(name)                          \
+  do {                                                  \
+    cudaError_t e__ = cudaGetLastError();               \
+    if (e__ != cudaSuccess) {                           \
+      ::npp::set_error(name, e__);                      \
+      return NPP_E_CUDA;                                \
+    }                                                   \
+  } while (0)
+
+static inline cudaStream_t as_stream(npp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- dtype traits: storage T, math in fp32 ---------------------------------------------------
+template <typename T> struct VecOf;  // 16-byte vector of T
+template <> struct VecOf<float> { static constexpr int N = 4; };
+template <> struct VecOf<__nv_bfloat16> { static constexpr int N = 8; };
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte load/store of VecOf<T>::N elements converted to/from fp32 registers
+template <typename T> struct Pack;
+template <> struct Pack<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Pack<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(u[i] << 16);
+      v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      u[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+  }
+};
+
+// ---- view checks -------------------------------------------------------------------------------
+static inline bool view_ok(const npp_view4* v, int dtype) {
+  if (!v || !v->ptr || v->n <= 0 || v->h <= 0 || v->w <= 0 || v->c <= 0) return false;
+  const int vec = dtype == NPP_BF16 ? 8 : 4;
+  const int esz = dtype == NPP_BF16 ? 2 : 4;
+  if (v->c % vec) return false;
+  if (v->sw % vec || v->sh % vec || v->sn % vec) return false;
+  if (reinterpret_cast<uintptr_t>(v->ptr) % 16) return false;
+  (void)esz;
+  return true;
+}
+static inline bool same_shape(const npp_view4* a, const npp_view4* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();
+
+}  // namespace npp

@@ -1,0 +1,838 @@
+// Dense convolution (fprop / dgrad / wgrad) as implicit GEMM on the sm_100a tensor cores.
+//
+//   fprop / dgrad : D[pixels, Cout] = sum_taps A_tap[pixels, Cin] * W_tap[Cout, Cin]^T
+//       A_tap is the activation box shifted by the tap offset, fetched by ONE 4-D TMA per
+//       (tap, 64-channel chunk); out-of-bounds coordinates are zero-filled by the TMA unit, which
+//       is exactly the convolution's zero padding.  Stride-2 convolutions address four "phase"
+//       tensor maps (even/odd rows x even/odd columns) so every tap is still a dense box.
+//       Both operands are K-major SWIZZLE_128B tiles consumed by tcgen05.mma (M=128, N=BN, K=16)
+//       with the fp32 accumulator in TMEM; a 4-warp epilogue drains TMEM (tcgen05.ld), adds the
+//       bias, rounds to bf16, accumulates BatchNorm batch statistics and TMA-stores the tile.
+//       Persistent CTAs (one per SM), STAGES-deep smem ring, two TMEM accumulator stages so the
+//       epilogue of tile i overlaps the MMAs of tile i+1.
+//   wgrad : dW_tap[Cout, Cin] = sum_pixels dY[pixels, Cout]^T * X_tap[pixels, Cin]
+//       Same boxes, but now the pixel axis is the GEMM K axis, i.e. both operands are MN-major
+//       SWIZZLE_128B tiles (tcgen05 handles the transpose in the descriptor).  Split-K over
+//       pixels; partial sums are combined with red.global.add.f32.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM lane quarter = warp & 3).
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <string.h>
+
+namespace npp {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int kMaxTaps = 9;
+constexpr int BM = 128;       // pixels per tile (UMMA M)
+constexpr int BK = 64;        // channels per k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+struct TapTable {
+  int8_t map[kMaxTaps];   // which activation tensor map (phase) the tap reads
+  int8_t dh[kMaxTaps];    // row / column offset of the box in that map's coordinates
+  int8_t dw[kMaxTaps];
+  int8_t btap[kMaxTaps];  // index into the weight tensor's tap dimension
+};
+
+struct Maps {
+  CUtensorMap a[4];  // activation (phase) maps: dims (C, W, H, N)
+  CUtensorMap b;     // weights: dims (K, taps, rows)
+  CUtensorMap d;     // output: dims (C, W, H, N)
+};
+
+struct Geom {
+  int num_taps, kc_blocks;
+  int tw, th, tn;                 // pixel tile box, tw*th*tn == 128 (fprop) or 64 (wgrad K block)
+  int tiles_w, tiles_h, tiles_n;  // pixel tiles per dimension
+  int W, H, N;                    // output (fprop) pixel-space extents, for masking
+  int n_blocks;                   // Cout blocks of BN
+  int cout;
+  int total_tiles;
+};
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = 2 * BM * 128;  // two bf16 staging slabs (128 rows x 64 ch)
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32..256}
+};
+
+// =================================================================================================
+// fprop / dgrad kernel
+// =================================================================================================
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
+                 const float* __restrict__ bias, float* __restrict__ stats) {
+  using Cfg = FpropCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t smem_out = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_out + Cfg::OUT_BYTES;
+  const uint32_t full_bar = bar_base;                   // STAGES x 8 B
+  const uint32_t empty_bar = bar_base + 8 * STAGES;     // STAGES x 8 B
+  const uint32_t tfull_bar = bar_base + 16 * STAGES;    // 2 x 8 B
+  const uint32_t tempty_bar = tfull_bar + 16;           // 2 x 8 B
+  const uint32_t tmem_slot = tempty_bar + 16;           // 4 B
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.a[0]);
+    prefetch_tensormap(&maps.b);
+    prefetch_tensormap(&maps.d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int num_k = g.num_taps * g.kc_blocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int nb = tile % g.n_blocks;
+        int pt = tile / g.n_blocks;
+        const int w0 = (pt % g.tiles_w) * g.tw;
+        pt /= g.tiles_w;
+        const int h0 = (pt % g.tiles_h) * g.th;
+        const int n0 = (pt / g.tiles_h) * g.tn;
+        for (int t = 0; t < g.num_taps; ++t) {
+          const CUtensorMap* ma = &maps.a[taps.map[t]];
+          const int cw = w0 + taps.dw[t], ch = h0 + taps.dh[t], bt = taps.btap[t];
+          for (int kc = 0; kc < g.kc_blocks; ++kc) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+            tma_load_4d(smem_a + stage * Cfg::A_BYTES, ma, full_bar + 8 * stage, kc * BK, cw, ch, n0);
+            tma_load_3d(smem_b + stage * Cfg::B_BYTES, &maps.b, full_bar + 8 * stage, kc * BK, bt,
+                        nb * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // tile row == TMEM lane
+    const int etid = threadIdx.x - kEpiWarp0 * 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int sbuf = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int nb = tile % g.n_blocks;
+      int pt = tile / g.n_blocks;
+      const int w0 = (pt % g.tiles_w) * g.tw;
+      pt /= g.tiles_w;
+      const int h0 = (pt % g.tiles_h) * g.th;
+      const int n0 = (pt / g.tiles_h) * g.tn;
+      // validity of this thread's pixel row (ragged tiles), for the statistics
+      bool row_valid;
+      {
+        const int rw = row % g.tw, rh = (row / g.tw) % g.th, rn = row / (g.tw * g.th);
+        row_valid = (w0 + rw < g.W) && (h0 + rh < g.H) && (n0 + rn < g.N);
+      }
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
+      constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
+#pragma unroll 1
+      for (int slab = 0; slab < SLABS; ++slab) {
+        const int co_base = nb * BN + slab * 64;
+        if (co_base >= g.cout) break;  // uniform across the CTA
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (etid == 0) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* stg = smem_gen + (smem_out - smem_base) + sbuf * (BM * 128);
+#pragma unroll
+        for (int half = 0; half < SLAB_COLS / 32; ++half) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + slab * 64 + half * 32);
+          tmem_ld_32x32(taddr, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // four 16-byte chunks (8 channels each)
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = half * 32 + j * 8 + e * 2;
+              float v0 = __uint_as_float(r[j * 8 + e * 2]);
+              float v1 = __uint_as_float(r[j * 8 + e * 2 + 1]);
+              if (bias != nullptr) {
+                const int c0 = co_base + col;
+                v0 += (c0 < g.cout) ? __ldg(bias + c0) : 0.f;
+                v1 += (c0 + 1 < g.cout) ? __ldg(bias + c0 + 1) : 0.f;
+              }
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const int chunk = half * 4 + j;
+            *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          tma_store_4d(&maps.d, smem_out + sbuf * (BM * 128), co_base, w0, h0, n0);
+          tma_store_commit();
+        }
+        if (stats != nullptr) {
+          // per-channel sum / sum of squares of the bf16-rounded tile: thread -> (column, row half)
+          const int col = etid & 63;
+          const int rbeg = (etid >> 6) * 64;
+          if (col < SLAB_COLS && co_base + col < g.cout) {
+            float s = 0.f, s2 = 0.f;
+            const int chunk = col >> 3, e = col & 7;
+            for (int rr = rbeg; rr < rbeg + 64; ++rr) {
+              const int rw = rr % g.tw, rh = (rr / g.tw) % g.th, rn = rr / (g.tw * g.th);
+              const bool ok = (w0 + rw < g.W) && (h0 + rh < g.H) && (n0 + rn < g.N);
+              const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16*>(
+                  stg + rr * 128 + ((chunk ^ (rr & 7)) << 4) + e * 2);
+              const float v = ok ? __bfloat162float(hv) : 0.f;
+              s += v;
+              s2 += v * v;
+            }
+            atomicAdd(stats + co_base + col, s);
+            atomicAdd(stats + g.cout + co_base + col, s2);
+          }
+        }
+        sbuf ^= 1;
+      }
+      (void)row_valid;
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// wgrad kernel: dW[co, tap, ci] += sum_{pixels in this CTA's K range} dY[p, co] * X[p + tap, ci]
+// =================================================================================================
+struct WMaps {
+  CUtensorMap x[4];  // activation (phase) maps
+  CUtensorMap dy;
+};
+struct WGeom {
+  int num_taps;
+  int tw, th, tn;  // K block = 64 pixels
+  int tiles_w, tiles_h, tiles_n;
+  int total_ptiles;
+  int co_blocks, ci_blocks;  // of 128 / BN
+  int cout, cin, dw_ld;      // dw_ld = leading dimension (cin of the fp32 gradient)
+  int ksplit;
+};
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int KP = 64;                 // pixels per k-block
+  static constexpr int A_BYTES = 2 * KP * 128;  // two 64-channel slabs of dY
+  static constexpr int B_BYTES = (BN / 64) * KP * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTable taps,
+                  float* __restrict__ dw) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int SLAB = Cfg::KP * 128;  // bytes of one [64 pixels x 64 channels] slab
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8 * STAGES;
+  const uint32_t tfull_bar = bar_base + 16 * STAGES;
+  const uint32_t tmem_slot = tfull_bar + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // output tile of this CTA
+  int ot = blockIdx.x;
+  const int ci_blk = ot % g.ci_blocks;
+  ot /= g.ci_blocks;
+  const int co_blk = ot % g.co_blocks;
+  const int tap = ot / g.co_blocks;
+  // K range (pixel tiles)
+  const int p_begin = static_cast<int>((static_cast<int64_t>(g.total_ptiles) * blockIdx.y) / g.ksplit);
+  const int p_end = static_cast<int>((static_cast<int64_t>(g.total_ptiles) * (blockIdx.y + 1)) / g.ksplit);
+  const int num_k = p_end - p_begin;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.dy);
+    prefetch_tensormap(&maps.x[taps.map[tap]]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* mx = &maps.x[taps.map[tap]];
+        const int dwx = taps.dw[tap], dhx = taps.dh[tap];
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int p = p_begin; p < p_end; ++p) {
+          int pt = p;
+          const int w0 = (pt % g.tiles_w) * g.tw;
+          pt /= g.tiles_w;
+          const int h0 = (pt % g.tiles_h) * g.th;
+          const int n0 = (pt / g.tiles_h) * g.tn;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
+          const uint32_t sb = smem_b + stage * Cfg::B_BYTES;
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            tma_load_4d(sa + s * SLAB, &maps.dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
+#pragma unroll
+          for (int s = 0; s < BN / 64; ++s)
+            tma_load_4d(sb + s * SLAB, mx, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + dwx,
+                        h0 + dhx, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          // MN-major SW128: 64-element MN slabs LBO apart, 8-row K groups SBO = 1024 B apart
+          const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, SLAB, 1024);
+          const uint64_t db = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES, SLAB, 1024);
+#pragma unroll
+          for (int k = 0; k < Cfg::KP / 16; ++k) {
+            // 16 pixels (K) further = 16 rows x 128 B = 2048 B -> +128 in (addr>>4)
+            umma_f16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar);
+      }
+    } else if (warp >= kEpiWarp0) {
+      const int q = warp & 3;
+      const int co = co_blk * 128 + q * 32 + lane;
+      const int bt = taps.btap[tap];
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c32 * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int ci = ci_blk * BN + c32 * 32 + j;
+          if (co < g.cout && ci < g.cin)
+            atomicAdd(dw + (static_cast<int64_t>(co) * g.num_taps + bt) * g.dw_ld + ci,
+                      __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// =================================================================================================
+// Host side: tensor maps, tile geometry, launches
+// =================================================================================================
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 4-D bf16 map over (C, W, H, N) with element strides (1, sw, sh, sn); box (64, bw, bh, bn).
+static int encode_act_map(CUtensorMap* m, const void* ptr, int64_t C, int64_t W, int64_t H, int64_t N,
+                          int64_t sw, int64_t sh, int64_t sn, int bw, int bh, int bn) {
+  auto fn = get_encode_fn();
+  if (!fn) return NPP_E_NODRIVER;
+  if (W <= 0 || H <= 0 || N <= 0 || C <= 0) return NPP_E_INVALID;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled(act) failed: %d dims=(%lld,%lld,%lld,%lld) strides=(%lld,%lld,%lld) "
+             "box=(64,%d,%d,%d) ptr=%p",
+             (int)r, (long long)C, (long long)W, (long long)H, (long long)N, (long long)sw, (long long)sh,
+             (long long)sn, bw, bh, bn, ptr);
+    set_error_str(buf);
+    return NPP_E_CUDA;
+  }
+  return NPP_OK;
+}
+
+// 3-D bf16 weight map over (K, taps, rows) of a dense [rows, taps, K] array; box (64, 1, brows).
+static int encode_w_map(CUtensorMap* m, const void* ptr, int64_t K, int64_t taps, int64_t rows, int brows) {
+  auto fn = get_encode_fn();
+  if (!fn) return NPP_E_NODRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)taps, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * taps * 2};
+  cuuint32_t box[3] = {64u, 1u, (cuuint32_t)brows};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weight) failed: %d K=%lld taps=%lld rows=%lld", (int)r,
+             (long long)K, (long long)taps, (long long)rows);
+    set_error_str(buf);
+    return NPP_E_CUDA;
+  }
+  return NPP_OK;
+}
+
+struct PixTile { int tw, th, tn; };
+// Factor `prod` (a power of two) into a (tw, th, tn) box minimising padded work for a (W,H,N) grid.
+static PixTile choose_tile(int64_t W, int64_t H, int64_t N, int prod) {
+  PixTile best{prod, 1, 1};
+  double best_cost = 1e300;
+  for (int tw = 1; tw <= prod; tw <<= 1)
+    for (int th = 1; tw * th <= prod; th <<= 1) {
+      const int tn = prod / (tw * th);
+      if (tw > 256 || th > 256 || tn > 256) continue;
+      const double cost = (double)(cdiv64(W, tw) * tw) * (double)(cdiv64(H, th) * th) * (double)(cdiv64(N, tn) * tn);
+      // prefer wide boxes on ties (longer contiguous runs per TMA row)
+      if (cost < best_cost || (cost == best_cost && tw > best.tw)) {
+        best_cost = cost;
+        best = PixTile{tw, th, tn};
+      }
+    }
+  return best;
+}
+
+struct PixSpace {  // the (W,H,N) pixel grid a launch tiles, possibly flattened to one dimension
+  int64_t W, H, N;
+};
+
+static bool dense_pixels(const npp_view4* v) { return v->sh == (int64_t)v->w * v->sw && v->sn == (int64_t)v->h * v->sh; }
+
+static bool bf16_view_ok(const npp_view4* v) { return view_ok(v, NPP_BF16); }
+
+template <int BN>
+static int launch_fprop(const Maps& maps, const Geom& g, const TapTable& taps, const float* bias, float* stats,
+                        cudaStream_t st) {
+  using Cfg = FpropCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm)", e); return NPP_E_CUDA; }
+    attr_set = true;
+  }
+  const int grid = g.total_tiles < sm_count() ? g.total_tiles : sm_count();
+  conv_gemm_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, bias, stats);
+  NPP_CHECK_LAUNCH("conv_gemm_kernel");
+  return NPP_OK;
+}
+
+static int pick_bn(int cout) {
+  if (cout <= 32) return 32;
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  const int64_t w256 = cdiv64(cout, 256) * 256, w128 = cdiv64(cout, 128) * 128;
+  return w256 <= w128 ? 256 : 128;
+}
+
+// One implicit-GEMM launch: D(pixel space of `d`) = sum_taps A(map, offset) * B(tap)
+//   a_maps[i]: activation views addressed by the taps (already phase-decomposed), d: output view.
+static int run_gemm(const npp_view4* a_views, int n_a, const npp_view4* d, const void* wmat, int wK, int wTaps,
+                    int wRows, const TapTable& taps, int num_taps, bool allow_flatten, const float* bias,
+                    float* stats, cudaStream_t st) {
+  Maps maps;
+  memset(&maps, 0, sizeof maps);
+  Geom g;
+  memset(&g, 0, sizeof g);
+  bool flat = allow_flatten && n_a == 1 && num_taps == 1 && taps.dh[0] == 0 && taps.dw[0] == 0 &&
+              dense_pixels(&a_views[0]) && dense_pixels(d) && a_views[0].n == d->n && a_views[0].h == d->h &&
+              a_views[0].w == d->w;
+  PixSpace ps{d->w, d->h, d->n};
+  if (flat) ps = PixSpace{(int64_t)d->w * d->h * d->n, 1, 1};
+  const PixTile t = choose_tile(ps.W, ps.H, ps.N, BM);
+  int rc;
+  for (int i = 0; i < n_a; ++i) {
+    const npp_view4& v = a_views[i];
+    if (!v.ptr) continue;
+    if (flat)
+      rc = encode_act_map(&maps.a[i], v.ptr, v.c, ps.W, 1, 1, v.sw, v.sw * ps.W, v.sw * ps.W, t.tw, t.th, t.tn);
+    else
+      rc = encode_act_map(&maps.a[i], v.ptr, v.c, v.w, v.h, v.n, v.sw, v.sh, v.sn, t.tw, t.th, t.tn);
+    if (rc) return rc;
+  }
+  if (flat)
+    rc = encode_act_map(&maps.d, d->ptr, d->c, ps.W, 1, 1, d->sw, d->sw * ps.W, d->sw * ps.W, t.tw, t.th, t.tn);
+  else
+    rc = encode_act_map(&maps.d, d->ptr, d->c, d->w, d->h, d->n, d->sw, d->sh, d->sn, t.tw, t.th, t.tn);
+  if (rc) return rc;
+  const int bn = pick_bn(wRows);
+  rc = encode_w_map(&maps.b, wmat, wK, wTaps, wRows, bn);
+  if (rc) return rc;
+  g.num_taps = num_taps;
+  g.kc_blocks = (int)cdiv64(wK, BK);
+  g.tw = t.tw; g.th = t.th; g.tn = t.tn;
+  g.tiles_w = (int)cdiv64(ps.W, t.tw);
+  g.tiles_h = (int)cdiv64(ps.H, t.th);
+  g.tiles_n = (int)cdiv64(ps.N, t.tn);
+  g.W = (int)ps.W; g.H = (int)ps.H; g.N = (int)ps.N;
+  g.n_blocks = (int)cdiv64(wRows, bn);
+  g.cout = wRows;
+  const int64_t total = (int64_t)g.tiles_w * g.tiles_h * g.tiles_n * g.n_blocks;
+  if (total > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  g.total_tiles = (int)total;
+  switch (bn) {
+    case 32: return launch_fprop<32>(maps, g, taps, bias, stats, st);
+    case 64: return launch_fprop<64>(maps, g, taps, bias, stats, st);
+    case 128: return launch_fprop<128>(maps, g, taps, bias, stats, st);
+    default: return launch_fprop<256>(maps, g, taps, bias, stats, st);
+  }
+}
+
+static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
+
+// phase (ph,pw) sub-view of v for stride-2 addressing
+static npp_view4 phase_view(const npp_view4& v, int ph, int pw) {
+  npp_view4 r = v;
+  r.ptr = static_cast<char*>(v.ptr) + (ph * v.sh + pw * v.sw) * 2;
+  r.h = (v.h - ph + 1) / 2;
+  r.w = (v.w - pw + 1) / 2;
+  r.sh = 2 * v.sh;
+  r.sw = 2 * v.sw;
+  if (r.h <= 0 || r.w <= 0) r.ptr = nullptr;
+  return r;
+}
+
+static int check_conv_args(const npp_view4* x, const npp_view4* y, int kh, int kw, int stride, int pad, int dil) {
+  if (!bf16_view_ok(x) || !bf16_view_ok(y)) return NPP_E_INVALID;
+  if (kh <= 0 || kw <= 0 || kh * kw > kMaxTaps || (stride != 1 && stride != 2) || pad < 0 || dil < 1)
+    return NPP_E_UNSUPPORTED;
+  if (x->n != y->n) return NPP_E_INVALID;
+  if (pad + dil * (kh > kw ? kh : kw) > 100) return NPP_E_UNSUPPORTED;  // int8 tap offsets
+  return NPP_OK;
+}
+
+int conv_fwd(const npp_view4* x, const void* w, const float* bias, const npp_view4* y, int kh, int kw, int stride,
+             int pad, int dil, int hoff, int woff, float* stats, cudaStream_t st) {
+  int rc = check_conv_args(x, y, kh, kw, stride, pad, dil);
+  if (rc) return rc;
+  if (!w) return NPP_E_INVALID;
+  TapTable taps;
+  memset(&taps, 0, sizeof taps);
+  npp_view4 av[4];
+  memset(av, 0, sizeof av);
+  int n_a = 1;
+  if (stride == 1) {
+    av[0] = *x;
+  } else {
+    n_a = 4;
+  }
+  int t = 0;
+  for (int r = 0; r < kh; ++r)
+    for (int s = 0; s < kw; ++s, ++t) {
+      const int ah = -pad + r * dil + hoff, aw = -pad + s * dil + woff;
+      if (stride == 1) {
+        taps.map[t] = 0; taps.dh[t] = (int8_t)ah; taps.dw[t] = (int8_t)aw;
+      } else {
+        const int ph = ((ah % 2) + 2) % 2, pw = ((aw % 2) + 2) % 2;
+        taps.map[t] = (int8_t)(ph * 2 + pw);
+        taps.dh[t] = (int8_t)floordiv2(ah - ph);
+        taps.dw[t] = (int8_t)floordiv2(aw - pw);
+        if (!av[ph * 2 + pw].ptr) av[ph * 2 + pw] = phase_view(*x, ph, pw);
+        if (!av[ph * 2 + pw].ptr) return NPP_E_UNSUPPORTED;
+      }
+      taps.btap[t] = (int8_t)t;
+    }
+  return run_gemm(av, n_a, y, w, x->c, kh * kw, y->c, taps, kh * kw, stride == 1, bias, stats, st);
+}
+
+int fill_zero_view_bf16(const npp_view4* v, cudaStream_t st);  // elementwise.cu
+
+int conv_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, int kh, int kw, int stride, int pad,
+               int dil, int hoff, int woff, cudaStream_t st) {
+  int rc = check_conv_args(dx, dy, kh, kw, stride, pad, dil);
+  if (rc) return rc;
+  if (!wt) return NPP_E_INVALID;
+  if (stride == 1) {
+    TapTable taps;
+    memset(&taps, 0, sizeof taps);
+    int t = 0;
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s, ++t) {
+        taps.map[t] = 0;
+        taps.dh[t] = (int8_t)(pad - r * dil - hoff);
+        taps.dw[t] = (int8_t)(pad - s * dil - woff);
+        taps.btap[t] = (int8_t)t;
+      }
+    return run_gemm(dy, 1, dx, wt, dy->c, kh * kw, dx->c, taps, kh * kw, true, nullptr, nullptr, st);
+  }
+  // stride 2: each output phase of dx is its own dense convolution over dy with a tap subset
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      npp_view4 dv = phase_view(*dx, ph, pw);
+      if (!dv.ptr) continue;
+      TapTable taps;
+      memset(&taps, 0, sizeof taps);
+      int nt = 0;
+      for (int r = 0; r < kh; ++r)
+        for (int s = 0; s < kw; ++s) {
+          const int eh = ph + pad - r * dil - hoff, ew = pw + pad - s * dil - woff;
+          if ((eh & 1) || (ew & 1)) continue;
+          taps.map[nt] = 0;
+          taps.dh[nt] = (int8_t)(eh / 2);   // eh even: exact also for negatives
+          taps.dw[nt] = (int8_t)(ew / 2);
+          taps.btap[nt] = (int8_t)(r * kw + s);
+          ++nt;
+        }
+      if (nt == 0) {
+        rc = fill_zero_view_bf16(&dv, st);
+      } else {
+        rc = run_gemm(dy, 1, &dv, wt, dy->c, kh * kw, dx->c, taps, nt, false, nullptr, nullptr, st);
+      }
+      if (rc) return rc;
+    }
+  return NPP_OK;
+}
+
+template <int BN>
+static int launch_wgrad(const WMaps& maps, const WGeom& g, const TapTable& taps, float* dw, cudaStream_t st) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_wgrad)", e); return NPP_E_CUDA; }
+    attr_set = true;
+  }
+  dim3 grid(g.num_taps * g.co_blocks * g.ci_blocks, g.ksplit);
+  conv_wgrad_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, dw);
+  NPP_CHECK_LAUNCH("conv_wgrad_kernel");
+  return NPP_OK;
+}
+
+int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, int kh, int kw,
+               int stride, int pad, int dil, int hoff, int woff, cudaStream_t st) {
+  int rc = check_conv_args(x, dy, kh, kw, stride, pad, dil);
+  if (rc) return rc;
+  if (!dw || dw_cout <= 0 || dw_cin <= 0 || dw_cout > dy->c || dw_cin > x->c) return NPP_E_INVALID;
+  TapTable taps;
+  memset(&taps, 0, sizeof taps);
+  npp_view4 av[4];
+  memset(av, 0, sizeof av);
+  if (stride == 1) av[0] = *x;
+  int t = 0;
+  for (int r = 0; r < kh; ++r)
+    for (int s = 0; s < kw; ++s, ++t) {
+      const int ah = -pad + r * dil + hoff, aw = -pad + s * dil + woff;
+      if (stride == 1) {
+        taps.map[t] = 0; taps.dh[t] = (int8_t)ah; taps.dw[t] = (int8_t)aw;
+      } else {
+        const int ph = ((ah % 2) + 2) % 2, pw = ((aw % 2) + 2) % 2;
+        taps.map[t] = (int8_t)(ph * 2 + pw);
+        taps.dh[t] = (int8_t)floordiv2(ah - ph);
+        taps.dw[t] = (int8_t)floordiv2(aw - pw);
+        if (!av[ph * 2 + pw].ptr) av[ph * 2 + pw] = phase_view(*x, ph, pw);
+        if (!av[ph * 2 + pw].ptr) return NPP_E_UNSUPPORTED;
+      }
+      taps.btap[t] = (int8_t)t;
+    }
+  const bool flat = stride == 1 && kh * kw == 1 && taps.dh[0] == 0 && taps.dw[0] == 0 && dense_pixels(x) &&
+                    dense_pixels(dy) && x->h == dy->h && x->w == dy->w;
+  PixSpace ps{dy->w, dy->h, dy->n};
+  if (flat) ps = PixSpace{(int64_t)dy->w * dy->h * dy->n, 1, 1};
+  const PixTile pt = choose_tile(ps.W, ps.H, ps.N, 64);
+  WMaps maps;
+  memset(&maps, 0, sizeof maps);
+  for (int i = 0; i < 4; ++i) {
+    const npp_view4& v = av[i];
+    if (!v.ptr) continue;
+    if (flat)
+      rc = encode_act_map(&maps.x[i], v.ptr, v.c, ps.W, 1, 1, v.sw, v.sw * ps.W, v.sw * ps.W, pt.tw, pt.th, pt.tn);
+    else
+      rc = encode_act_map(&maps.x[i], v.ptr, v.c, v.w, v.h, v.n, v.sw, v.sh, v.sn, pt.tw, pt.th, pt.tn);
+    if (rc) return rc;
+  }
+  if (flat)
+    rc = encode_act_map(&maps.dy, dy->ptr, dy->c, ps.W, 1, 1, dy->sw, dy->sw * ps.W, dy->sw * ps.W, pt.tw, pt.th, pt.tn);
+  else
+    rc = encode_act_map(&maps.dy, dy->ptr, dy->c, dy->w, dy->h, dy->n, dy->sw, dy->sh, dy->sn, pt.tw, pt.th, pt.tn);
+  if (rc) return rc;
+  WGeom g;
+  memset(&g, 0, sizeof g);
+  g.num_taps = kh * kw;
+  g.tw = pt.tw; g.th = pt.th; g.tn = pt.tn;
+  g.tiles_w = (int)cdiv64(ps.W, pt.tw);
+  g.tiles_h = (int)cdiv64(ps.H, pt.th);
+  g.tiles_n = (int)cdiv64(ps.N, pt.tn);
+  const int64_t ptiles = (int64_t)g.tiles_w * g.tiles_h * g.tiles_n;
+  if (ptiles > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  g.total_ptiles = (int)ptiles;
+  const int bn = dw_cin <= 64 ? 64 : (dw_cin <= 128 ? 128 : 256);
+  g.co_blocks = (int)cdiv64(dw_cout, 128);
+  g.ci_blocks = (int)cdiv64(dw_cin, bn);
+  g.cout = dw_cout; g.cin = dw_cin; g.dw_ld = dw_cin;
+  const int out_tiles = g.num_taps * g.co_blocks * g.ci_blocks;
+  int ks = sm_count() / out_tiles;
+  if (ks < 1) ks = 1;
+  if (ks > g.total_ptiles / 2) ks = g.total_ptiles / 2;
+  if (ks < 1) ks = 1;
+  g.ksplit = ks;
+  switch (bn) {
+    case 64: return launch_wgrad<64>(maps, g, taps, dw, st);
+    case 128: return launch_wgrad<128>(maps, g, taps, dw, st);
+    default: return launch_wgrad<256>(maps, g, taps, dw, st);
+  }
+}
+
+// fp32 [cout, taps, cin] -> bf16 [cout_pad, taps, cin_pad] and/or transposed bf16 [cin_pad, taps, cout_pad]
+__global__ void pack_weight_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ w,
+                                   __nv_bfloat16* __restrict__ wt, int cout, int taps, int cin, int cout_pad,
+                                   int cin_pad) {
+  const int64_t total = (int64_t)cout_pad * taps * cin_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int t = (int)((i / cin_pad) % taps);
+    const int co = (int)(i / ((int64_t)cin_pad * taps));
+    const float v = (co < cout && ci < cin) ? w32[((int64_t)co * taps + t) * cin + ci] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (w) w[i] = h;
+    if (wt) wt[((int64_t)ci * taps + t) * cout_pad + co] = h;
+  }
+}
+
+int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
+                cudaStream_t st) {
+  if (!w32 || (!w && !wt) || cout <= 0 || taps <= 0 || cin <= 0 || cout_pad < cout || cin_pad < cin)
+    return NPP_E_INVALID;
+  const int64_t total = (int64_t)cout_pad * taps * cin_pad;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 4096) grid = 4096;
+  pack_weight_kernel<<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(wt),
+                                            cout, taps, cin, cout_pad, cin_pad);
+  NPP_CHECK_LAUNCH("pack_weight_kernel");
+  return NPP_OK;
+}
+
+}  // namespace tc
+}  // namespace npp
