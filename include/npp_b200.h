@@ -57,7 +57,7 @@ int npp_sm_count(void);
  * Replaces nn.Conv2d(groups=1) in ReLUConvBN (models/operations.py:69-82), the pointwise
  * half of DilConvS (:214), FactorizedReduce (:149-150), Pooled_Conv (:239), the stems, layer
  * convs and heads of models/model_augment.py:244-398 and extra_conv (:592-596).
- *   w     bf16 [cout, kh, kw, cin]   (OHWI == torch channels_last weight)
+ *   w     bf16 [cout, kh, kw, cin]   (packed OHWI, see npp_pack_weight)
  *   bias  fp32 [cout] or NULL
  *   y[n,ho,wo,co] = bias[co] + sum_{r,s,ci} x[n, ho*stride - pad + r*dil, wo*stride - pad + s*dil, ci] * w[co,r,s,ci]
  * stats (optional, fp32 [2*cout], must be zeroed by the caller): per-channel sum and sum of
@@ -75,18 +75,20 @@ int npp_conv2d_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, i
                      int stride, int pad, int dil, int in_h_off, int in_w_off,
                      npp_stream_t stream);
 
-/* wgrad: dw fp32 [dw_cout, kh, kw, dw_cin] += sum_pixels dy (x) x ; caller zeroes dw first
+/* wgrad: dw fp32 in torch OIHW order [dw_cout, dw_cin, kh, kw] += sum_pixels dy (x) x ; caller zeroes dw first
  * (split-K partial sums are combined with red.global.add.f32).  dw_cout <= dy->c and
  * dw_cin <= x->c are the un-padded channel counts of the fp32 master weight. */
 int npp_conv2d_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin,
                      int kh, int kw, int stride, int pad, int dil, int in_h_off, int in_w_off,
                      npp_stream_t stream);
 
-/* fp32 master weight [cout,taps,cin] -> bf16 [cout_pad,taps,cin_pad] (w) and/or transposed
- * [cin_pad,taps,cout_pad] (wt), zero padded; either output may be NULL.  Activation buffers
- * keep channel counts that are multiples of 8 (16-byte TMA rows), hence the padding. */
+/* fp32 master weight in torch OIHW order [cout,cin,taps] -> packed OHWI [cout_pad,taps,cin_pad]
+ * (w) and/or its transpose [cin_pad,taps,cout_pad] (wt), zero padded, stored as out_dtype
+ * (NPP_BF16 for the tcgen05 path, NPP_F32 for validation mode); either output may be NULL.
+ * Activation buffers keep channel counts that are multiples of 8 (16-byte TMA rows), hence
+ * the padding. */
 int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin,
-                    int cout_pad, int cin_pad, npp_stream_t stream);
+                    int cout_pad, int cin_pad, int out_dtype, npp_stream_t stream);
 
 /* Validation-mode / cross-check convolution on CUDA cores (fp32 accumulate, dtype-templated).
  * Same arithmetic as the three functions above, any dtype, groups==1. w/dw are fp32 OHWI
@@ -118,7 +120,8 @@ int npp_dwconv_bwd(const npp_view4* x, const float* w, const npp_view4* dy, cons
  *  stats:    sums[0:c] += sum x, sums[c:2c] += sum x^2 over all pixels (fp32, caller zeroes).
  *            In SyncBN mode the caller all-reduces `sums` over ranks between stats and finalize.
  *  finalize: mean/var from sums and `count`; writes scale = gamma*invstd, shift = beta-mean*scale,
- *            save_mean, save_invstd; updates running_mean/var (unbiased var, momentum) if non-NULL.
+ *            save_mean, save_invstd; updates running_mean/var[0:c_running] (unbiased var, momentum)
+ *            if non-NULL (c_running < c when the activation carries zero padding channels).
  *  eval_coef: scale/shift from running statistics.
  *  apply:    y = x*scale + shift (+ res) (relu)   — y may be a channel slice of a concat buffer.
  *  bwd_reduce: sums[0:c] += sum dy, sums[c:2c] += sum dy * (x-mean)*invstd
@@ -129,7 +132,7 @@ int npp_bn_stats(const npp_view4* x, float* sums, int dtype, npp_stream_t stream
 int npp_bn_finalize(const float* sums, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps,
                     float* scale, float* shift, float* save_mean, float* save_invstd, int c,
-                    npp_stream_t stream);
+                    int c_running, npp_stream_t stream);
 int npp_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean,
                      const float* running_var, float eps, float* scale, float* shift, int c,
                      npp_stream_t stream);
@@ -187,96 +190,119 @@ int npp_avgpool2x2_bwd(const npp_view4* dy, const npp_view4* dx, int dtype, npp_
 
 /* ------------------------------------------------------------------------------------------
  * SE_Block (operations.py:105-129): w = sigmoid(W2 relu(W1 gap(x) + b1) + b2); out = x*w.
- *  gap_fwd:  g[n,c] = mean_hw x  (fp32 [n,c])
- *  se_fc_fwd: h = relu(W1 g + b1) [n, c/2];  s = sigmoid(W2 h + b2) [n, c]   (fp32 weights [out,in])
- *  se_scale_fwd: y = x * s[n,c]
- *  se_scale_bwd: dx_partial = dy * s ; ds[n,c] = sum_hw dy*x   (fp32)
- *  se_fc_bwd: from ds: dW2, db2, dW1, db1 (+=) and dg[n,c]
- *  gap_bwd_add: dx += dg[n,c]/(h*w)
+ *  gap_fwd:       g[n,c] += mean_hw x           (fp32 [n,c], caller zeroes)
+ *  se_fc_fwd:     h = relu(W1 g + b1) [n,c/2];  s = sigmoid(W2 h + b2) [n,c]  (fp32, W [out,in])
+ *  se_scale_fwd:  y = x * s[n,c]
+ *  se_bwd_reduce: ds[n,c] += sum_hw dy*x        (fp32, caller zeroes)
+ *  se_fc_bwd:     from ds: dW2, db2, dW1, db1 (+=) and dg[n,c]
+ *  se_bwd_apply:  dx = dy * s[n,c] + dg[n,c]/(h*w)
  * ---------------------------------------------------------------------------------------- */
 int npp_gap_fwd(const npp_view4* x, float* g, int dtype, npp_stream_t stream);
 int npp_se_fc_fwd(const float* g, const float* w1, const float* b1, const float* w2,
                   const float* b2, float* hbuf, float* s, int n, int c, npp_stream_t stream);
 int npp_se_scale_fwd(const npp_view4* x, const float* s, const npp_view4* y, int dtype,
                      npp_stream_t stream);
-int npp_se_scale_bwd(const npp_view4* x, const float* s, const npp_view4* dy,
-                     const npp_view4* dx, float* ds, int dtype, npp_stream_t stream);
+int npp_se_bwd_reduce(const npp_view4* x, const npp_view4* dy, float* ds, int dtype,
+                      npp_stream_t stream);
 int npp_se_fc_bwd(const float* g, const float* hbuf, const float* s, const float* ds,
                   const float* w1, const float* w2, float* dw1, float* db1, float* dw2,
                   float* db2, float* dg, int n, int c, npp_stream_t stream);
-int npp_gap_bwd_add(const float* dg, const npp_view4* dx, int dtype, npp_stream_t stream);
+int npp_se_bwd_apply(const npp_view4* dy, const float* s, const float* dg, const npp_view4* dx,
+                     int dtype, npp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Resampling.  bilinear: F.interpolate(mode='bilinear', align_corners=True|False)
- * (model_augment.py:116,539-543; criterion.py:181; function.py:927 uses align_corners=False).
+ * (model_augment.py:116,539-543; operations.py:241; function.py:927 uses align_corners=False).
  * nearest: F.interpolate default mode (model_search_interact.py:63-64).
- * bwd accumulates into dx, which the caller zeroes.
+ * scale_h/scale_w: the scale_factor passed to F.interpolate (0 when the call gave size=); only
+ * used where ATen uses it (align_corners=False and nearest).  Backward is a deterministic gather.
  * ---------------------------------------------------------------------------------------- */
-int npp_bilinear_fwd(const npp_view4* x, const npp_view4* y, int align_corners, int dtype,
-                     npp_stream_t stream);
-int npp_bilinear_bwd(const npp_view4* dy, const npp_view4* dx, int align_corners, int dtype,
-                     npp_stream_t stream);
-int npp_nearest_fwd(const npp_view4* x, const npp_view4* y, int dtype, npp_stream_t stream);
-int npp_nearest_bwd(const npp_view4* dy, const npp_view4* dx, int dtype, npp_stream_t stream);
+int npp_bilinear_fwd(const npp_view4* x, const npp_view4* y, int align_corners, double scale_h,
+                     double scale_w, int dtype, npp_stream_t stream);
+int npp_bilinear_bwd(const npp_view4* dy, const npp_view4* dx, int align_corners, double scale_h,
+                     double scale_w, int dtype, npp_stream_t stream);
+int npp_nearest_fwd(const npp_view4* x, const npp_view4* y, double scale_h, double scale_w,
+                    int dtype, npp_stream_t stream);
+int npp_nearest_bwd(const npp_view4* dy, const npp_view4* dx, double scale_h, double scale_w,
+                    int dtype, npp_stream_t stream);
 
 /* per-channel column sum: out[c] += sum_pixels x  (conv bias gradient) */
 int npp_colsum(const npp_view4* x, float* out, int dtype, npp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Losses (core/criterion.py).  Logits are read at head resolution (NHWC, channel-padded) and
- * bilinearly upsampled (align_corners=True, :181,194) on the fly to the label resolution;
- * the upsampled tensors never touch HBM.
+ * Losses (core/criterion.py) on the reference's boundary tensors: NCHW fp32 logits at head
+ * resolution [n,c,h,w], int64 labels [n,lh,lw].  The bilinear upsample to label resolution
+ * (align_corners=True, criterion.py:181,194) is evaluated on the fly from a shared-memory
+ * tile of head logits; the upsampled [n,c,lh,lw] tensors never exist in HBM.
  *
- * par_loss_pixels: per label pixel p: softmax over classes, prob[p] = p(target) (2.0f for
- *   ignored pixels so they sort last / never pass `< thr`), loss[p] = -w[t]*log p(target).
- *   Also counts valid pixels (count[0], int64).                       (criterion.py:54-64)
- * ohem_select: thr = max(kth smallest prob (k = min(min_kept, n_valid-1)), thres) via a
- *   radix select on the fp32 bit patterns (exactly the element a full sort would pick, :65-67);
- *   out[0] = sum of kept losses, out[1] = number kept (:69-72 mean = out0/out1), out[2] = thr.
- * par_loss_bwd: dlogits (head resolution, fp32 accumulate via atomics then cast by caller)
- *   of  gscale * mean_kept(loss).
- * edge_loss: weighted 2-class CE, weights from pos/neg counts of this batch (:161-166,196).
- * mse_loss: sum over all elements of (pred-gt)^2 (criterion.py:98-128 gives per-joint means;
- *   with equal-sized joints their sum/num_joints == total_sum/(B*J*H*W) * ... see criterion.py).
+ * par_loss_pixels (OhemCrossEntropy.forward :54-64): per label pixel softmax; prob[p] =
+ *   p(target) (2.0f for ignored pixels: never below any threshold), loss[p] = -w[t]*log p(t)
+ *   (0 for ignored); n_valid[0] += number of non-ignored pixels (int64, caller zeroes).
+ * ohem_select (:65-72): thr = max(k-th smallest valid prob, thres), k = min(min_kept, n_valid-1)
+ *   by an 8-bit x 4-pass radix select on the fp32 bit patterns — exactly the element the
+ *   reference's full sort() picks; out3 = {sum of kept losses, number kept, thr}; the loss is
+ *   out3[0]/out3[1] (plain mean over pixels with prob < thr).  workspace: >= 4200 bytes, zeroed.
+ * par_loss_bwd: dlogits[n,c,h,w] += gscale[0]/n_kept * w[t]*(softmax - onehot) pulled back
+ *   through the bilinear upsample (caller zeroes dlogits).
+ * edge_*: weighted 2-class CE (:161-166,196): weights [pos/(pos+neg), neg/(pos+neg)] from the
+ *   batch label counts posneg = {#(t==1), #(t==0)}; out2 = {sum w[t]*nll, sum w[t]};
+ *   loss = out2[0]/out2[1].
+ * mse_*: out[0] += sum (w*(pred-target))^2 over n elements, w = row_w[i / row_len] or 1 when
+ *   row_w is NULL (criterion.py:100-104 target_weight); dpred = gscale[0]*2*w^2*(pred-target).
  * ---------------------------------------------------------------------------------------- */
-int npp_par_loss_pixels(const npp_view4* logits, const int64_t* target, int th, int tw,
-                        int num_classes, const float* class_w, int ignore_index, float* prob,
-                        float* loss, int64_t* count, int dtype, npp_stream_t stream);
-int npp_ohem_select(const float* prob, const float* loss, int64_t npix, const int64_t* count,
+int npp_par_loss_pixels(const float* logits, int n, int c, int h, int w, const int64_t* target,
+                        int lh, int lw, const float* class_w, int ignore_index,
+                        int align_corners, float* prob, float* loss, int64_t* n_valid,
+                        npp_stream_t stream);
+int npp_ohem_select(const float* prob, const float* loss, int64_t npix, const int64_t* n_valid,
                     int min_kept, float thres, float* out3, void* workspace,
-                    int64_t workspace_bytes, npp_stream_t stream);
-int npp_par_loss_bwd(const npp_view4* logits, const int64_t* target, int th, int tw,
-                     int num_classes, const float* class_w, int ignore_index, const float* prob,
-                     const float* out3, const float* gscale, float* dlogits_f32, int dtype,
+                    npp_stream_t stream);
+int npp_par_loss_bwd(const float* logits, int n, int c, int h, int w, const int64_t* target,
+                     int lh, int lw, const float* class_w, int ignore_index, int align_corners,
+                     const float* prob, const float* out3, const float* gscale, float* dlogits,
                      npp_stream_t stream);
 int npp_edge_count(const int64_t* target, int64_t npix, int64_t* posneg, npp_stream_t stream);
-int npp_edge_loss_fwd(const npp_view4* logits, const int64_t* target, int th, int tw,
-                      int ignore_index, const int64_t* posneg, float* out2, int dtype,
+int npp_edge_loss_fwd(const float* logits, int n, int h, int w, const int64_t* target, int lh,
+                      int lw, int ignore_index, int align_corners, const int64_t* posneg,
+                      float* out2, npp_stream_t stream);
+int npp_edge_loss_bwd(const float* logits, int n, int h, int w, const int64_t* target, int lh,
+                      int lw, int ignore_index, int align_corners, const int64_t* posneg,
+                      const float* out2, const float* gscale, float* dlogits,
                       npp_stream_t stream);
-int npp_edge_loss_bwd(const npp_view4* logits, const int64_t* target, int th, int tw,
-                      int ignore_index, const int64_t* posneg, const float* out2,
-                      const float* gscale, float* dlogits_f32, int dtype, npp_stream_t stream);
-int npp_mse_fwd(const npp_view4* pred, const float* target_nchw, int num_joints, float* out,
-                int dtype, npp_stream_t stream);
-int npp_mse_bwd(const npp_view4* pred, const float* target_nchw, int num_joints,
-                const float* gscale, const npp_view4* dpred, int dtype, npp_stream_t stream);
+int npp_mse_fwd(const float* pred, const float* target, int64_t n, const float* row_w,
+                int64_t row_len, float* out, npp_stream_t stream);
+int npp_mse_bwd(const float* pred, const float* target, int64_t n, const float* row_w,
+                int64_t row_len, const float* gscale, float* dpred, npp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Integer evaluation kernels — bit-exact.
  * confusion_hist: utils/utils.py:192-218 get_confusion_matrix: argmax over classes (first
- *   maximum on ties), skip label == ignore, hist[gt*C + pred] += 1 (int64 [C*C], caller zeroes).
- *   logits NCHW fp32 (the reference's layout at that call site, function.py:955).
+ *   maximum on ties, numpy.argmax), skip label == ignore, hist[gt*C + pred] += 1
+ *   (int64 [C*C], caller zeroes).  logits NCHW fp32 [n,c,h,w]; label int64 [n,label_h,label_w]
+ *   cropped to [:h,:w] like the reference (:201-202).
+ * tta_merge: core/function.py:927-939 flip-test merge: bilinear (align_corners=False) resize of
+ *   both predictions to (oh,ow), the reference's aliasing left/right channel "swap" (channels
+ *   14,16,18 of the flipped prediction read 15,17,19; 15,17,19 keep their own), horizontal flip,
+ *   0.5*(a+b).  swap_lr=0 gives the pascal variant (function_ppp.py:923-928).
  * heatmap_argmax: core/evaluate.py:13-41 get_max_preds: per (n,j) first arg-max and max value.
- * pck_counts: core/evaluate.py:43-99: hit[j], valid[j] int64 from pred/gt argmax coordinates.
+ * pck_counts: core/evaluate.py:43-99: per joint hit/valid counters from pred/gt arg-max
+ *   (valid: gt x>=1 or y>=1; hit: ||(p-t)/(h/10, w/10)|| < thr), int64, caller zeroes.
  * ---------------------------------------------------------------------------------------- */
 int npp_confusion_hist(const float* logits_nchw, const int64_t* label, int n, int c, int h,
                        int w, int label_h, int label_w, int ignore, int64_t* hist,
                        npp_stream_t stream);
-int npp_heatmap_argmax(const float* hm_nchw, int n, int j, int h, int w, int32_t* idx,
-                       float* maxval, npp_stream_t stream);
+int npp_tta_merge(const float* pred, const float* flip_pred, int n, int c, int h, int w, int oh,
+                  int ow, int swap_lr, float* out, npp_stream_t stream);
+int npp_heatmap_argmax(const float* hm_nchw, int nj, int h, int w, int32_t* idx, float* maxval,
+                       npp_stream_t stream);
 int npp_pck_counts(const int32_t* pred_idx, const float* pred_max, const int32_t* gt_idx,
                    const float* gt_max, int n, int j, int h, int w, float thr, int64_t* hit,
                    int64_t* valid, npp_stream_t stream);
+/* pckh_counts: utils/calc_pckh.py:35-97 on fp64 image-space coordinates pred/gt [n,p,2]
+ *   (gt < 0 marks a missing joint): per joint valid (head size != 0 and joint present) and hit
+ *   (||gt-pred||/head <= thr) counters; PCKh = 100*hit/valid. */
+int npp_pckh_counts(const double* pred, const double* gt, int n, int p, double thr, int64_t* hit,
+                    int64_t* valid, npp_stream_t stream);
 
 /* MixedOp channel interleave (model_search_interact.py:22-36,70-71 cat + channel_shuffle(2)):
  *   out[..., 2c] = a[..., c], out[..., 2c+1] = b[..., c];  bwd splits. */

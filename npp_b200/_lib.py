@@ -1,0 +1,113 @@
+"""ctypes binding of libnpp_b200.so (the C ABI declared in include/npp_b200.h).
+
+The product path has no fallback: if the shared library is missing or a kernel returns an error
+code, a RuntimeError is raised.  PyTorch is used for device memory (caching allocator), the
+current CUDA stream and torch.distributed only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnpp_b200.so")
+
+NPP_F32 = 0
+NPP_BF16 = 1
+
+_ERRORS = {-1: "NPP_E_INVALID (bad argument / misaligned view)", -2: "NPP_E_UNSUPPORTED (shape or dtype not implemented)",
+           -3: "NPP_E_CUDA", -4: "NPP_E_NODRIVER (cuTensorMapEncodeTiled unavailable)"}
+
+
+class View4(ctypes.Structure):
+    """Mirror of `npp_view4` (include/npp_b200.h)."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("c", ctypes.c_int32), ("sn", ctypes.c_int64), ("sh", ctypes.c_int64), ("sw", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libnpp_b200.so not found at %s — build it with `python -m npp_b200.build` "
+                "(there is no CPU / cuDNN fallback)" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.npp_last_error.restype = ctypes.c_char_p
+        _lib.npp_version.restype = ctypes.c_char_p
+    return _lib
+
+
+def dtype_code(t):
+    if t.dtype == torch.bfloat16:
+        return NPP_BF16
+    if t.dtype == torch.float32:
+        return NPP_F32
+    raise RuntimeError("npp_b200 kernels take bf16 or fp32 activations, got %s" % t.dtype)
+
+
+def view(t):
+    """npp_view4 over a 4-D tensor with logical shape [N, C, H, W] and channel stride 1 (channels_last)."""
+    if t.dim() != 4:
+        raise RuntimeError("expected a 4-D NCHW-shaped tensor, got %s" % (tuple(t.shape),))
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if c > 1 and sc != 1:
+        raise RuntimeError("expected a channels_last tensor (channel stride 1), got strides %s" % (t.stride(),))
+    if h == 1:
+        sh = w * sw
+    if n == 1:
+        sn = h * sh
+    return View4(t.data_ptr(), n, h, w, c, sn, sh, sw)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def fptr(t):
+    """Raw pointer of a dense tensor (or NULL for None)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_contiguous():
+        raise RuntimeError("expected a contiguous tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = _ERRORS.get(rc, "error %d" % rc)
+        detail = lib().npp_last_error().decode() if rc == -3 else ""
+        raise RuntimeError("%s failed: %s %s" % (name, msg, detail))
+
+
+def call(name, *args):
+    fn = getattr(lib(), name)
+    check(fn(*args), name)
+
+
+def i32(v):
+    return ctypes.c_int(int(v))
+
+
+def i64(v):
+    return ctypes.c_int64(int(v))
+
+
+def f32(v):
+    return ctypes.c_float(float(v))
+
+
+def f64(v):
+    return ctypes.c_double(float(v))
+
+
+def ref(v):
+    return ctypes.byref(v)
+
+
+NULL = ctypes.c_void_p(0)

@@ -26,7 +26,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, double count,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd, int C) {
+                                   float* __restrict__ save_invstd, int C, int C_run) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = (double)sums[c] / count;
@@ -40,8 +40,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, double count,
   shift[c] = b - (float)mean * sc;
   if (save_mean) save_mean[c] = (float)mean;
   if (save_invstd) save_invstd[c] = invstd;
-  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-  if (running_var) {
+  if (running_mean && c < C_run) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var && c < C_run) {
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
@@ -176,10 +176,10 @@ int npp_bn_stats(const npp_view4* x, float* sums, int dtype, npp_stream_t s) {
 }
 int npp_bn_finalize(const float* sums, double count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
-                    float* save_invstd, int c, npp_stream_t s) {
-  if (!sums || !scale || !shift || c <= 0 || count <= 0) return NPP_E_INVALID;
+                    float* save_invstd, int c, int c_running, npp_stream_t s) {
+  if (!sums || !scale || !shift || c <= 0 || count <= 0 || c_running > c) return NPP_E_INVALID;
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(s)>>>(sums, count, gamma, beta, running_mean, running_var,
-                                                                momentum, eps, scale, shift, save_mean, save_invstd, c);
+                                                                momentum, eps, scale, shift, save_mean, save_invstd, c, c_running);
   NPP_CHECK_LAUNCH("bn_finalize_kernel");
   return NPP_OK;
 }

@@ -75,10 +75,10 @@ __global__ void direct_wgrad_kernel(const T* __restrict__ x, const T* __restrict
                                     int64_t ysn, int64_t ysh, int64_t ysw, int dw_cout, int dw_cin, int kh, int kw,
                                     int stride, int pad, int dil, int hoff, int woff, int pix_per_chunk) {
   const int64_t total = (int64_t)dw_cout * kh * kw * dw_cin;
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // OIHW index
   if (i >= total) return;
-  const int ci = (int)(i % dw_cin);
-  const int t = (int)((i / dw_cin) % (kh * kw));
+  const int t = (int)(i % (kh * kw));
+  const int ci = (int)((i / (kh * kw)) % dw_cin);
   const int co = (int)(i / ((int64_t)dw_cin * kh * kw));
   const int r = t / kw, s = t % kw;
   const int64_t npix = (int64_t)N * Ho * Wo;
@@ -146,7 +146,7 @@ int conv_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, int kh,
 int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, int kh, int kw, int stride,
                int pad, int dil, int hoff, int woff, cudaStream_t st);
 int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
-                cudaStream_t st);
+                int out_dtype, cudaStream_t st);
 }  // namespace tc
 
 }  // namespace npp
@@ -171,8 +171,8 @@ int npp_conv2d_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_
   return tc::conv_wgrad(x, dy, dw, dw_cout, dw_cin, kh, kw, stride, pad, dil, in_h_off, in_w_off, as_stream(stream));
 }
 int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
-                    npp_stream_t stream) {
-  return tc::pack_weight(w32, w, wt, cout, taps, cin, cout_pad, cin_pad, as_stream(stream));
+                    int out_dtype, npp_stream_t stream) {
+  return tc::pack_weight(w32, w, wt, cout, taps, cin, cout_pad, cin_pad, out_dtype, as_stream(stream));
 }
 
 int npp_conv2d_direct_fwd(const npp_view4* x, const void* w, const float* bias, const npp_view4* y, int kh, int kw,

@@ -10,7 +10,7 @@
 //       bias, rounds to bf16, accumulates BatchNorm batch statistics and TMA-stores the tile.
 //       Persistent CTAs (one per SM), STAGES-deep smem ring, two TMEM accumulator stages so the
 //       epilogue of tile i overlaps the MMAs of tile i+1.
-//   wgrad : dW_tap[Cout, Cin] = sum_pixels dY[pixels, Cout]^T * X_tap[pixels, Cin]
+//   wgrad : dW_tap[Cout, Cin] = sum_pixels dY[pixels, Cout]^T * X_tap[pixels, Cin]   (written in torch OIHW order)
 //       Same boxes, but now the pixel axis is the GEMM K axis, i.e. both operands are MN-major
 //       SWIZZLE_128B tiles (tcgen05 handles the transpose in the descriptor).  Split-K over
 //       pixels; partial sums are combined with red.global.add.f32.
@@ -429,8 +429,7 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
         for (int j = 0; j < 32; ++j) {
           const int ci = ci_blk * BN + c32 * 32 + j;
           if (co < g.cout && ci < g.cin)
-            atomicAdd(dw + (static_cast<int64_t>(co) * g.num_taps + bt) * g.dw_ld + ci,
-                      __uint_as_float(r[j]));
+            atomicAdd(dw + (static_cast<int64_t>(co) * g.cin + ci) * g.num_taps + bt, __uint_as_float(r[j]));
         }
       }
     }
@@ -805,31 +804,39 @@ int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, 
   }
 }
 
-// fp32 [cout, taps, cin] -> bf16 [cout_pad, taps, cin_pad] and/or transposed bf16 [cin_pad, taps, cout_pad]
-__global__ void pack_weight_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ w,
-                                   __nv_bfloat16* __restrict__ wt, int cout, int taps, int cin, int cout_pad,
-                                   int cin_pad) {
+// fp32 master weight in torch's OIHW layout [cout, cin, taps] -> packed OHWI [cout_pad, taps, cin_pad] and/or its
+// transpose [cin_pad, taps, cout_pad] (zero padded), as bf16 (tcgen05 path) or fp32 (validation mode).
+template <typename D>
+__global__ void pack_weight_kernel(const float* __restrict__ w32, D* __restrict__ w, D* __restrict__ wt, int cout,
+                                   int taps, int cin, int cout_pad, int cin_pad) {
   const int64_t total = (int64_t)cout_pad * taps * cin_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin_pad);
     const int t = (int)((i / cin_pad) % taps);
     const int co = (int)(i / ((int64_t)cin_pad * taps));
-    const float v = (co < cout && ci < cin) ? w32[((int64_t)co * taps + t) * cin + ci] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float v = (co < cout && ci < cin) ? w32[((int64_t)co * cin + ci) * taps + t] : 0.f;
+    const D h = from_f<D>(v);
     if (w) w[i] = h;
     if (wt) wt[((int64_t)ci * taps + t) * cout_pad + co] = h;
   }
 }
 
 int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
-                cudaStream_t st) {
+                int out_dtype, cudaStream_t st) {
   if (!w32 || (!w && !wt) || cout <= 0 || taps <= 0 || cin <= 0 || cout_pad < cout || cin_pad < cin)
     return NPP_E_INVALID;
   const int64_t total = (int64_t)cout_pad * taps * cin_pad;
   int grid = (int)((total + 255) / 256);
   if (grid > 4096) grid = 4096;
-  pack_weight_kernel<<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(wt),
-                                            cout, taps, cin, cout_pad, cin_pad);
+  if (out_dtype == NPP_BF16)
+    pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w),
+                                                             static_cast<__nv_bfloat16*>(wt), cout, taps, cin, cout_pad,
+                                                             cin_pad);
+  else if (out_dtype == NPP_F32)
+    pack_weight_kernel<float><<<grid, 256, 0, st>>>(w32, static_cast<float*>(w), static_cast<float*>(wt), cout, taps,
+                                                    cin, cout_pad, cin_pad);
+  else
+    return NPP_E_UNSUPPORTED;
   NPP_CHECK_LAUNCH("pack_weight_kernel");
   return NPP_OK;
 }

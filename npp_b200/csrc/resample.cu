@@ -1,0 +1,149 @@
+// Bilinear / nearest resampling over NHWC views.
+//  bilinear: F.interpolate(mode='bilinear', align_corners=True)  models/model_augment.py:116,539-543,
+//            nn.UpsamplingBilinear2d (operations.py:241), criterion.py:181; align_corners=False for the
+//            flip-TTA merge (core/function.py:927).  Index arithmetic follows ATen's
+//            area_pixel_compute_source_index in fp32 so the sampled taps are identical.
+//  nearest : F.interpolate default mode (model_search_interact.py:63-64, model_augment.py:165-166).
+// Backward is in gather form: each dx element scans the (small) range of outputs that can touch it and
+// re-derives the forward taps, so results are deterministic and need no atomics / fp32 scratch.
+#include "view.cuh"
+#include "resample.cuh"
+
+namespace npp {
+
+template <typename T>
+static int bilinear_fwd_t(const npp_view4* x, const npp_view4* y, Axis ah, Axis aw, cudaStream_t st) {
+  constexpr int V = Pack<T>::N;
+  const auto X = dview<const T>(x);
+  const auto Y = dview<T>(y);
+  return foreach_vec<V>(y->n, y->h, y->w, y->c, st, "bilinear_fwd", [=] __device__(int n, int ho, int wo, int c) {
+    int h0, h1, w0, w1;
+    float lh0, lh1, lw0, lw1;
+    bilinear_taps(ah, ho, h0, h1, lh0, lh1);
+    bilinear_taps(aw, wo, w0, w1, lw0, lw1);
+    float a[V], b[V], cc[V], d[V], o[V];
+    Pack<T>::load(X.at(n, h0, w0, c), a);
+    Pack<T>::load(X.at(n, h0, w1, c), b);
+    Pack<T>::load(X.at(n, h1, w0, c), cc);
+    Pack<T>::load(X.at(n, h1, w1, c), d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] = lh0 * (lw0 * a[i] + lw1 * b[i]) + lh1 * (lw0 * cc[i] + lw1 * d[i]);
+    Pack<T>::store(Y.at(n, ho, wo, c), o);
+  });
+}
+
+template <typename T>
+static int bilinear_bwd_t(const npp_view4* dy, const npp_view4* dx, Axis ah, Axis aw, cudaStream_t st) {
+  constexpr int V = Pack<T>::N;
+  const auto DY = dview<const T>(dy);
+  const auto DX = dview<T>(dx);
+  return foreach_vec<V>(dx->n, dx->h, dx->w, dx->c, st, "bilinear_bwd", [=] __device__(int n, int h, int w, int c) {
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+    int hlo, hhi, wlo, whi;
+    bilinear_range(ah, h, hlo, hhi);
+    bilinear_range(aw, w, wlo, whi);
+    for (int ho = hlo; ho <= hhi; ++ho) {
+      int h0, h1;
+      float lh0, lh1;
+      bilinear_taps(ah, ho, h0, h1, lh0, lh1);
+      const float wh = (h0 == h ? lh0 : 0.f) + (h1 == h ? lh1 : 0.f);
+      if (wh == 0.f) continue;
+      for (int wo = wlo; wo <= whi; ++wo) {
+        int w0, w1;
+        float lw0, lw1;
+        bilinear_taps(aw, wo, w0, w1, lw0, lw1);
+        const float ww = (w0 == w ? lw0 : 0.f) + (w1 == w ? lw1 : 0.f);
+        if (ww == 0.f) continue;
+        float d[V];
+        Pack<T>::load(DY.at(n, ho, wo, c), d);
+        const float f = wh * ww;
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] = fmaf(f, d[i], g[i]);
+      }
+    }
+    Pack<T>::store(DX.at(n, h, w, c), g);
+  });
+}
+
+// nearest: src = min(floor(dst * scale), in-1), scale = 1/scale_factor (ATen nearest_neighbor_compute_source_index)
+__device__ __forceinline__ int nearest_src(const Axis& a, int o) {
+  int s = (int)floorf((float)o * a.scale);
+  return s < a.in - 1 ? s : a.in - 1;
+}
+
+template <typename T>
+static int nearest_fwd_t(const npp_view4* x, const npp_view4* y, Axis ah, Axis aw, cudaStream_t st) {
+  constexpr int V = Pack<T>::N;
+  const auto X = dview<const T>(x);
+  const auto Y = dview<T>(y);
+  return foreach_vec<V>(y->n, y->h, y->w, y->c, st, "nearest_fwd", [=] __device__(int n, int ho, int wo, int c) {
+    *reinterpret_cast<uint4*>(Y.at(n, ho, wo, c)) =
+        *reinterpret_cast<const uint4*>(X.at(n, nearest_src(ah, ho), nearest_src(aw, wo), c));
+  });
+}
+
+template <typename T>
+static int nearest_bwd_t(const npp_view4* dy, const npp_view4* dx, Axis ah, Axis aw, cudaStream_t st) {
+  constexpr int V = Pack<T>::N;
+  const auto DY = dview<const T>(dy);
+  const auto DX = dview<T>(dx);
+  return foreach_vec<V>(dx->n, dx->h, dx->w, dx->c, st, "nearest_bwd", [=] __device__(int n, int h, int w, int c) {
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+    const float ih = ah.scale > 0.f ? 1.f / ah.scale : 0.f, iw = aw.scale > 0.f ? 1.f / aw.scale : 0.f;
+    int hlo = (int)floorf((float)h * ih) - 2, hhi = (int)ceilf((float)(h + 1) * ih) + 2;
+    int wlo = (int)floorf((float)w * iw) - 2, whi = (int)ceilf((float)(w + 1) * iw) + 2;
+    if (hlo < 0) hlo = 0;
+    if (wlo < 0) wlo = 0;
+    if (hhi > ah.out - 1) hhi = ah.out - 1;
+    if (whi > aw.out - 1) whi = aw.out - 1;
+    for (int ho = hlo; ho <= hhi; ++ho) {
+      if (nearest_src(ah, ho) != h) continue;
+      for (int wo = wlo; wo <= whi; ++wo) {
+        if (nearest_src(aw, wo) != w) continue;
+        float d[V];
+        Pack<T>::load(DY.at(n, ho, wo, c), d);
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] += d[i];
+      }
+    }
+    Pack<T>::store(DX.at(n, h, w, c), g);
+  });
+}
+
+}  // namespace npp
+
+using namespace npp;
+
+extern "C" {
+
+/* scale_h/scale_w: the scale_factor given to F.interpolate (0 if the call gave `size=`); only used
+ * when align_corners == 0, mirroring ATen (align_corners=True always uses (in-1)/(out-1)). */
+int npp_bilinear_fwd(const npp_view4* x, const npp_view4* y, int align_corners, double scale_h, double scale_w,
+                     int dtype, npp_stream_t s) {
+  if (!view_ok(x, dtype) || !view_ok(y, dtype) || x->n != y->n || x->c != y->c) return NPP_E_INVALID;
+  const Axis ah = make_axis(x->h, y->h, align_corners, scale_h), aw = make_axis(x->w, y->w, align_corners, scale_w);
+  NPP_DISPATCH_DTYPE(dtype, return bilinear_fwd_t<T>(x, y, ah, aw, as_stream(s)););
+}
+int npp_bilinear_bwd(const npp_view4* dy, const npp_view4* dx, int align_corners, double scale_h, double scale_w,
+                     int dtype, npp_stream_t s) {
+  if (!view_ok(dx, dtype) || !view_ok(dy, dtype) || dx->n != dy->n || dx->c != dy->c) return NPP_E_INVALID;
+  const Axis ah = make_axis(dx->h, dy->h, align_corners, scale_h), aw = make_axis(dx->w, dy->w, align_corners, scale_w);
+  NPP_DISPATCH_DTYPE(dtype, return bilinear_bwd_t<T>(dy, dx, ah, aw, as_stream(s)););
+}
+int npp_nearest_fwd(const npp_view4* x, const npp_view4* y, double scale_h, double scale_w, int dtype, npp_stream_t s) {
+  if (!view_ok(x, dtype) || !view_ok(y, dtype) || x->n != y->n || x->c != y->c) return NPP_E_INVALID;
+  const Axis ah = make_axis(x->h, y->h, 0, scale_h), aw = make_axis(x->w, y->w, 0, scale_w);
+  NPP_DISPATCH_DTYPE(dtype, return nearest_fwd_t<T>(x, y, ah, aw, as_stream(s)););
+}
+int npp_nearest_bwd(const npp_view4* dy, const npp_view4* dx, double scale_h, double scale_w, int dtype,
+                    npp_stream_t s) {
+  if (!view_ok(dx, dtype) || !view_ok(dy, dtype) || dx->n != dy->n || dx->c != dy->c) return NPP_E_INVALID;
+  const Axis ah = make_axis(dx->h, dy->h, 0, scale_h), aw = make_axis(dx->w, dy->w, 0, scale_w);
+  NPP_DISPATCH_DTYPE(dtype, return nearest_bwd_t<T>(dy, dx, ah, aw, as_stream(s)););
+}
+
+}  // extern "C"

@@ -1,0 +1,605 @@
+"""Autograd bindings of the libnpp_b200 kernels.
+
+Internal activation format ("internal tensor"): a torch tensor with logical shape [N, C, H, W],
+channels_last strides (physical NHWC), dtype bf16 (product path) or fp32 (validation mode) and
+C padded to a multiple of 8 with zero channels.  Every Function below launches hand-written
+kernels on torch's current CUDA stream through the C ABI; torch only owns the memory.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from ._lib import call, view, stream, fptr, i32, i64, f32, f64, ref, NULL
+
+_state = {"dtype": torch.bfloat16, "sync_bn": None}
+
+
+def set_compute_dtype(dtype):
+    """torch.bfloat16 (tcgen05 product path) or torch.float32 (fp32 validation mode)."""
+    if dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError("compute dtype must be torch.bfloat16 or torch.float32")
+    _state["dtype"] = dtype
+
+
+def get_compute_dtype():
+    return _state["dtype"]
+
+
+def pad8(c):
+    return (int(c) + 7) // 8 * 8
+
+
+def empty_internal(n, c, h, w, dtype, device):
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def is_internal(t):
+    return (t.dim() == 4 and t.is_cuda and t.dtype in (torch.bfloat16, torch.float32) and t.shape[1] % 8 == 0
+            and t.stride(1) == 1 and t.stride(3) % 8 == 0 and t.stride(2) % 8 == 0 and t.stride(0) % 8 == 0
+            and t.data_ptr() % 16 == 0)
+
+
+def as_internal_grad(g, like):
+    """Gradients normally arrive in internal format from our own kernels; anything else (a grad
+    produced by a torch op in user code) is re-laid-out once."""
+    if g.dtype != like.dtype:
+        g = g.to(like.dtype)
+    if not is_internal(g) or g.stride(3) < g.shape[1]:
+        g = g.contiguous(memory_format=torch.channels_last)
+        if not is_internal(g):  # e.g. C == 1 edge cases cannot occur for padded tensors
+            raise RuntimeError("cannot express gradient as an NHWC view: shape %s strides %s" % (g.shape, g.stride()))
+    return g
+
+
+def pad_vec(p, n, value=0.0):
+    """Pads a 1-D parameter to n entries (autograd-aware); channel padding of internal tensors."""
+    if p is None or p.numel() == n:
+        return p
+    return torch.cat([p, p.new_full((n - p.numel(),), value)])
+
+
+# ------------------------------------------------------------------------------------------------
+# layout conversion at the module edge
+# ------------------------------------------------------------------------------------------------
+class _ToInternal(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        n, c, h, w = x.shape
+        ctx.c = c
+        xs = x.contiguous().float()
+        y = empty_internal(n, pad8(c), h, w, dtype, x.device)
+        call("npp_nchw_to_nhwc", fptr(xs), i32(c), ref(view(y)), i32(L.dtype_code(y)), stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_internal_grad(dy, dy)
+        n, _, h, w = dy.shape
+        dx = torch.empty((n, ctx.c, h, w), dtype=torch.float32, device=dy.device)
+        call("npp_nhwc_to_nchw", ref(view(dy)), fptr(dx), i32(ctx.c), i32(L.dtype_code(dy)), stream())
+        return dx, None
+
+
+class _FromInternal(Function):
+    @staticmethod
+    def forward(ctx, x, c):
+        n, cp, h, w = x.shape
+        ctx.cp, ctx.dtype = cp, x.dtype
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call("npp_nhwc_to_nchw", ref(view(x)), fptr(y), i32(c), i32(L.dtype_code(x)), stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = dy.shape
+        dys = dy.contiguous().float()
+        dx = empty_internal(n, ctx.cp, h, w, ctx.dtype, dy.device)
+        call("npp_nchw_to_nhwc", fptr(dys), i32(c), ref(view(dx)), i32(L.dtype_code(dx)), stream())
+        return dx, None
+
+
+def to_internal(x, dtype=None):
+    """NCHW fp32 (any torch layout) -> internal; internal tensors pass through."""
+    if is_internal(x) and (dtype is None or x.dtype == dtype):
+        return x
+    return _ToInternal.apply(x, dtype or _state["dtype"])
+
+
+def from_internal(x, c=None):
+    """internal -> contiguous NCHW fp32 with the first c channels (drops channel padding)."""
+    return _FromInternal.apply(x, int(c if c is not None else x.shape[1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# ReLU
+# ------------------------------------------------------------------------------------------------
+class _ReluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = empty_internal(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
+        call("npp_relu_fwd", ref(view(x)), ref(view(y)), i32(L.dtype_code(x)), stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = as_internal_grad(dy, y)
+        dx = torch.empty_like(y)
+        call("npp_relu_bwd", ref(view(y)), ref(view(dy)), ref(view(dx)), i32(L.dtype_code(y)), stream())
+        return dx
+
+
+def relu(x):
+    """nn.ReLU; the result is cached on the input tensor so that the several primitives of a cell
+    that read the same state (each starts with its own nn.ReLU, operations.py:76,212) share one pass."""
+    y = getattr(x, "_npp_relu", None)
+    if y is None:
+        y = _ReluFn.apply(x)
+        x._npp_relu = y
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# dense convolution
+# ------------------------------------------------------------------------------------------------
+def conv_out_size(size, k, stride, pad, dil, off=0):
+    return (size - off + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+class _ConvFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, dil, hoff, woff, want_stats):
+        n, cx, h, w = x.shape
+        cout, cin, kh, kw = weight.shape
+        if cx != pad8(cin):
+            raise RuntimeError("conv input has %d channels, weight expects %d (padded %d)" % (cx, cin, pad8(cin)))
+        cop = pad8(cout)
+        ho, wo = conv_out_size(h, kh, stride, pad, dil, hoff), conv_out_size(w, kw, stride, pad, dil, woff)
+        code = L.dtype_code(x)
+        bf16 = code == L.NPP_BF16
+        w32 = weight.detach().contiguous()
+        wp = torch.empty(cop * kh * kw * cx, dtype=x.dtype, device=x.device)
+        need_wt = bf16 and ctx.needs_input_grad[0]
+        wt = torch.empty_like(wp) if need_wt else None
+        call("npp_pack_weight", fptr(w32), fptr(wp), fptr(wt), i32(cout), i32(kh * kw), i32(cin), i32(cop), i32(cx),
+             i32(code), stream())
+        bp = None
+        if bias is not None:
+            bp = pad_vec(bias.detach().float(), cop).contiguous()
+        y = empty_internal(n, cop, ho, wo, x.dtype, x.device)
+        stats = None
+        if bf16:
+            if want_stats:
+                stats = torch.zeros(2 * cop, dtype=torch.float32, device=x.device)
+            call("npp_conv2d_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw), i32(stride),
+                 i32(pad), i32(dil), i32(hoff), i32(woff), fptr(stats), stream())
+        else:
+            call("npp_conv2d_direct_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw),
+                 i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
+        ctx.cfg = (stride, pad, dil, hoff, woff, cout, cin, kh, kw, bias is not None)
+        ctx.save_for_backward(x, wt if bf16 else wp)
+        if stats is None:
+            stats = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x, wmat = ctx.saved_tensors
+        stride, pad, dil, hoff, woff, cout, cin, kh, kw, has_bias = ctx.cfg
+        dy = as_internal_grad(dy, x)
+        code = L.dtype_code(x)
+        bf16 = code == L.NPP_BF16
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if bf16:
+                call("npp_conv2d_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw), i32(stride),
+                     i32(pad), i32(dil), i32(hoff), i32(woff), stream())
+            else:
+                call("npp_conv2d_direct_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw),
+                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+            if bf16:
+                call("npp_conv2d_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
+                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream())
+            else:
+                call("npp_conv2d_direct_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh),
+                     i32(kw), i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            dbp = torch.zeros(dy.shape[1], dtype=torch.float32, device=x.device)
+            call("npp_colsum", ref(view(dy)), fptr(dbp), i32(code), stream())
+            db = dbp[:cout]
+        return dx, dw, db, None, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_stats=False):
+    """Dense conv on an internal tensor.  Returns (y, stats) where stats is the fused per-channel
+    (sum, sum of squares) of y from the tcgen05 epilogue (empty when not requested / fp32 mode)."""
+    return _ConvFn.apply(x, weight, bias, int(stride), int(pad), int(dil), int(hoff), int(woff), bool(want_stats))
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise convolution (+ fused leading ReLU)
+# ------------------------------------------------------------------------------------------------
+class _DwConvFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad, dil, relu_in):
+        n, c, h, w = x.shape
+        k = weight.shape[-1]
+        if weight.shape[0] != c or weight.shape[1] != 1:
+            raise RuntimeError("depthwise weight %s does not match %d channels" % (tuple(weight.shape), c))
+        ho, wo = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
+        y = empty_internal(n, c, ho, wo, x.dtype, x.device)
+        w32 = weight.detach().contiguous()
+        call("npp_dwconv_fwd", ref(view(x)), fptr(w32), ref(view(y)), i32(k), i32(stride), i32(pad), i32(dil),
+             i32(relu_in), i32(L.dtype_code(x)), stream())
+        ctx.cfg = (k, stride, pad, dil, relu_in)
+        ctx.save_for_backward(x, w32)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w32 = ctx.saved_tensors
+        k, stride, pad, dil, relu_in = ctx.cfg
+        dy = as_internal_grad(dy, x)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w32) if ctx.needs_input_grad[1] else None
+        call("npp_dwconv_bwd", ref(view(x)), fptr(w32), ref(view(dy)), ref(view(dx)) if dx is not None else NULL,
+             fptr(dw), i32(k), i32(stride), i32(pad), i32(dil), i32(relu_in), i32(L.dtype_code(x)), stream())
+        return dx, dw, None, None, None, None
+
+
+def dwconv2d(x, weight, stride, pad, dil, relu_in):
+    return _DwConvFn.apply(x, weight, int(stride), int(pad), int(dil), int(bool(relu_in)))
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm (training: batch statistics, optionally all-reduced across ranks = SyncBN)
+# ------------------------------------------------------------------------------------------------
+def _sync_group():
+    g = _state["sync_bn"]
+    if g is None:
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(g if g is not True else None) == 1:
+        return None
+    return g
+
+
+def _allreduce_sum(t):
+    import torch.distributed as dist
+    g = _state["sync_bn"]
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if g is True else g)
+    return dist.get_world_size(None if g is True else g)
+
+
+class _BNTrainFn(Function):
+    @staticmethod
+    def forward(ctx, x, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual):
+        n, c, h, w = x.shape
+        code = L.dtype_code(x)
+        dev = x.device
+        if stats is None or stats.numel() == 0:
+            stats = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+            call("npp_bn_stats", ref(view(x)), fptr(stats), i32(code), stream())
+        count = float(n * h * w)
+        sync = _sync_group() is not None
+        if sync:
+            count *= _allreduce_sum(stats)
+        coef = torch.empty(4 * c, dtype=torch.float32, device=dev)  # scale | shift | mean | invstd
+        scale, shift, mean, invstd = coef[:c], coef[c:2 * c], coef[2 * c:3 * c], coef[3 * c:]
+        c_run = running_mean.numel() if running_mean is not None else 0
+        call("npp_bn_finalize", fptr(stats), f64(count), fptr(gamma), fptr(beta), fptr(running_mean),
+             fptr(running_var), f32(momentum), f32(eps), fptr(scale), fptr(shift), fptr(mean), fptr(invstd), i32(c),
+             i32(c_run), stream())
+        y = empty_internal(n, c, h, w, x.dtype, dev)
+        call("npp_bn_apply", ref(view(x)), fptr(scale), fptr(shift), ref(view(residual)) if residual is not None else NULL,
+             i32(relu), ref(view(y)), i32(code), stream())
+        ctx.relu, ctx.count, ctx.sync, ctx.has_res = relu, count, sync, residual is not None
+        ctx.save_for_backward(x, gamma, mean, invstd, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, invstd, y = ctx.saved_tensors
+        dy = as_internal_grad(dy, x)
+        c = x.shape[1]
+        code = L.dtype_code(x)
+        sums = torch.zeros(2 * c, dtype=torch.float32, device=x.device)
+        ymask = ref(view(y)) if ctx.relu else NULL
+        call("npp_bn_bwd_reduce", ref(view(dy)), ref(view(x)), ymask, fptr(mean), fptr(invstd), fptr(sums), i32(code),
+             stream())
+        dbeta, dgamma = sums[:c], sums[c:]
+        if ctx.sync:
+            dbeta, dgamma = dbeta.clone(), dgamma.clone()  # parameter grads stay local (DDP averages them)
+            _allreduce_sum(sums)
+        dx = torch.empty_like(x)
+        call("npp_bn_bwd_apply", ref(view(dy)), ref(view(x)), ymask, fptr(gamma), fptr(mean), fptr(invstd), fptr(sums),
+             f64(ctx.count), ref(view(dx)), i32(code), stream())
+        dres = None
+        if ctx.has_res:
+            if ctx.relu:
+                raise RuntimeError("residual + relu fusion has no backward")
+            dres = dy
+        return (dx, None, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
+                None, None, None, None, None, dres)
+
+
+class _AffineFn(Function):
+    """y = x*scale[c] + shift[c] (+relu): eval-mode BatchNorm with running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, relu):
+        y = empty_internal(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
+        call("npp_bn_apply", ref(view(x)), fptr(scale), fptr(shift), NULL, i32(relu), ref(view(y)),
+             i32(L.dtype_code(x)), stream())
+        if x.requires_grad:
+            raise RuntimeError("eval-mode BatchNorm backward is not implemented; run under torch.no_grad()")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        raise RuntimeError("eval-mode BatchNorm backward is not implemented")
+
+
+def batch_norm(x, stats, gamma, beta, running_mean, running_var, training, momentum, eps, relu=False, residual=None):
+    c = x.shape[1]
+    gp = pad_vec(gamma, c, 1.0)
+    bp = pad_vec(beta, c, 0.0)
+    if training:
+        return _BNTrainFn.apply(x, stats, gp, bp, running_mean, running_var, float(momentum), float(eps), int(relu),
+                                residual)
+    coef = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    rm = pad_vec(running_mean, c, 0.0).contiguous()
+    rv = pad_vec(running_var, c, 1.0).contiguous()
+    call("npp_bn_eval_coef", fptr(gp.detach().contiguous() if gp is not None else None),
+         fptr(bp.detach().contiguous() if bp is not None else None), fptr(rm), fptr(rv), f32(eps), fptr(coef[:c]),
+         fptr(coef[c:]), i32(c), stream())
+    y = _AffineFn.apply(x, coef[:c], coef[c:], int(relu))
+    if residual is not None:
+        y = add(y, residual)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# add / concat
+# ------------------------------------------------------------------------------------------------
+class _AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        y = empty_internal(a.shape[0], a.shape[1], a.shape[2], a.shape[3], a.dtype, a.device)
+        call("npp_add", ref(view(a)), ref(view(b)), ref(view(y)), i32(L.dtype_code(a)), stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    if a.shape != b.shape:
+        raise RuntimeError("add: shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+    return _AddFn.apply(a, b)
+
+
+class _CatFn(Function):
+    @staticmethod
+    def forward(ctx, *ts):
+        n, _, h, w = ts[0].shape
+        cs = [t.shape[1] for t in ts]
+        y = empty_internal(n, sum(cs), h, w, ts[0].dtype, ts[0].device)
+        off = 0
+        code = L.dtype_code(y)
+        for t, c in zip(ts, cs):
+            call("npp_add", ref(view(t)), NULL, ref(view(y[:, off:off + c])), i32(code), stream())
+            off += c
+        ctx.cs = cs
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        outs, off = [], 0
+        for c in ctx.cs:
+            outs.append(dy[:, off:off + c])
+            off += c
+        return tuple(outs)
+
+
+def cat(ts):
+    """torch.cat(dim=1) of internal tensors (model_augment.py:62); backward hands out channel slices."""
+    ts = list(ts)
+    if len(ts) == 1:
+        return ts[0]
+    return _CatFn.apply(*ts)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling
+# ------------------------------------------------------------------------------------------------
+class _MaxPool3Fn(Function):
+    @staticmethod
+    def forward(ctx, x, stride):
+        n, c, h, w = x.shape
+        ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        y = empty_internal(n, c, ho, wo, x.dtype, x.device)
+        call("npp_maxpool3x3_fwd", ref(view(x)), ref(view(y)), i32(stride), i32(L.dtype_code(x)), stream())
+        ctx.stride = stride
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = as_internal_grad(dy, x)
+        dx = torch.empty_like(x)
+        call("npp_maxpool3x3_bwd", ref(view(x)), ref(view(dy)), ref(view(dx)), i32(ctx.stride), i32(L.dtype_code(x)),
+             stream())
+        return dx, None
+
+
+class _AvgPool3Fn(Function):
+    @staticmethod
+    def forward(ctx, x, stride):
+        n, c, h, w = x.shape
+        ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        y = empty_internal(n, c, ho, wo, x.dtype, x.device)
+        call("npp_avgpool3x3_fwd", ref(view(x)), ref(view(y)), i32(stride), i32(L.dtype_code(x)), stream())
+        ctx.stride, ctx.shape = stride, x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_internal_grad(dy, dy)
+        n, c, h, w = ctx.shape
+        dx = empty_internal(n, c, h, w, dy.dtype, dy.device)
+        call("npp_avgpool3x3_bwd", ref(view(dy)), ref(view(dx)), i32(ctx.stride), i32(L.dtype_code(dy)), stream())
+        return dx, None
+
+
+class _AvgPool2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, c, h, w = x.shape
+        y = empty_internal(n, c, h // 2, w // 2, x.dtype, x.device)
+        call("npp_avgpool2x2_fwd", ref(view(x)), ref(view(y)), i32(L.dtype_code(x)), stream())
+        ctx.shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_internal_grad(dy, dy)
+        n, c, h, w = ctx.shape
+        dx = empty_internal(n, c, h, w, dy.dtype, dy.device)
+        call("npp_avgpool2x2_bwd", ref(view(dy)), ref(view(dx)), i32(L.dtype_code(dy)), stream())
+        return dx
+
+
+def max_pool3x3(x, stride):
+    return _MaxPool3Fn.apply(x, int(stride))
+
+
+def avg_pool3x3(x, stride):
+    return _AvgPool3Fn.apply(x, int(stride))
+
+
+def avg_pool2x2(x):
+    return _AvgPool2Fn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# SE block
+# ------------------------------------------------------------------------------------------------
+class _SEFn(Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        n, c, h, w = x.shape
+        dev, code = x.device, L.dtype_code(x)
+        g = torch.zeros((n, c), dtype=torch.float32, device=dev)
+        call("npp_gap_fwd", ref(view(x)), fptr(g), i32(code), stream())
+        w1c, w2c = w1.detach().reshape(c // 2, c).contiguous(), w2.detach().reshape(c, c // 2).contiguous()
+        b1c = b1.detach().contiguous() if b1 is not None else None
+        b2c = b2.detach().contiguous() if b2 is not None else None
+        hbuf = torch.empty((n, c // 2), dtype=torch.float32, device=dev)
+        s = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("npp_se_fc_fwd", fptr(g), fptr(w1c), fptr(b1c), fptr(w2c), fptr(b2c), fptr(hbuf), fptr(s), i32(n), i32(c),
+             stream())
+        y = empty_internal(n, c, h, w, x.dtype, dev)
+        call("npp_se_scale_fwd", ref(view(x)), fptr(s), ref(view(y)), i32(code), stream())
+        ctx.save_for_backward(x, g, hbuf, s, w1c, w2c)
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        ctx.wshapes = (w1.shape, w2.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, hbuf, s, w1c, w2c = ctx.saved_tensors
+        dy = as_internal_grad(dy, x)
+        n, c, h, w = x.shape
+        dev, code = x.device, L.dtype_code(x)
+        ds = torch.zeros((n, c), dtype=torch.float32, device=dev)
+        call("npp_se_bwd_reduce", ref(view(x)), ref(view(dy)), fptr(ds), i32(code), stream())
+        dw1, dw2 = torch.zeros_like(w1c), torch.zeros_like(w2c)
+        db1 = torch.zeros(c // 2, dtype=torch.float32, device=dev)
+        db2 = torch.zeros(c, dtype=torch.float32, device=dev)
+        dg = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("npp_se_fc_bwd", fptr(g), fptr(hbuf), fptr(s), fptr(ds), fptr(w1c), fptr(w2c), fptr(dw1), fptr(db1),
+             fptr(dw2), fptr(db2), fptr(dg), i32(n), i32(c), stream())
+        dx = torch.empty_like(x)
+        call("npp_se_bwd_apply", ref(view(dy)), fptr(s), fptr(dg), ref(view(dx)), i32(code), stream())
+        return (dx, dw1.reshape(ctx.wshapes[0]), db1 if ctx.has_bias[0] else None, dw2.reshape(ctx.wshapes[1]),
+                db2 if ctx.has_bias[1] else None)
+
+
+def se_scale(x, w1, b1, w2, b2):
+    return _SEFn.apply(x, w1, b1, w2, b2)
+
+
+# ------------------------------------------------------------------------------------------------
+# resampling
+# ------------------------------------------------------------------------------------------------
+class _ResampleFn(Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow, mode, align, sh, sw):
+        n, c, h, w = x.shape
+        y = empty_internal(n, c, oh, ow, x.dtype, x.device)
+        code = L.dtype_code(x)
+        if mode == "bilinear":
+            call("npp_bilinear_fwd", ref(view(x)), ref(view(y)), i32(align), f64(sh), f64(sw), i32(code), stream())
+        else:
+            call("npp_nearest_fwd", ref(view(x)), ref(view(y)), f64(sh), f64(sw), i32(code), stream())
+        ctx.cfg = (x.shape, mode, align, sh, sw)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, mode, align, sh, sw = ctx.cfg
+        dy = as_internal_grad(dy, dy)
+        n, c, h, w = shape
+        dx = empty_internal(n, c, h, w, dy.dtype, dy.device)
+        code = L.dtype_code(dy)
+        if mode == "bilinear":
+            call("npp_bilinear_bwd", ref(view(dy)), ref(view(dx)), i32(align), f64(sh), f64(sw), i32(code), stream())
+        else:
+            call("npp_nearest_bwd", ref(view(dy)), ref(view(dx)), f64(sh), f64(sw), i32(code), stream())
+        return dx, None, None, None, None, None, None
+
+
+def interpolate(x, scale_factor=None, size=None, mode="nearest", align_corners=None):
+    """F.interpolate for internal tensors (bilinear / nearest), output size floor(in*scale) as ATen."""
+    import math
+    n, c, h, w = x.shape
+    if size is not None:
+        oh, ow = (size, size) if isinstance(size, int) else size
+        sh = sw = 0.0
+    else:
+        sf = scale_factor if isinstance(scale_factor, (tuple, list)) else (scale_factor, scale_factor)
+        sh, sw = float(sf[0]), float(sf[1])
+        oh, ow = int(math.floor(h * sh)), int(math.floor(w * sw))
+    if mode not in ("bilinear", "nearest"):
+        raise RuntimeError("interpolate mode %r is not implemented" % mode)
+    return _ResampleFn.apply(x, int(oh), int(ow), mode, int(bool(align_corners)), sh, sw)
+
+
+# ------------------------------------------------------------------------------------------------
+# Zero primitive
+# ------------------------------------------------------------------------------------------------
+class _ZeroFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = empty_internal(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.dtype, x.device)
+        call("npp_fill_zero", ref(view(y)), i32(L.dtype_code(y)), stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = torch.empty_like(dy)
+        call("npp_fill_zero", ref(view(dx)), i32(L.dtype_code(dx)), stream())
+        return dx
+
+
+def zeros_like_internal(x):
+    """`x * 0.` of the Zero primitive (operations.py:31-41): zero output, zero gradient."""
+    return _ZeroFn.apply(x)

@@ -1,0 +1,415 @@
+"""Derived NPPNet (joint human parsing + pose) on libnpp_b200 kernels.
+
+Drop-in for the reference's models/model_augment.py: `Network(cfg)` takes the same config fields
+(model_augment.py:236-242), builds the same module tree in the same order (identical state_dict
+keys and identical xavier initialisation under a given torch seed) and `forward(x)` returns the
+same `(pose_list, par_list)` structure of NCHW fp32 tensors (model_augment.py:402-574).  Internally
+activations are NHWC bf16 (or fp32 in validation mode) and every op is one of our kernels.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import functional as F_
+from ..nn import BatchNorm2d, Conv2d, ReLU, Sequential
+from . import genotypes as gt
+from .operations import OPS, FactorizedReduce, ReLUConvBN
+
+BN_MOMENTUM = 0.1
+
+
+class Interpolate(nn.Module):
+    """F.interpolate(scale_factor, 'bilinear', align_corners=True) — model_augment.py:109-116."""
+
+    def __init__(self, scale_factor, mode="bilinear"):
+        super().__init__()
+        self.s = scale_factor
+        self.mode = mode
+
+    def forward(self, x):
+        return F_.interpolate(F_.to_internal(x), scale_factor=self.s, mode=self.mode, align_corners=True)
+
+
+class _RescaleProject(Sequential):
+    """`nn.Sequential(Interpolate(s), nn.Conv2d(C_in, C_out, 1))` of model_augment.py:592-596 / 642-646.
+    Bilinear weights sum to one, so the 1x1 convolution (with bias) commutes with the resampling;
+    when upsampling we project first and resample the narrower/smaller tensor.
+    Child indices (0: Interpolate, 1: Conv2d) match the reference for state_dict parity."""
+
+    def forward(self, x):
+        resample, proj = self[0], self[1]
+        if resample.s > 1:
+            return resample(proj(x))
+        return proj(resample(x))
+
+
+def _edge_lists(edges):
+    names, idx = zip(*edges)
+    return list(names), list(idx)
+
+
+class _StepCell(nn.Module):
+    """Shared evaluation of a DARTS-style cell: every step adds the outputs of two primitives applied to
+    earlier states (model_augment.py:48-62, 90-106, 153-174, 210-229)."""
+
+    def _build_ops(self, C, edges, wrap=None):
+        names, self._indices = _edge_lists(edges)
+        assert len(names) % 2 == 0
+        self._steps = len(names) // 2
+        self._ops = nn.ModuleList()
+        for k, (name, index) in enumerate(zip(names, self._indices)):
+            stride = self._stride_for(index)
+            op = OPS[name](C, stride, True)
+            if wrap is not None:
+                op = wrap(op, index)
+            self._ops.append(op)
+
+    def _stride_for(self, index):
+        return 1
+
+    def _run_steps(self, states):
+        for i in range(self._steps):
+            a = self._ops[2 * i](states[self._indices[2 * i]])
+            b = self._ops[2 * i + 1](states[self._indices[2 * i + 1]])
+            states.append(F_.add(a, b))
+        return states
+
+
+class Cell(_StepCell):
+    """Encoder cell — model_augment.py:16-62."""
+
+    def __init__(self, genotype, C_prev_prev, C_prev, C, reduction, reduction_prev):
+        super().__init__()
+        if reduction_prev:
+            self.preprocess0 = FactorizedReduce(C_prev_prev, C)
+        else:
+            self.preprocess0 = ReLUConvBN(C_prev_prev, C, 1, 1, 0, affine=True)
+        self.preprocess1 = ReLUConvBN(C_prev, C, 1, 1, 0, affine=True)
+        self._reduction = reduction
+        if reduction:
+            edges, concat = genotype.reduce, genotype.reduce_concat
+        else:
+            edges, concat = genotype.normal, genotype.normal_concat
+        self._concat = concat
+        self.multiplier = len(concat)
+        self._build_ops(C, edges)
+
+    def _stride_for(self, index):
+        return 2 if self._reduction and index < 2 else 1
+
+    def forward(self, s0, s1):
+        states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1)])
+        return F_.cat([states[i] for i in self._concat])
+
+
+class Upsample(_StepCell):
+    """Decoder cell: primitives reading state 0 (the coarser input) are followed by a x2 bilinear
+    upsample — model_augment.py:64-106."""
+
+    def __init__(self, upsample, upsample_concat, C_prev_prev, C_prev):
+        super().__init__()
+        self.preprocess0 = ReLUConvBN(C_prev_prev, C_prev // 4, 1, 1, 0, affine=True)
+        self.preprocess1 = ReLUConvBN(C_prev, C_prev // 4, 1, 1, 0, affine=True)
+        self._concat = upsample_concat
+        self.multiplier = len(upsample_concat)
+        self._build_ops(C_prev // 4, upsample,
+                        wrap=lambda op, index: Sequential(op, Interpolate(scale_factor=2)) if index == 0 else op)
+
+    def forward(self, s0, s1):
+        states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1)])
+        return F_.cat([states[i] for i in self._concat])
+
+
+class _FusionCell(_StepCell):
+    """PoseCell1 / ParCell1 — model_augment.py:119-229: three preprocessed inputs, four steps, returns
+    (cat(states[0:3]), cat(states[concat]))."""
+
+    def __init__(self, edges, concat, C_prev_prev, C_prev, C_cur, order):
+        super().__init__()
+        self.order = order
+        if order == 0:
+            cins = (C_prev_prev, C_prev, C_cur)
+        else:
+            cins = (3 * C_cur, 4 * C_cur, 4 * C_cur)
+        self.preprocess0 = ReLUConvBN(cins[0], C_cur, 1, 1, 0, affine=True)
+        self.preprocess1 = ReLUConvBN(cins[1], C_cur, 1, 1, 0, affine=True)
+        self.preprocess2 = ReLUConvBN(cins[2], C_cur, 1, 1, 0, affine=True)
+        self._concat = concat
+        self.multiplier = len(concat)
+
+        def wrap(op, index):
+            if order == 0 and index == 0:
+                return Sequential(op, Interpolate(scale_factor=4))
+            if order == 0 and index == 1:
+                return Sequential(op, Interpolate(scale_factor=2))
+            return op
+
+        self._build_ops(C_cur, edges, wrap=wrap)
+
+    def forward(self, s0, s1, s2):
+        states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1), self.preprocess2(s2)])
+        if self.order == 0:  # model_augment.py:164-166: default-mode (nearest) F.interpolate
+            states[0] = F_.interpolate(states[0], scale_factor=4)
+            states[1] = F_.interpolate(states[1], scale_factor=2)
+        return F_.cat(states[0:3]), F_.cat([states[i] for i in self._concat])
+
+
+class PoseCell1(_FusionCell):
+    def __init__(self, pose, pose_concat, C_prev_prev, C_prev, C_cur, order):
+        super().__init__(pose, pose_concat, C_prev_prev, C_prev, C_cur, order)
+
+
+class ParCell1(_FusionCell):
+    def __init__(self, par, par_concat, C_prev_prev, C_prev, C_cur, order):
+        super().__init__(par, par_concat, C_prev_prev, C_prev, C_cur, order)
+
+
+def _stem(cin, cout, stride, relu):
+    layers = [Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False), BatchNorm2d(cout, momentum=BN_MOMENTUM)]
+    if relu:
+        layers.append(ReLU(inplace=True))
+    return Sequential(*layers)
+
+
+def _layer_1x1(cin, cout):
+    """ReLU -> Conv1x1(bias) -> BN — model_augment.py:332-351."""
+    return Sequential(ReLU(), Conv2d(cin, cout, kernel_size=1, padding=0, dilation=1),
+                      BatchNorm2d(cout, momentum=BN_MOMENTUM))
+
+
+def _head(cin, mid, cout, k, first_bias=True):
+    """ReLU -> Conv(k) -> BN -> ReLU -> Conv1x1(bias) — model_augment.py:371-398."""
+    return Sequential(ReLU(), Conv2d(cin, mid, kernel_size=k, padding=k // 2, dilation=1, bias=first_bias),
+                      BatchNorm2d(mid, momentum=BN_MOMENTUM), ReLU(inplace=True),
+                      Conv2d(mid, cout, kernel_size=1, padding=0, dilation=1, bias=True))
+
+
+class Network(nn.Module):
+    """model_augment.py:231-709."""
+
+    def __init__(self, cfg, steps=4, multiplier=4, stem_multiplier=4):
+        super().__init__()
+        self._num_classes = cfg.DATASET.NUM_CLASSES
+        self._num_joints = cfg.DATASET.NUM_JOINTS
+        self._layers = cfg.TRAIN.LAYERS
+        self.C = cfg.TRAIN.INIT_CHANNELS
+        self.deconv_with_bias = cfg.MODEL.DECONV_WITH_BIAS
+        self._head = cfg.MODEL.HEAD
+        self.refine_layers = cfg.MODEL.REFINE_LAYERS
+        C, L = self.C, self._layers
+
+        # two independent stems, one per task stream (model_augment.py:244-272)
+        self.stem0 = _stem(3, C, 2, True)
+        self.stem1 = _stem(C, 2 * C, 2, True)
+        self.stem2 = _stem(2 * C, 2 * C, 1, False)
+        self.stem3 = _stem(3, C, 2, True)
+        self.stem4 = _stem(C, 2 * C, 2, True)
+        self.stem5 = _stem(2 * C, 2 * C, 1, False)
+
+        # encoder: L cells per stream, channel doubling + reduction at L/4, L/2, 3L/4 (:274-295)
+        self._tap_layers = [L // 4 - 1, 2 * L // 4 - 1, 3 * L // 4 - 1, 4 * L // 4 - 1]
+        reduce_layers = [L // 4, 2 * L // 4, 3 * L // 4]
+        C_pp, C_p, C_cur = 2 * C, 2 * C, int(C / 2)
+        self.cells1 = nn.ModuleList()
+        self.cells2 = nn.ModuleList()
+        widths = []
+        reduction_prev = False
+        for i in range(L):
+            if i in self._tap_layers:
+                widths.append(int(C_cur * multiplier))
+            reduction = i in reduce_layers
+            if reduction:
+                C_cur *= 2
+            self.cells1.append(Cell(gt.ENCODER, C_pp, C_p, C_cur, reduction, reduction_prev))
+            self.cells2.append(Cell(gt.ENCODER, C_pp, C_p, C_cur, reduction, reduction_prev))
+            reduction_prev = reduction
+            C_pp, C_p = C_p, multiplier * C_cur
+        self.num_inchannels = widths[::-1]  # coarse -> fine, as in the reference (:297)
+
+        # cross-task interaction ops in the encoder (:299-306) and decoder (:308-317)
+        self._indices1, ops = self._compile(gt.INTER.task1, widths)
+        self._ops1 = nn.ModuleList(ops)
+        self._indices2, ops = self._compile(gt.INTER.task2, widths)
+        self._ops2 = nn.ModuleList(ops)
+        resolution = [1, 1 / 2, 1 / 4, 1 / 8, 1 / 4, 1 / 2, 1]
+        channels = [int(2 * C / r) for r in resolution]
+        self.up_indices1, ops = self._compile3(gt.INTER.task3, resolution, channels)
+        self.up_ops1 = nn.ModuleList(ops)
+        self.up_indices2, ops = self._compile3(gt.INTER.task4, resolution, channels)
+        self.up_ops2 = nn.ModuleList(ops)
+
+        # decoder (:319-330)
+        nin = self.num_inchannels
+        self.upsamples1 = nn.ModuleList()
+        self.upsamples2 = nn.ModuleList()
+        for j in range(len(nin) - 1):
+            self.upsamples1.append(Upsample(gt.DECODER.upsample1, gt.DECODER.upsample_concat1, nin[j], nin[j + 1]))
+        for j in range(len(nin) - 1):
+            self.upsamples2.append(Upsample(gt.DECODER.upsample2, gt.DECODER.upsample_concat2, nin[j], nin[j + 1]))
+
+        # 1x1 projections of the 8*C3-channel multi-scale concat (:332-351)
+        C3 = nin[3]
+        self.pose_layer = _layer_1x1(8 * C3, 4 * C3)
+        self.pose_auxlayer = _layer_1x1(8 * C3, 3 * C3)
+        self.par_layer = _layer_1x1(8 * C3, 4 * C3)
+        self.edge_layer = _layer_1x1(8 * C3, 3 * C3)
+
+        # refinement cells (:354-364)
+        self.pose_net = nn.ModuleList()
+        self.par_net = nn.ModuleList()
+        for _ in range(3):
+            self.pose_net.append(PoseCell1(gt.FUSION.pose, gt.FUSION.pose_concat, C3, C3, C3, 1))
+            self.par_net.append(ParCell1(gt.FUSION.par, gt.FUSION.par_concat, C3, C3, C3, 1))
+
+        # heads, one set per refinement stage (:366-398)
+        self.pose_head = nn.ModuleList()
+        self.pose_auxnet = nn.ModuleList()
+        self.par_head = nn.ModuleList()
+        self.edge_head = nn.ModuleList()
+        for _ in range(self.refine_layers + 1):
+            self.pose_head.append(_head(4 * C3, 256, self._num_joints, 1))
+            self.pose_auxnet.append(_head(3 * C3, 128, self._num_joints, 3))
+            self.par_head.append(_head(4 * C3, 256, self._num_classes, 1))
+            self.edge_head.append(_head(3 * C3, 6, 2, 3, first_bias=False))
+
+        self._init_params()
+
+    # ------------------------------------------------------------------ construction helpers
+    @staticmethod
+    def _interaction_op(name, c_src, c_dst, scale, same):
+        op = OPS[name](c_src, 1, True)
+        if not same:
+            op = Sequential(op, _RescaleProject(Interpolate(scale), Conv2d(c_src, c_dst, 1)))
+        return op
+
+    def _compile(self, geno, C_list):
+        """Encoder interaction ops: target scale `cont`, source scale `ind` (:576-598)."""
+        indices, ops = [], []
+        for cont, edges in enumerate(geno):
+            names, idx = zip(*edges)
+            indices.append(idx)
+            for n, ind in zip(names, idx):
+                ops.append(self._interaction_op(n, C_list[ind], C_list[cont], 1 / 2 ** (cont - ind), ind == cont))
+        return indices, ops
+
+    def _compile3(self, geno, resolutions, C_list):
+        """Decoder interaction ops over the 7-entry feature list (:626-649)."""
+        indices, ops = [], []
+        for cont, edges in enumerate(geno):
+            names, idx = zip(*edges)
+            indices.append(idx)
+            for n, ind in zip(names, idx):
+                ops.append(self._interaction_op(n, C_list[ind], C_list[4 + cont],
+                                                resolutions[4 + cont] / resolutions[ind], ind == 4 + cont))
+        return indices, ops
+
+    def _init_params(self):
+        """xavier_normal on every conv weight, zero conv bias, BN weight 1 / bias 0 (:651-671); iterates
+        self.modules() in the same order as the reference so equal seeds give equal weights."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_normal_(m.weight.data)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, BatchNorm2d):
+                if m.affine:
+                    m.weight.data.fill_(1)
+                    m.bias.data.zero_()
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _exchange(ops, cursor, idx, feats):
+        """sum_j ops[cursor+j](feats[idx[j]]) — the cross-task message (:429-436)."""
+        z = None
+        for j, src in enumerate(idx):
+            y = ops[cursor + j](feats[src])
+            z = y if z is None else F_.add(z, y)
+        return z, cursor + len(idx)
+
+    def forward(self, x):
+        x = F_.to_internal(x)
+        s0 = self.stem1(self.stem0(x))
+        s1 = self.stem2(s0)
+        s2 = self.stem4(self.stem3(x))
+        s3 = self.stem5(s2)
+        f1, f2 = [], []           # per-stream feature pyramids (fine -> coarse, then decoder outputs)
+        c1 = c2 = stage = 0
+        for i, (cell1, cell2) in enumerate(zip(self.cells1, self.cells2)):
+            s0, s1 = s1, cell1(s0, s1)
+            s2, s3 = s3, cell2(s2, s3)
+            if i in self._tap_layers:
+                f1.append(s1)
+                f2.append(s3)
+                z1, c1 = self._exchange(self._ops1, c1, self._indices1[stage], f2)
+                z2, c2 = self._exchange(self._ops2, c2, self._indices2[stage], f1)
+                stage += 1
+                s1 = F_.add(s1, z1)
+                s3 = F_.add(s3, z2)
+                f1[-1], f2[-1] = s1, s3
+
+        # decoder: three upsample cells per stream with interaction after each (:453-533)
+        c1 = c2 = 0
+        prev1, prev2 = f1[3], f2[3]
+        for d in range(3):
+            o1 = self.upsamples1[d](prev1, f1[2 - d])
+            o2 = self.upsamples2[d](prev2, f2[2 - d])
+            f1.append(o1)
+            f2.append(o2)
+            z1, c1 = self._exchange(self.up_ops1, c1, self.up_indices1[d], f2)
+            z2, c2 = self._exchange(self.up_ops2, c2, self.up_indices2[d], f1)
+            o1 = F_.add(o1, z1)
+            o2 = F_.add(o2, z2)
+            f1[-1], f2[-1] = o1, o2
+            prev1, prev2 = o1, o2
+
+        def pyramid(f):  # (:538-543)
+            return F_.cat([f[0], f[6],
+                           F_.interpolate(f[5], scale_factor=2, mode="bilinear", align_corners=True),
+                           F_.interpolate(f[4], scale_factor=4, mode="bilinear", align_corners=True)])
+
+        x1, x2 = pyramid(f1), pyramid(f2)
+        in1 = self.pose_auxlayer(x1)
+        in2 = self.edge_layer(x2)
+        in3 = self.pose_layer(x1)
+        in4 = self.par_layer(x2)
+
+        pose_list, par_list = [], []
+
+        def emit(stage_idx):
+            edge = self.edge_head[stage_idx](in2)
+            pose_aux = self.pose_auxnet[stage_idx](in1)
+            pose_map = self.pose_head[stage_idx](in3)
+            par_map = self.par_head[stage_idx](in4)
+            pose_list.append([F_.from_internal(pose_map, self._num_joints), F_.from_internal(pose_aux, self._num_joints)])
+            par_list.append([F_.from_internal(par_map, self._num_classes), F_.from_internal(edge, 2)])
+
+        emit(0)
+        for i in range(1, self.refine_layers + 1):
+            for j in range(3):
+                in1, tmp = self.pose_net[2 * (i - 1) + j](in1, in3, in4)
+                in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4)
+                in3 = tmp
+            emit(i)
+        return pose_list, par_list
+
+    # ------------------------------------------------------------------ checkpoints
+    def load_pretrain_backbone(self, path=""):
+        """Loads a reference checkpoint: strips DDP's `module.` prefix, skips shape mismatches and
+        missing keys (strict=False) — model_augment.py:673-709."""
+        if not os.path.isfile(path):
+            return
+        loaded = torch.load(path, map_location="cpu")
+        own = self.state_dict()
+        merged = {}
+        for k, v in loaded.items():
+            k = k[7:] if k.startswith("module") else k
+            if k in own and tuple(own[k].shape) != tuple(v.shape):
+                print("Skip loading parameter {}, required shape{}, loaded shape{}.".format(k, own[k].shape, v.shape))
+                v = own[k]
+            merged[k] = v
+        for k, v in own.items():
+            merged.setdefault(k, v)
+        msg = self.load_state_dict(merged, strict=False)
+        print("=> loading information:", msg)
+        print("successful load pretrained backbone from {}".format(path))

@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
   CK(cudaMemset(ddx_tc, 0x7f, xn * 2)); CK(cudaMemset(ddx_ref, 0x7f, xn * 2));
   CK(cudaMemset(stats, 0, 2 * c.cout * 4)); CK(cudaMemset(dw_tc, 0, hw.size() * 4)); CK(cudaMemset(dw_ref, 0, hw.size() * 4));
 
-  int rc = npp_pack_weight(w32, w, wt, c.cout, taps, c.cin, c.cout, c.cin, 0);
+  int rc = npp_pack_weight(w32, w, wt, c.cout, taps, c.cin, c.cout, c.cin, NPP_BF16, 0);
   if (rc) { printf("pack rc=%d %s\n", rc, npp_last_error()); return 1; }
 
   npp_view4 vx{dx, c.n, c.h, c.w, c.cin, (int64_t)c.h * c.w * xc, (int64_t)c.w * xc, xc};

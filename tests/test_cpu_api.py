@@ -1,0 +1,119 @@
+"""CPU: the drop-in boundary — module API / state_dict parity with the reference, the C-ABI library exports
+every symbol include/npp_b200.h declares, and the host-side helpers behave."""
+import ctypes
+import os
+import re
+import types
+
+import pytest
+import torch
+
+import _refshim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "npp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(npp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 50
+    lib = ctypes.CDLL(lib_built)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.npp_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.npp_version()
+
+
+def test_ops_table_matches_reference_keys():
+    from npp_b200.models.operations import OPS
+    expected = {"none", "avg_pool_3x3", "max_pool_3x3", "skip_connect", "std_conv_3x3", "std_conv_1x1",
+                "dil_conv_3x3_2", "dil_conv_3x3_4", "dil_conv_5x5_4", "se_connect", "conv_7x1_1x7", "sep_conv_3x3",
+                "sep_conv_5x5", "poled_conv_x1", "poled_conv_x2"}
+    assert set(OPS) == expected
+    with pytest.raises(NotImplementedError):
+        OPS["conv_7x1_1x7"](16, 1, True)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from npp_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libnpp_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU / cuDNN fallback"):
+        _lib.lib()
+
+
+def test_kernels_refuse_cpu_tensors(lib_built):
+    from npp_b200.models.operations import OPS
+    op = OPS["std_conv_3x3"](16, 1, True)
+    with pytest.raises(Exception):
+        op(torch.randn(1, 16, 8, 8))
+
+
+@pytest.mark.skipif(not _refshim.have_reference(), reason="needs /root/reference (build container only)")
+def test_state_dict_and_seeded_init_identical_to_reference():
+    ref = _refshim.import_reference()
+    from npp_b200.models.model_augment import Network
+    cfg = _refshim.cfg(layers=8, init_channels=16)
+    torch.manual_seed(0)
+    rn = ref.model_augment.Network(cfg)
+    torch.manual_seed(0)
+    mn = Network(cfg)
+    rsd, msd = rn.state_dict(), mn.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    for k in rsd:
+        assert rsd[k].shape == msd[k].shape and torch.equal(rsd[k], msd[k]), k
+    # optimizer param grouping of augment_lip_sync.py:193-202 relies on these name prefixes
+    assert any(k.startswith("cells1.") for k in msd) and any(k.startswith("stem") for k in msd)
+    # reference checkpoints load (strict) into ours and vice versa
+    mn.load_state_dict(rsd, strict=True)
+    rn.load_state_dict(msd, strict=True)
+
+
+@pytest.mark.skipif(not _refshim.have_reference(), reason="needs /root/reference (build container only)")
+def test_full_size_state_dict_keys():
+    ref = _refshim.import_reference()
+    from npp_b200.models.model_augment import Network
+    cfg = _refshim.cfg(layers=16, init_channels=64)
+    with torch.device("meta"):
+        rn = ref.model_augment.Network.__new__(ref.model_augment.Network)
+    # constructing the full 77M-parameter nets twice is slow; compare key lists/shapes via meta tensors
+    import torch.nn as nn
+    from unittest import mock
+    with mock.patch.object(ref.model_augment.Network, "_init_params", lambda self: None), torch.device("meta"):
+        rn = ref.model_augment.Network(cfg)
+    from npp_b200.models import model_augment as M
+    with mock.patch.object(M.Network, "_init_params", lambda self: None), torch.device("meta"):
+        mn = M.Network(cfg)
+    rk = [(k, tuple(v.shape)) for k, v in rn.state_dict().items()]
+    mk = [(k, tuple(v.shape)) for k, v in mn.state_dict().items()]
+    assert rk == mk
+    assert len(rk) == 3226
+    assert sum(p.numel() for p in mn.parameters()) == sum(p.numel() for p in rn.parameters())
+
+
+@pytest.mark.skipif(not _refshim.have_reference(), reason="needs /root/reference (build container only)")
+def test_oracle_matches_reference_network():
+    ref = _refshim.import_reference()
+    from oracle import nppnet_ref as O
+    cfg = _refshim.cfg(layers=8, init_channels=16)
+    torch.manual_seed(1)
+    rn = ref.model_augment.Network(cfg).train()
+    sd = {k: v.detach().clone() for k, v in rn.state_dict().items()}
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        pl, par = rn(x)
+        opl, opar = O.network_forward(sd, x, layers=8, training=True)
+    for a, b in zip([t for p in pl + par for t in p], [t for p in opl + opar for t in p]):
+        assert torch.equal(a, b)
+    after = rn.state_dict()
+    for k in sd:
+        if "running" in k:
+            assert torch.equal(after[k], sd[k]), k
+
+
+def test_genotypes_fields():
+    from npp_b200.models import genotypes as gt
+    assert gt.Genotype._fields == ("normal", "normal_concat", "reduce", "reduce_concat")
+    assert len(gt.ENCODER.normal) == 8 and len(gt.FUSION.pose) == 8 and list(gt.FUSION.par_concat) == [3, 4, 5, 6]
+    assert gt.PRIMITIVES_PC[0] == "std_conv_3x3" and len(gt.PRIMITIVES_INTER) == 7
