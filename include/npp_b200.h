@@ -51,6 +51,7 @@ typedef struct {
 const char* npp_version(void);
 const char* npp_last_error(void); /* thread-local text of the last NPP_E_CUDA */
 int npp_sm_count(void);
+long long npp_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------
  * Dense convolution as implicit GEMM on tcgen05 / TMEM, operands staged by TMA (bf16 only).

@@ -39,6 +39,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.npp_last_error.restype = ctypes.c_char_p
         _lib.npp_version.restype = ctypes.c_char_p
+        _lib.npp_launch_count.restype = ctypes.c_longlong
     return _lib
 
 
@@ -85,9 +86,47 @@ def check(rc, name):
         raise RuntimeError("%s failed: %s %s" % (name, msg, detail))
 
 
-def call(name, *args):
+_prof = None  # when profiling: list of (name, start_event, end_event, work)
+
+
+def call(name, *args, work=None):
+    """Invokes a C-ABI entry point.  `work` = (algorithmic flops, algorithmic bytes) of this call, only
+    used by the event profiler (bench.py's live roofline measurement)."""
     fn = getattr(lib(), name)
+    if _prof is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(fn(*args), name)
+    e1.record()
+    _prof.append((name, e0, e1, work or (0.0, 0.0)))
+
+
+def profile_begin():
+    """Starts bracketing every kernel-launching ABI call with CUDA events on torch's current stream."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Returns {abi name: dict(calls, ms, flops, bytes)} and stops profiling."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, (fl, by) in rec:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
+def launch_count():
+    """Number of kernels libnpp_b200 has launched in this process (bench.py's gpu_launches evidence)."""
+    return int(lib().npp_launch_count())
 
 
 def i32(v):

@@ -10,6 +10,7 @@ namespace npp {
 
 void set_error(const char* what, cudaError_t e);
 void set_error_str(const char* what);
+void count_launch(int n);  // kernel-launch counter behind npp_launch_count()
 
 #define NPP_CHECK_LAUNCH(name)                          \
   do {                                                  \
@@ -18,6 +19,7 @@ void set_error_str(const char* what);
       ::npp::set_error(name, e__);                      \
       return NPP_E_CUDA;                                \
     }                                                   \
+    ::npp::count_launch(1);                             \
   } while (0)
 
 static inline cudaStream_t as_stream(npp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

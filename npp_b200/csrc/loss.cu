@@ -400,6 +400,7 @@ int npp_ohem_select(const float* prob, const float* loss, int64_t npix, const in
   }
   ohem_sum_kernel<<<grid, 256, 0, st>>>(prob, loss, npix, ws, thres, out3);
   NPP_CHECK_LAUNCH("ohem_select");
+  count_launch(9);  // init + 4 x (hist, scan); the sum kernel is counted by the check above
   return NPP_OK;
 }
 

@@ -1,10 +1,13 @@
 // Library-level state: version string, thread-local error text, cached SM count.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace npp {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof g_err, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -30,4 +33,5 @@ extern "C" {
 const char* npp_version(void) { return "npp_b200 0.1 (sm_100a)"; }
 const char* npp_last_error(void) { return npp::g_err; }
 int npp_sm_count(void) { return npp::sm_count(); }
+long long npp_launch_count(void) { return npp::g_launches.load(); }
 }

@@ -147,6 +147,15 @@ def conv_out_size(size, k, stride, pad, dil, off=0):
     return (size - off + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
 
+def _conv_work(n, ho, wo, cout, cin, kh, kw, x, y):
+    """(algorithmic FLOPs, algorithmic bytes) of one conv direction: 2*N*Ho*Wo*Cout*Cin*kh*kw; unique input +
+    output elements + weights once."""
+    flops = 2.0 * n * ho * wo * cout * cin * kh * kw
+    esz = x.element_size()
+    byts = float(x.shape[0] * x.shape[2] * x.shape[3] * cin * esz + n * ho * wo * cout * esz + cout * cin * kh * kw * esz)
+    return flops, byts
+
+
 class _ConvFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad, dil, hoff, woff, want_stats):
@@ -173,11 +182,13 @@ class _ConvFn(Function):
             if want_stats:
                 stats = torch.zeros(2 * cop, dtype=torch.float32, device=x.device)
             call("npp_conv2d_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw), i32(stride),
-                 i32(pad), i32(dil), i32(hoff), i32(woff), fptr(stats), stream())
+                 i32(pad), i32(dil), i32(hoff), i32(woff), fptr(stats), stream(),
+                 work=_conv_work(n, ho, wo, cout, cin, kh, kw, x, y))
         else:
             call("npp_conv2d_direct_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw),
                  i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
         ctx.cfg = (stride, pad, dil, hoff, woff, cout, cin, kh, kw, bias is not None)
+        ctx.work = _conv_work(n, ho, wo, cout, cin, kh, kw, x, y)
         ctx.save_for_backward(x, wt if bf16 else wp)
         if stats is None:
             stats = torch.empty(0, device=x.device)
@@ -196,7 +207,7 @@ class _ConvFn(Function):
             dx = torch.empty_like(x)
             if bf16:
                 call("npp_conv2d_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw), i32(stride),
-                     i32(pad), i32(dil), i32(hoff), i32(woff), stream())
+                     i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work)
             else:
                 call("npp_conv2d_direct_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw),
                      i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
@@ -204,7 +215,7 @@ class _ConvFn(Function):
             dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
             if bf16:
                 call("npp_conv2d_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
-                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream())
+                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work)
             else:
                 call("npp_conv2d_direct_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh),
                      i32(kw), i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
