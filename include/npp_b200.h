@@ -174,14 +174,15 @@ int npp_fill_zero(const npp_view4* y, int dtype, npp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pooling.  maxpool3x3: nn.MaxPool2d(3, stride, 1) (operations.py:55), -inf padding.
- * bwd routes dy to the FIRST maximum in window scan order (ATen semantics).
+ * argmax (optional, dense uint8 [n,ho,wo,c]): winning window position 0..8 = FIRST maximum in
+ * scan order (ATen semantics); bwd gathers dy through it.
  * avgpool3x3: nn.AvgPool2d(3, stride, 1, count_include_pad=False) (:57).
  * avgpool2x2: nn.AvgPool2d(2) (:115, :237).   gap: nn.AdaptiveAvgPool2d(1) (:111).
  * ---------------------------------------------------------------------------------------- */
-int npp_maxpool3x3_fwd(const npp_view4* x, const npp_view4* y, int stride, int dtype,
-                       npp_stream_t stream);
-int npp_maxpool3x3_bwd(const npp_view4* x, const npp_view4* dy, const npp_view4* dx, int stride,
+int npp_maxpool3x3_fwd(const npp_view4* x, const npp_view4* y, uint8_t* argmax, int stride,
                        int dtype, npp_stream_t stream);
+int npp_maxpool3x3_bwd(const uint8_t* argmax, const npp_view4* dy, const npp_view4* dx,
+                       int stride, int dtype, npp_stream_t stream);
 int npp_avgpool3x3_fwd(const npp_view4* x, const npp_view4* y, int stride, int dtype,
                        npp_stream_t stream);
 int npp_avgpool3x3_bwd(const npp_view4* dy, const npp_view4* dx, int stride, int dtype,

@@ -54,7 +54,7 @@ struct Geom {
   int W, H, N;                    // output (fprop) pixel-space extents, for masking
   int n_blocks;                   // Cout blocks of BN
   int cout;
-  int total_tiles;
+  int num_ptiles;                 // pixel tiles; total work items = num_ptiles * n_blocks
 };
 
 template <int BN>
@@ -121,15 +121,21 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int num_k = g.num_taps * g.kc_blocks;
+  // Static schedule: CTA b owns output-channel block nb = b % n_blocks and every pt_step-th pixel tile; CTAs
+  // b..b+n_blocks-1 work on the same pixel tile at the same time, so its activation boxes are L2 hits.
+  const int nb = blockIdx.x % g.n_blocks;
+  const int pt_start = blockIdx.x / g.n_blocks;
+  const int pt_step = gridDim.x / g.n_blocks;
+  constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
+  constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int nb = tile % g.n_blocks;
-        int pt = tile / g.n_blocks;
+      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+        int pt = ptile;
         const int w0 = (pt % g.tiles_w) * g.tw;
         pt /= g.tiles_w;
         const int h0 = (pt % g.tiles_h) * g.th;
@@ -156,7 +162,7 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -186,27 +192,28 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
     int acc = 0;
     uint32_t acc_phase = 0;
     int sbuf = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const int nb = tile % g.n_blocks;
-      int pt = tile / g.n_blocks;
+    // BatchNorm statistics are accumulated in registers over all tiles of this CTA (same channel block nb for
+    // every tile) and flushed once at the end: per-channel atomics drop from one per tile to one per CTA —
+    // same-address atomics serialise in L2 and were the bottleneck of the first version.
+    float acc_s[SLABS][8], acc_q[SLABS][8];
+#pragma unroll
+    for (int sl = 0; sl < SLABS; ++sl)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc_s[sl][k] = 0.f; acc_q[sl][k] = 0.f; }
+    for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+      int pt = ptile;
       const int w0 = (pt % g.tiles_w) * g.tw;
       pt /= g.tiles_w;
       const int h0 = (pt % g.tiles_h) * g.th;
       const int n0 = (pt / g.tiles_h) * g.tn;
-      // validity of this thread's pixel row (ragged tiles), for the statistics
-      bool row_valid;
-      {
-        const int rw = row % g.tw, rh = (row / g.tw) % g.th, rn = row / (g.tw * g.th);
-        row_valid = (w0 + rw < g.W) && (h0 + rh < g.H) && (n0 + rn < g.N);
-      }
+      // ragged tiles (rows that fall outside the tensor) are masked out of the statistics
+      const bool tile_full = (w0 + g.tw <= g.W) && (h0 + g.th <= g.H) && (n0 + g.tn <= g.N);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
-      constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
-#pragma unroll 1
+#pragma unroll
       for (int slab = 0; slab < SLABS; ++slab) {
         const int co_base = nb * BN + slab * 64;
-        if (co_base >= g.cout) break;  // uniform across the CTA
+        if (co_base >= g.cout) continue;  // uniform across the CTA
         // the TMA store that last read this staging buffer must have finished reading it
         if (etid == 0) tma_store_wait_read<1>();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -246,33 +253,63 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
           tma_store_commit();
         }
         if (stats != nullptr) {
-          // per-channel sum / sum of squares of the bf16-rounded tile: thread -> (column, row half)
-          const int col = etid & 63;
-          const int rbeg = (etid >> 6) * 64;
-          if (col < SLAB_COLS && co_base + col < g.cout) {
-            float s = 0.f, s2 = 0.f;
-            const int chunk = col >> 3, e = col & 7;
-            for (int rr = rbeg; rr < rbeg + 64; ++rr) {
-              const int rw = rr % g.tw, rh = (rr / g.tw) % g.th, rn = rr / (g.tw * g.th);
-              const bool ok = (w0 + rw < g.W) && (h0 + rh < g.H) && (n0 + rn < g.N);
-              const __nv_bfloat16 hv = *reinterpret_cast<const __nv_bfloat16*>(
-                  stg + rr * 128 + ((chunk ^ (rr & 7)) << 4) + e * 2);
-              const float v = ok ? __bfloat162float(hv) : 0.f;
-              s += v;
-              s2 += v * v;
+          // Per-channel sum / sum of squares of the bf16-rounded tile.  Epilogue warp q owns the 16-byte chunks
+          // {2q, 2q+1} (8 channels each); its 32 lanes are (chunk, 8-row group) pairs, each lane adds up 8 rows with
+          // LDS.128 (rows visited in a lane-skewed order so the 128B swizzle keeps the 8 lanes of a phase on
+          // different banks) into its register accumulators.
+          const int c2 = lane >> 4, rg = lane & 15;
+          const int chunk = 2 * q + c2;
+          if (chunk * 8 < SLAB_COLS) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = rg * 8 + ((i + rg) & 7);
+              bool ok = true;
+              if (!tile_full) {
+                const int rw = rr % g.tw, rh = (rr / g.tw) % g.th, rn = rr / (g.tw * g.th);
+                ok = (w0 + rw < g.W) && (h0 + rh < g.H) && (n0 + rn < g.N);
+              }
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+              if (ok) {
+                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float v0 = __uint_as_float(uu[e] << 16), v1 = __uint_as_float(uu[e] & 0xffff0000u);
+                  acc_s[slab][2 * e] += v0; acc_q[slab][2 * e] = fmaf(v0, v0, acc_q[slab][2 * e]);
+                  acc_s[slab][2 * e + 1] += v1; acc_q[slab][2 * e + 1] = fmaf(v1, v1, acc_q[slab][2 * e + 1]);
+                }
+              }
             }
-            atomicAdd(stats + co_base + col, s);
-            atomicAdd(stats + g.cout + co_base + col, s2);
           }
         }
         sbuf ^= 1;
       }
-      (void)row_valid;
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (stats != nullptr) {
+      // fold the 16 row groups of each half-warp, then one atomic per (CTA, channel, moment)
+      const int c2 = lane >> 4, rg = lane & 15;
+      const int chunk = 2 * q + c2;
+#pragma unroll
+      for (int sl = 0; sl < SLABS; ++sl) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float a = acc_s[sl][k], b = acc_q[sl][k];
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          const int co = nb * BN + sl * 64 + chunk * 8 + k;
+          if (rg == 0 && chunk * 8 < SLAB_COLS && co < g.cout) {
+            atomicAdd(stats + co, a);
+            atomicAdd(stats + g.cout + co, b);
+          }
+        }
+      }
     }
     if (etid == 0) tma_store_wait_all<0>();
   }
@@ -543,7 +580,10 @@ static int launch_fprop(const Maps& maps, const Geom& g, const TapTable& taps, c
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm)", e); return NPP_E_CUDA; }
     attr_set = true;
   }
-  const int grid = g.total_tiles < sm_count() ? g.total_tiles : sm_count();
+  // grid = (CTAs per channel block) x n_blocks, one persistent CTA per SM
+  int per_nb = sm_count() / g.n_blocks;
+  if (per_nb > g.num_ptiles) per_nb = g.num_ptiles;
+  const int grid = per_nb * g.n_blocks;
   conv_gemm_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, bias, stats);
   NPP_CHECK_LAUNCH("conv_gemm_kernel");
   return NPP_OK;
@@ -599,9 +639,9 @@ static int run_gemm(const npp_view4* a_views, int n_a, const npp_view4* d, const
   g.W = (int)ps.W; g.H = (int)ps.H; g.N = (int)ps.N;
   g.n_blocks = (int)cdiv64(wRows, bn);
   g.cout = wRows;
-  const int64_t total = (int64_t)g.tiles_w * g.tiles_h * g.tiles_n * g.n_blocks;
-  if (total > 0x7fffffff) return NPP_E_UNSUPPORTED;
-  g.total_tiles = (int)total;
+  const int64_t ptiles = (int64_t)g.tiles_w * g.tiles_h * g.tiles_n;
+  if (ptiles * g.n_blocks > 0x7fffffff || g.n_blocks > sm_count()) return NPP_E_UNSUPPORTED;
+  g.num_ptiles = (int)ptiles;
   switch (bn) {
     case 32: return launch_fprop<32>(maps, g, taps, bias, stats, st);
     case 64: return launch_fprop<64>(maps, g, taps, bias, stats, st);

@@ -79,23 +79,24 @@ static int dw_bwd_data_t(const npp_view4* x, const float* w, const npp_view4* dy
   });
 }
 
-// dw[c, r*K+s] += sum_pixels dy[ho,wo,c] * relu(x)[ho*stride-pad+r*dil, wo*stride-pad+s*dil, c]; one kernel row
-// (K taps) per launch keeps the accumulators in registers.
-template <typename T, int K>
-static int dw_bwd_weight_t(const npp_view4* x, const npp_view4* dy, float* dw, int stride, int pad, int dil,
-                           int relu_in, cudaStream_t st) {
+// dw[c, r*K+s] += sum_pixels dy[ho,wo,c] * relu(x)[ho*stride-pad+r*dil, wo*stride-pad+s*dil, c].
+// ROWS kernel rows per launch: all 9 taps of a 3x3 in one pass (72 accumulators), one row at a time for 5x5.
+template <typename T, int K, int ROWS>
+static int dw_bwd_weight_rows(const npp_view4* x, const npp_view4* dy, float* dw, int r0, int stride, int pad, int dil,
+                              int relu_in, cudaStream_t st) {
   constexpr int V = Pack<T>::N;
   const auto X = dview<const T>(x);
   const auto DY = dview<const T>(dy);
   const int H = x->h, W = x->w;
-  for (int r = 0; r < K; ++r) {
-    int rc = reduce_ch<V, K>(
-        dy->n, dy->h, dy->w, dy->c, false, dw + r * K, 1, st, "dwconv_bwd_weight",
-        [=] __device__(int n, int ho, int wo, int c, float (&acc)[K][V]) {
-          const int hi = ho * stride - pad + r * dil;
-          if (hi < 0 || hi >= H) return;
-          float d[V];
-          Pack<T>::load(DY.at(n, ho, wo, c), d);
+  return reduce_ch<V, ROWS * K>(
+      dy->n, dy->h, dy->w, dy->c, false, dw + r0 * K, 1, st, "dwconv_bwd_weight",
+      [=] __device__(int n, int ho, int wo, int c, float (&acc)[ROWS * K][V]) {
+        float d[V];
+        Pack<T>::load(DY.at(n, ho, wo, c), d);
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) {
+          const int hi = ho * stride - pad + (r0 + rr) * dil;
+          if (hi < 0 || hi >= H) continue;
 #pragma unroll
           for (int s = 0; s < K; ++s) {
             const int wi = wo * stride - pad + s * dil;
@@ -103,10 +104,20 @@ static int dw_bwd_weight_t(const npp_view4* x, const npp_view4* dy, float* dw, i
             float v[V];
             Pack<T>::load(X.at(n, hi, wi, c), v);
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[s][i] = fmaf(d[i], relu_in ? fmaxf(v[i], 0.f) : v[i], acc[s][i]);
+            for (int i = 0; i < V; ++i)
+              acc[rr * K + s][i] = fmaf(d[i], relu_in ? fmaxf(v[i], 0.f) : v[i], acc[rr * K + s][i]);
           }
-        },
-        K * K);
+        }
+      },
+      K * K);
+}
+
+template <typename T, int K>
+static int dw_bwd_weight_t(const npp_view4* x, const npp_view4* dy, float* dw, int stride, int pad, int dil,
+                           int relu_in, cudaStream_t st) {
+  if (K == 3) return dw_bwd_weight_rows<T, K, (K == 3 ? 3 : 1)>(x, dy, dw, 0, stride, pad, dil, relu_in, st);
+  for (int r = 0; r < K; ++r) {
+    int rc = dw_bwd_weight_rows<T, K, 1>(x, dy, dw, r, stride, pad, dil, relu_in, st);
     if (rc) return rc;
   }
   return NPP_OK;

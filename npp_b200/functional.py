@@ -436,17 +436,19 @@ class _MaxPool3Fn(Function):
         n, c, h, w = x.shape
         ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
         y = empty_internal(n, c, ho, wo, x.dtype, x.device)
-        call("npp_maxpool3x3_fwd", ref(view(x)), ref(view(y)), i32(stride), i32(L.dtype_code(x)), stream())
-        ctx.stride = stride
-        ctx.save_for_backward(x)
+        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if ctx.needs_input_grad[0] else None
+        call("npp_maxpool3x3_fwd", ref(view(x)), ref(view(y)), fptr(idx), i32(stride), i32(L.dtype_code(x)), stream())
+        ctx.stride, ctx.shape = stride, tuple(x.shape)
+        ctx.save_for_backward(idx)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        dy = as_internal_grad(dy, x)
-        dx = torch.empty_like(x)
-        call("npp_maxpool3x3_bwd", ref(view(x)), ref(view(dy)), ref(view(dx)), i32(ctx.stride), i32(L.dtype_code(x)),
+        (idx,) = ctx.saved_tensors
+        dy = as_internal_grad(dy, dy)
+        n, c, h, w = ctx.shape
+        dx = empty_internal(n, c, h, w, dy.dtype, dy.device)
+        call("npp_maxpool3x3_bwd", fptr(idx), ref(view(dy)), ref(view(dx)), i32(ctx.stride), i32(L.dtype_code(dy)),
              stream())
         return dx, None
 

@@ -45,6 +45,12 @@ static const Case cases[] = {
     {"1x1 8->8 bias 24x24 n2 (tiny K)", 2, 24, 24, 8, 8, 1, 1, 0, 1, 0, 0, 0, 0, 1},
     {"3x3 512->512 24x24 n2", 2, 24, 24, 512, 512, 3, 1, 1, 1, 0, 0, 0, 0, 0},
     {"3x3 128->128 96x96 n8 (perf shape)", 8, 96, 96, 128, 128, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 128->128 96x96 n32 (bench shape)", 32, 96, 96, 128, 128, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"1x1 128->128 96x96 n32 (bench shape)", 32, 96, 96, 128, 128, 1, 1, 0, 1, 0, 0, 0, 0, 0},
+    {"1x1 512->128 96x96 n32 (bench shape)", 32, 96, 96, 512, 128, 1, 1, 0, 1, 0, 0, 0, 0, 0},
+    {"1x1 1024->512 bias 96x96 n32 (bench shape)", 32, 96, 96, 1024, 512, 1, 1, 0, 1, 0, 0, 0, 0, 1},
+    {"3x3 32->32 96x96 n32 (bench shape)", 32, 96, 96, 32, 32, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 256->256 48x48 n32 (bench shape)", 32, 48, 48, 256, 256, 3, 1, 1, 1, 0, 0, 0, 0, 0},
 };
 
 static uint32_t rng_state = 12345;
@@ -219,6 +225,10 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 10; ++i) npp_conv2d_fwd(&vx, w, bptr, &vy_tc, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, nullptr, 0);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("  time  : fprop %.1f us (%.1f TFLOP/s)", ms * 100, flops / (ms * 1e-4) / 1e12);
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 10; ++i) npp_conv2d_fwd(&vx, w, bptr, &vy_tc, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, stats, 0);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("  +stats %.1f us (%.1f TFLOP/s)", ms * 100, flops / (ms * 1e-4) / 1e12);
     CK(cudaEventRecord(e0));
     for (int i = 0; i < 10; ++i) npp_conv2d_dgrad(&vdy, wt, &vdx_tc, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, 0);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
