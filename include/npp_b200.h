@@ -306,6 +306,16 @@ int npp_pck_counts(const int32_t* pred_idx, const float* pred_max, const int32_t
 int npp_pckh_counts(const double* pred, const double* gt, int n, int p, double thr, int64_t* hit,
                     int64_t* valid, npp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-tensor Adam (torch.optim.Adam arithmetic, no amsgrad; augment_lip_sync.py:210-212):
+ * tensor_table: device array of {float* p; const float* g; float* m; float* v; int64 n; float lr;
+ * float wd} (48 bytes each); chunk_tensor/chunk_index: for every block, which tensor and which
+ * chunk of chunk_elems elements it updates; step: device int64 counter (incremented by the call).
+ * ---------------------------------------------------------------------------------------- */
+int npp_adam_step(const void* tensor_table, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                  int nchunks, int chunk_elems, int64_t* step, float beta1, float beta2, float eps,
+                  npp_stream_t stream);
+
 /* MixedOp channel interleave (model_search_interact.py:22-36,70-71 cat + channel_shuffle(2)):
  *   out[..., 2c] = a[..., c], out[..., 2c+1] = b[..., c];  bwd splits. */
 int npp_interleave2_fwd(const npp_view4* a, const npp_view4* b, const npp_view4* y, int dtype,

@@ -86,13 +86,17 @@ def check(rc, name):
         raise RuntimeError("%s failed: %s %s" % (name, msg, detail))
 
 
-_prof = None  # when profiling: list of (name, start_event, end_event, work)
+_prof = None   # when profiling: list of (name, start_event, end_event, work)
+_trace = None  # when tracing: list of (name, args, work, keep) of the calls that passed keep=
 
 
-def call(name, *args, work=None):
-    """Invokes a C-ABI entry point.  `work` = (algorithmic flops, algorithmic bytes) of this call, only
-    used by the event profiler (bench.py's live roofline measurement)."""
+def call(name, *args, work=None, keep=None):
+    """Invokes a C-ABI entry point.  `work` = (algorithmic flops, algorithmic bytes) of this call and `keep` = the
+    tensors behind its pointer arguments; both are only used by bench.py's live roofline measurement (event
+    profiler / call trace that is replayed back-to-back)."""
     fn = getattr(lib(), name)
+    if _trace is not None and keep is not None:
+        _trace.append((name, args, work or (0.0, 0.0), keep))
     if _prof is None:
         check(fn(*args), name)
         return
@@ -101,6 +105,27 @@ def call(name, *args, work=None):
     check(fn(*args), name)
     e1.record()
     _prof.append((name, e0, e1, work or (0.0, 0.0)))
+
+
+def trace_begin():
+    """Starts recording every traced ABI call (those passing keep=) with its arguments kept alive."""
+    global _trace
+    _trace = []
+
+
+def trace_end():
+    global _trace
+    t, _trace = _trace, None
+    return t
+
+
+def replay(trace, names):
+    """Re-issues the recorded calls whose ABI name is in `names` on the current stream (same pointers, same
+    shapes).  Stream arguments are re-read so the replay can be captured into a CUDA graph."""
+    cur = stream()
+    for name, args, _, _ in trace:
+        if name in names:
+            check(getattr(lib(), name)(*args[:-1], cur), name)
 
 
 def profile_begin():

@@ -23,31 +23,55 @@ static inline DView<T> dview(const npp_view4* v) {
   return d;
 }
 
-// One thread per (pixel, channel-vector) of an [n,h,w,c] index space, grid-stride.
-// f(n, h, w, c0) is called with c0 a multiple of the vector width.
+// ---- launch geometry shared by the two launchers ------------------------------------------------------
+// A 256-thread block is laid out as (cvb channel-vectors) x (rows pixels): consecutive threads touch
+// consecutive 16-byte channel vectors of one pixel (coalesced), the block then strides over pixels.
+// Pixel index -> (n, h, w) is one 32-bit div/mod pair per pixel (64-bit divisions were the bottleneck of
+// the first version of these kernels).
+struct VecGeom {
+  int cv;      // channel vectors per pixel
+  int cvb;     // channel vectors handled by one block (<= 256)
+  int rows;    // pixels handled per block iteration
+  int gy;      // blocks along the channel axis
+};
+static inline VecGeom vec_geom(int C, int VEC) {
+  VecGeom g;
+  g.cv = C / VEC;
+  g.cvb = g.cv < 256 ? g.cv : 256;
+  g.rows = 256 / g.cvb;
+  g.gy = (g.cv + g.cvb - 1) / g.cvb;
+  return g;
+}
+
+// f(n, h, w, c0) for every pixel and every channel vector (c0 multiple of VEC).
 template <int VEC, typename F>
-__global__ void __launch_bounds__(256) foreach_vec_kernel(int N, int H, int W, int C, F f) {
-  const int cv = C / VEC;
-  const int64_t total = (int64_t)N * H * W * cv;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) * VEC;
-    int64_t p = i / cv;
-    const int w = (int)(p % W);
-    p /= W;
-    const int h = (int)(p % H);
-    const int n = (int)(p / H);
+__global__ void __launch_bounds__(256) foreach_vec_kernel(int npix, int H, int W, VecGeom g, F f) {
+  const int tcv = threadIdx.x % g.cvb;
+  const int trow = threadIdx.x / g.cvb;
+  const int mycv = blockIdx.y * g.cvb + tcv;
+  if (trow >= g.rows || mycv >= g.cv) return;
+  const int c0 = mycv * VEC;
+  const int step = gridDim.x * g.rows;
+  for (int p = blockIdx.x * g.rows + trow; p < npix; p += step) {
+    const int w = p % W;
+    const int t = p / W;
+    const int h = t % H;
+    const int n = t / H;
     f(n, h, w, c0);
   }
 }
 
 template <int VEC, typename F>
 static inline int foreach_vec(int N, int H, int W, int C, cudaStream_t st, const char* name, F f) {
-  const int64_t total = (int64_t)N * H * W * (C / VEC);
-  if (total <= 0) return NPP_OK;
-  int64_t grid = (total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;  // 16 x 256 threads resident per SM
-  if (grid > cap) grid = cap;
-  foreach_vec_kernel<VEC, F><<<(int)grid, 256, 0, st>>>(N, H, W, C, f);
+  const int64_t npix64 = (int64_t)N * H * W;
+  if (npix64 <= 0 || C <= 0) return NPP_OK;
+  if (npix64 > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  const VecGeom g = vec_geom(C, VEC);
+  int64_t gx = (npix64 + g.rows - 1) / g.rows;
+  const int64_t cap = ((int64_t)sm_count() * 16 + g.gy - 1) / g.gy;  // ~16 resident 256-thread blocks per SM
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)g.gy);
+  foreach_vec_kernel<VEC, F><<<grid, 256, 0, st>>>((int)npix64, H, W, g, f);
   NPP_CHECK_LAUNCH(name);
   return NPP_OK;
 }
@@ -56,29 +80,26 @@ static inline int foreach_vec(int N, int H, int W, int C, cudaStream_t st, const
 // quantities per channel; results are atomically added to out[k*out_kstride + (zoff + c)*out_cstride].
 // grid = (pixel chunks, channel-vector groups, Z) where Z = N if per_image else 1.
 template <int VEC, int K, typename F>
-__global__ void __launch_bounds__(256) reduce_ch_kernel(int N, int H, int W, int C, int per_image, float* out,
-                                                        int64_t out_kstride, int64_t out_cstride, F f) {
+__global__ void __launch_bounds__(256) reduce_ch_kernel(int npix, int H, int W, int C, VecGeom g, int per_image,
+                                                        float* out, int64_t out_kstride, int64_t out_cstride, F f) {
   __shared__ float red[256 * VEC];
-  const int cv = C / VEC;
-  const int cv_pb = cv < 256 ? cv : 256;        // channel vectors per block
-  const int rows_pb = 256 / cv_pb;              // pixel rows per block iteration
-  const int tcv = threadIdx.x % cv_pb;
-  const int trow = threadIdx.x / cv_pb;
-  const int mycv = blockIdx.y * cv_pb + tcv;
-  const bool active = trow < rows_pb && mycv < cv;
+  const int tcv = threadIdx.x % g.cvb;
+  const int trow = threadIdx.x / g.cvb;
+  const int mycv = blockIdx.y * g.cvb + tcv;
+  const bool active = trow < g.rows && mycv < g.cv;
   float acc[K][VEC];
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
-  const int nimg = per_image ? 1 : N;
   const int n_base = per_image ? blockIdx.z : 0;
-  const int64_t npix = (int64_t)nimg * H * W;
   if (active) {
-    for (int64_t p = (int64_t)blockIdx.x * rows_pb + trow; p < npix; p += (int64_t)gridDim.x * rows_pb) {
-      const int w = (int)(p % W);
-      const int h = (int)((p / W) % H);
-      const int n = n_base + (int)(p / ((int64_t)W * H));
+    const int step = gridDim.x * g.rows;
+    for (int p = blockIdx.x * g.rows + trow; p < npix; p += step) {
+      const int w = p % W;
+      const int t = p / W;
+      const int h = t % H;
+      const int n = n_base + t / H;
       f(n, h, w, mycv * VEC, acc);
     }
   }
@@ -92,7 +113,7 @@ __global__ void __launch_bounds__(256) reduce_ch_kernel(int N, int H, int W, int
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         float s = 0.f;
-        for (int r = 0; r < rows_pb; ++r) s += red[(r * cv_pb + tcv) * VEC + v];
+        for (int r = 0; r < g.rows; ++r) s += red[(r * g.cvb + tcv) * VEC + v];
         atomicAdd(out + k * out_kstride + ((per_image ? (int64_t)blockIdx.z * C : 0) + mycv * VEC + v) * out_cstride, s);
       }
     }
@@ -102,20 +123,20 @@ __global__ void __launch_bounds__(256) reduce_ch_kernel(int N, int H, int W, int
 template <int VEC, int K, typename F>
 static inline int reduce_ch(int N, int H, int W, int C, bool per_image, float* out, int64_t out_kstride, cudaStream_t st,
                             const char* name, F f, int64_t out_cstride = 1) {
-  const int cv = C / VEC;
-  const int cv_pb = cv < 256 ? cv : 256;
-  const int rows_pb = 256 / cv_pb;
-  const int gy = (cv + cv_pb - 1) / cv_pb;
+  const VecGeom g = vec_geom(C, VEC);
   const int64_t npix = (int64_t)(per_image ? 1 : N) * H * W;
-  int64_t gx = (npix + rows_pb - 1) / rows_pb;
-  // enough blocks to fill the machine a few times, but keep >= ~8 pixels per thread to amortise the atomics
-  const int64_t cap = (int64_t)sm_count() * 8 / (gy * (per_image ? N : 1)) + 1;
+  if (npix > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  const int z = per_image ? N : 1;
+  int64_t gx = (npix + g.rows - 1) / g.rows;
+  // fill the machine (~8 blocks per SM) but keep >= 16 pixels per thread so the per-block atomics stay negligible
+  const int64_t cap = ((int64_t)sm_count() * 8 + (int64_t)g.gy * z - 1) / ((int64_t)g.gy * z);
   if (gx > cap) gx = cap;
-  const int64_t min_rows = 8;
-  if (gx > (npix + rows_pb * min_rows - 1) / (rows_pb * min_rows)) gx = (npix + rows_pb * min_rows - 1) / (rows_pb * min_rows);
+  const int64_t max_by_work = (npix + (int64_t)g.rows * 16 - 1) / ((int64_t)g.rows * 16);
+  if (gx > max_by_work) gx = max_by_work;
   if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)(per_image ? N : 1));
-  reduce_ch_kernel<VEC, K, F><<<grid, 256, 0, st>>>(N, H, W, C, per_image ? 1 : 0, out, out_kstride, out_cstride, f);
+  dim3 grid((unsigned)gx, (unsigned)g.gy, (unsigned)z);
+  reduce_ch_kernel<VEC, K, F><<<grid, 256, 0, st>>>((int)npix, H, W, C, g, per_image ? 1 : 0, out, out_kstride,
+                                                    out_cstride, f);
   NPP_CHECK_LAUNCH(name);
   return NPP_OK;
 }

@@ -23,16 +23,21 @@ def make_cfg(num_classes=20, num_joints=16, layers=16, init_channels=64, refine_
               MODEL=ns(DECONV_WITH_BIAS=False, HEAD="PSP", REFINE_LAYERS=refine_layers))
 
 
-def build_optimizer(model, criterion_pose, criterion_par, lr=0.0015, capturable=True):
+def build_optimizer(model, criterion_pose, criterion_par, lr=0.0015, fused=True):
     """Adam with the reference's parameter groups (augment_lip_sync.py:193-212): backbone at 0.2*LR,
-    the rest at LR, the criteria's uncertainty weights at 1e-4."""
+    the rest at LR, the criteria's uncertainty weights at 1e-4.  fused=True uses npp_b200.optim.FusedAdam
+    (one launch per step), fused=False torch.optim.Adam(capturable=True)."""
     def backbone(n):
         return n.startswith("cells1.") or n.startswith("cells2") or n.startswith("stem")
     groups = [
         {"params": [p for n, p in model.named_parameters() if backbone(n) and p.requires_grad], "lr": 0.2 * lr},
         {"params": [p for n, p in model.named_parameters() if not backbone(n) and p.requires_grad]},
     ]
-    opt = torch.optim.Adam(groups, lr, capturable=capturable, foreach=True)
+    if fused:
+        from .optim import FusedAdam
+        opt = FusedAdam(groups, lr)
+    else:
+        opt = torch.optim.Adam(groups, lr, capturable=True, foreach=True)
     opt.add_param_group({"params": list(criterion_pose.parameters()), "lr": 0.0001})
     opt.add_param_group({"params": list(criterion_par.parameters()), "lr": 0.0001})
     return opt
@@ -148,6 +153,8 @@ class TrainStep:
         with torch.cuda.graph(self.graph):
             self._step_body()
         self.launches_per_step = _lib.launch_count() - c0
+        if hasattr(self.opt, "upload_tables"):
+            self.opt.upload_tables()  # pointer tables built during capture are uploaded once, outside it
 
     def run(self):
         """Runs one step on whatever is in the static input buffers; returns the (device) loss scalar."""

@@ -183,7 +183,7 @@ class _ConvFn(Function):
                 stats = torch.zeros(2 * cop, dtype=torch.float32, device=x.device)
             call("npp_conv2d_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw), i32(stride),
                  i32(pad), i32(dil), i32(hoff), i32(woff), fptr(stats), stream(),
-                 work=_conv_work(n, ho, wo, cout, cin, kh, kw, x, y))
+                 work=_conv_work(n, ho, wo, cout, cin, kh, kw, x, y), keep=(x, wp, bp, y, stats))
         else:
             call("npp_conv2d_direct_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw),
                  i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
@@ -207,7 +207,7 @@ class _ConvFn(Function):
             dx = torch.empty_like(x)
             if bf16:
                 call("npp_conv2d_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw), i32(stride),
-                     i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work)
+                     i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work, keep=(dy, wmat, dx))
             else:
                 call("npp_conv2d_direct_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw),
                      i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
@@ -215,7 +215,8 @@ class _ConvFn(Function):
             dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
             if bf16:
                 call("npp_conv2d_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
-                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work)
+                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work,
+                     keep=(x, dy, dw))
             else:
                 call("npp_conv2d_direct_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh),
                      i32(kw), i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
