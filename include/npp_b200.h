@@ -308,13 +308,14 @@ int npp_pckh_counts(const double* pred, const double* gt, int n, int p, double t
 
 /* ------------------------------------------------------------------------------------------
  * Multi-tensor Adam (torch.optim.Adam arithmetic, no amsgrad; augment_lip_sync.py:210-212):
- * tensor_table: device array of {float* p; const float* g; float* m; float* v; int64 n; float lr;
- * float wd} (48 bytes each); chunk_tensor/chunk_index: for every block, which tensor and which
- * chunk of chunk_elems elements it updates; step: device int64 counter (incremented by the call).
+ * tensor_table: device array of ntensors x {float* p; const float* g; float* m; float* v; int64 n;
+ * float lr; float wd; int64* step} (56 bytes each; step = that parameter's own device counter, as
+ * torch keeps one per parameter — incremented by the call); chunk_tensor/chunk_index: for every
+ * block, which tensor and which chunk of chunk_elems elements it updates.
  * ---------------------------------------------------------------------------------------- */
-int npp_adam_step(const void* tensor_table, const int32_t* chunk_tensor, const int32_t* chunk_index,
-                  int nchunks, int chunk_elems, int64_t* step, float beta1, float beta2, float eps,
-                  npp_stream_t stream);
+int npp_adam_step(const void* tensor_table, int ntensors, const int32_t* chunk_tensor,
+                  const int32_t* chunk_index, int nchunks, int chunk_elems, float beta1, float beta2,
+                  float eps, npp_stream_t stream);
 
 /* MixedOp channel interleave (model_search_interact.py:22-36,70-71 cat + channel_shuffle(2)):
  *   out[..., 2c] = a[..., c], out[..., 2c+1] = b[..., c];  bwd splits. */

@@ -13,18 +13,19 @@ struct AdamTensor {
   int64_t n;
   float lr;
   float wd;
+  int64_t* step;  // this tensor's own step counter (torch keeps one per parameter: a parameter whose gradient is
+                  // None in some step is skipped and its bias correction lags behind)
 };
-static_assert(sizeof(AdamTensor) == 48, "table layout is part of the ABI (npp_b200/optim.py mirrors it)");
+static_assert(sizeof(AdamTensor) == 56, "table layout is part of the ABI (npp_b200/optim.py mirrors it)");
 
 __global__ void __launch_bounds__(256)
 adam_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
-            const int* __restrict__ chunk_index, int chunk_elems, const int64_t* __restrict__ step, float beta1,
-            float beta2, float eps) {
+            const int* __restrict__ chunk_index, int chunk_elems, float beta1, float beta2, float eps) {
   const AdamTensor t = tensors[chunk_tensor[blockIdx.x]];
   const int64_t begin = (int64_t)chunk_index[blockIdx.x] * chunk_elems;
   int64_t end = begin + chunk_elems;
   if (end > t.n) end = t.n;
-  const double k = (double)(*step + 1);
+  const double k = (double)(*t.step + 1);
   const float bc1 = (float)(1.0 - pow((double)beta1, k));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, k));
   const float step_size = t.lr / bc1;
@@ -41,7 +42,10 @@ adam_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict__ chun
   }
 }
 
-__global__ void adam_bump_step_kernel(int64_t* step) { *step += 1; }
+__global__ void adam_bump_step_kernel(const AdamTensor* __restrict__ tensors, int ntensors) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ntensors) *tensors[i].step += 1;
+}
 
 }  // namespace npp
 
@@ -49,15 +53,16 @@ using namespace npp;
 
 extern "C" {
 
-int npp_adam_step(const void* tensor_table, const int32_t* chunk_tensor, const int32_t* chunk_index, int nchunks,
-                  int chunk_elems, int64_t* step, float beta1, float beta2, float eps, npp_stream_t s) {
-  if (!tensor_table || !chunk_tensor || !chunk_index || !step || nchunks < 0 || chunk_elems <= 0) return NPP_E_INVALID;
+int npp_adam_step(const void* tensor_table, int ntensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                  int nchunks, int chunk_elems, float beta1, float beta2, float eps, npp_stream_t s) {
+  if (!tensor_table || !chunk_tensor || !chunk_index || ntensors < 0 || nchunks < 0 || chunk_elems <= 0)
+    return NPP_E_INVALID;
   if (nchunks == 0) return NPP_OK;
   cudaStream_t st = as_stream(s);
   adam_kernel<<<nchunks, 256, 0, st>>>(static_cast<const AdamTensor*>(tensor_table), chunk_tensor, chunk_index,
-                                       chunk_elems, step, beta1, beta2, eps);
+                                       chunk_elems, beta1, beta2, eps);
   NPP_CHECK_LAUNCH("adam_kernel");
-  adam_bump_step_kernel<<<1, 1, 0, st>>>(step);
+  adam_bump_step_kernel<<<(ntensors + 255) / 256, 256, 0, st>>>(static_cast<const AdamTensor*>(tensor_table), ntensors);
   NPP_CHECK_LAUNCH("adam_bump_step_kernel");
   return NPP_OK;
 }

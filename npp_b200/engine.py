@@ -94,7 +94,9 @@ class TrainStep:
         self.pose_aux_gt = torch.zeros(batch, nj, hs, hs, device=dev)
         self.loss = torch.zeros((), device=dev)
         self.graph = None
-        self._warmup = warmup
+        self._warmup = max(1, warmup) if use_graph else warmup
+        # persistent flat gradients: static addresses for the graph, one memset per step, all-reduce without copies
+        self.flat_grads = optimizer.use_flat_grads() if hasattr(optimizer, "use_flat_grads") else None
         self.launches_per_step = None
 
     # ---- pieces ------------------------------------------------------------------------------------
@@ -112,6 +114,10 @@ class TrainStep:
 
     def _allreduce_grads(self):
         import torch.distributed as dist
+        if self.flat_grads is not None:
+            dist.all_reduce(self.flat_grads)
+            self.flat_grads.div_(self.world_size)
+            return
         params = [p for g in self.opt.param_groups for p in g["params"] if p.grad is not None]
         grads = [p.grad for p in params]
         flat = torch._utils._flatten_dense_tensors(grads)
@@ -153,8 +159,6 @@ class TrainStep:
         with torch.cuda.graph(self.graph):
             self._step_body()
         self.launches_per_step = _lib.launch_count() - c0
-        if hasattr(self.opt, "upload_tables"):
-            self.opt.upload_tables()  # pointer tables built during capture are uploaded once, outside it
 
     def run(self):
         """Runs one step on whatever is in the static input buffers; returns the (device) loss scalar."""

@@ -3,7 +3,10 @@
 Same constructor / param_groups interface as torch.optim.Adam (lr, betas, eps, weight_decay; no amsgrad), so it
 drops into augment_lip_sync.py:210-212 (`Adam(param_dicts, LR)` + `add_param_group`).  The kernel walks a device
 table of (param, grad, exp_avg, exp_avg_sq) pointers; the table is rebuilt only when a gradient's address
-changes — never under CUDA-graph replay, where all addresses are static.
+changes.  `use_flat_grads()` makes every gradient a persistent view into one flat fp32 buffer: addresses never
+change (required for CUDA-graph capture: a table allocated while capturing would live in the graph's private
+pool, whose blocks are reused by earlier graph nodes on every replay), zero_grad is one memset and the
+data-parallel gradient all-reduce runs on the flat buffer without flatten / unflatten copies.
 """
 import struct
 
@@ -19,8 +22,9 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._key = None
         self._tables = None       # (table, chunk_tensor, chunk_index) device tensors
-        self._host = None         # pinned host copies awaiting upload (graph capture)
-        self._step = None
+        self._steps = None        # one int64 device counter per parameter (torch.optim.Adam's state['step'])
+        self.flat_grads = None    # the flat gradient buffer once use_flat_grads() was called
+        self._flat_views = None
 
     def _init_state(self, p):
         st = self.state[p]
@@ -29,13 +33,49 @@ class FusedAdam(torch.optim.Optimizer):
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
+    def use_flat_grads(self):
+        """Allocates ONE fp32 buffer holding the gradient of every parameter (16-byte aligned slots) and installs
+        the slots as `p.grad`.  autograd then accumulates into them in place; zero_grad() zero-fills the buffer
+        instead of dropping the gradients.  Parameters that take no part in the forward (SE_Block.bn at stride 1,
+        operations.py:117) keep an all-zero gradient, for which the Adam update is exactly zero."""
+        params = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+        if not params:
+            return None
+        if self.flat_grads is not None and [id(p) for p, _ in self._flat_views] == [id(p) for p in params]:
+            return self.flat_grads
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            if p.dtype != torch.float32 or p.device != dev or not p.is_contiguous():
+                raise RuntimeError("FusedAdam.use_flat_grads needs contiguous fp32 parameters on one device")
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat_grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._flat_views = [(p, self.flat_grads[o:o + p.numel()].view_as(p)) for p, o in zip(params, offs)]
+        for p, v in self._flat_views:
+            p.grad = v
+        self._key = None
+        return self.flat_grads
+
+    def zero_grad(self, set_to_none=True):
+        if self.flat_grads is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        self.flat_grads.zero_()
+        for p, v in self._flat_views:
+            if p.grad is not v:
+                p.grad = v
+
     def _build(self, items, dev):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(
+                "FusedAdam: gradient addresses changed while capturing a CUDA graph — call use_flat_grads() and "
+                "run one eager step before the capture")
         rows, chunk_tensor, chunk_index = [], [], []
         for ti, (p, g, lr, wd) in enumerate(items):
             st = self._init_state(p)
             n = p.numel()
-            rows.append(struct.pack("<QQQQqff", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
-                                    st["exp_avg_sq"].data_ptr(), n, lr, wd))
+            rows.append(struct.pack("<QQQQqffQ", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                    st["exp_avg_sq"].data_ptr(), n, lr, wd, st["step"].data_ptr()))
             nch = (n + CHUNK - 1) // CHUNK
             chunk_tensor += [ti] * nch
             chunk_index += list(range(nch))
@@ -43,18 +83,7 @@ class FusedAdam(torch.optim.Optimizer):
         tbl = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8).clone()
         ct = torch.tensor(chunk_tensor, dtype=torch.int32)
         ci = torch.tensor(chunk_index, dtype=torch.int32)
-        self._host = (tbl, ct, ci)
-        self._tables = tuple(torch.empty_like(t, device=dev) for t in self._host)
-        if not torch.cuda.is_current_stream_capturing():
-            self.upload_tables()
-
-    def upload_tables(self):
-        """Copies the pointer tables to the device.  Called automatically in eager mode; after capturing a CUDA
-        graph (or after changing a learning rate) call it once before the next replay."""
-        if self._host is not None:
-            for d, h in zip(self._tables, self._host):
-                d.copy_(h, non_blocking=False)
-            self._host = None
+        self._tables = tuple(t.to(dev) for t in (tbl, ct, ci))
 
     def refresh_hyperparameters(self):
         """Rebuilds the table on the next step (e.g. after an lr scheduler changed group['lr'])."""
@@ -82,15 +111,21 @@ class FusedAdam(torch.optim.Optimizer):
                 dev = p.device
         if not items:
             return None
-        if self._step is None:
-            self._step = torch.zeros((), dtype=torch.int64, device=dev)
-            for p, _, _, _ in items:
-                self.state[p]["step"] = self._step
+        if self._steps is None:
+            allp = [p for group in self.param_groups for p in group["params"]]
+            self._steps = torch.zeros(len(allp), dtype=torch.int64, device=dev)
+            for i, p in enumerate(allp):
+                self.state[p]["step"] = self._steps[i]
+        for p, _, _, _ in items:
+            if "step" not in self.state[p]:  # parameter group added after the first step
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("FusedAdam: add parameter groups before capturing a CUDA graph")
+                self.state[p]["step"] = torch.zeros((), dtype=torch.int64, device=dev)
         key = tuple((p.data_ptr(), g.data_ptr(), lr, wd) for p, g, lr, wd in items)
         if key != self._key:
             self._build(items, dev)
             self._key = key
         tbl, ct, ci = self._tables
-        call("npp_adam_step", fptr(tbl), fptr(ct), fptr(ci), i32(ct.numel()), i32(CHUNK), fptr(self._step), f32(b1),
+        call("npp_adam_step", fptr(tbl), i32(len(items)), fptr(ct), fptr(ci), i32(ct.numel()), i32(CHUNK), f32(b1),
              f32(b2), f32(eps), stream())
         return None
