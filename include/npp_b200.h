@@ -317,6 +317,37 @@ int npp_adam_step(const void* tensor_table, int ntensors, const int32_t* chunk_t
                   const int32_t* chunk_index, int nchunks, int chunk_elems, float beta1, float beta2,
                   float eps, npp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused cell node (csrc/node.cu).  A cell node is s = op_a(h_a) + op_b(h_b)
+ * (models/model_augment.py:48-62, 90-106, 153-174); primitives end in BatchNorm2d
+ * (models/operations.py:61,79,97,215,240) and consumers start with nn.ReLU (:76,95,212,239).
+ *   node_fwd: y = f_a(a) [+ f_b(b)], f = x*scale[c]+shift[c] (scale == NULL: identity), written
+ *     as y_raw and/or relu(y) = y_relu (either may be NULL, not both; views may be channel slices
+ *     of a concat buffer — replaces torch.cat, model_augment.py:62).
+ *   node_bwd_reduce: g = g_raw + [relu_out > 0]*g_relu (either gradient may be NULL; g_out is
+ *     written when given) and, per BatchNorm input (a / b non-NULL), per-block partial sums of
+ *     (sum g, sum g*xhat) into partials[blocks][nq][C] with nq = 2 per BatchNorm input and
+ *     blocks = npp_node_bwd_blocks(n,h,w,c,dtype); npp_reduce_partials(partials, blocks, nq*C, out)
+ *     folds them (deterministic, no atomics) into out = [sum g, sum g*xhat_a, sum g, sum g*xhat_b].
+ *   node_bwd_apply: d_in = gamma*invstd*(g - s1/count - xhat*s2/count) per BatchNorm input, both
+ *     from one read of g; sums_x = [2][C] as produced above (all-reduced across ranks for SyncBN,
+ *     with count the global pixel count).
+ * ---------------------------------------------------------------------------------------- */
+int npp_node_fwd(const npp_view4* a, const float* scale_a, const float* shift_a, const npp_view4* b,
+                 const float* scale_b, const float* shift_b, const npp_view4* y_raw,
+                 const npp_view4* y_relu, int dtype, npp_stream_t stream);
+int npp_node_bwd_blocks(int n, int h, int w, int c, int dtype);
+int npp_node_bwd_reduce(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
+                        const npp_view4* a, const float* mean_a, const float* invstd_a,
+                        const npp_view4* b, const float* mean_b, const float* invstd_b,
+                        const npp_view4* g_out, float* partials, int dtype, npp_stream_t stream);
+int npp_reduce_partials(const float* partials, int rows, int len, float* out, npp_stream_t stream);
+int npp_node_bwd_apply(const npp_view4* g, const npp_view4* a, const float* gamma_a,
+                       const float* mean_a, const float* invstd_a, const float* sums_a,
+                       const npp_view4* da, const npp_view4* b, const float* gamma_b,
+                       const float* mean_b, const float* invstd_b, const float* sums_b,
+                       const npp_view4* db, double count, int dtype, npp_stream_t stream);
+
 /* MixedOp channel interleave (model_search_interact.py:22-36,70-71 cat + channel_shuffle(2)):
  *   out[..., 2c] = a[..., c], out[..., 2c+1] = b[..., c];  bwd splits. */
 int npp_interleave2_fwd(const npp_view4* a, const npp_view4* b, const npp_view4* y, int dtype,

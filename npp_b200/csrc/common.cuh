@@ -47,11 +47,22 @@ template <> struct Pack<float> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
 };
 template <> struct Pack<__nv_bfloat16> {
   static constexpr int N = 8;
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(u[i] << 16);
+      v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
     const uint32_t u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -69,6 +80,10 @@ template <> struct Pack<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
   }
 };
+
+// 16-byte raw load (kept packed in 4 registers until it is consumed: more loads in flight per thread)
+template <typename T>
+__device__ __forceinline__ uint4 ldraw(const T* p) { return *reinterpret_cast<const uint4*>(p); }
 
 // ---- view checks -------------------------------------------------------------------------------
 static inline bool view_ok(const npp_view4* v, int dtype) {

@@ -5,6 +5,7 @@ The reference issues ~4 000 kernel launches per step from Python; here the whole
 criteria, backward, gradient all-reduce and optimizer update — is captured once into a CUDA graph and
 replayed, so the host only enqueues one graph launch plus the H2D copies of the next batch.
 """
+import gc
 import types
 
 import torch
@@ -128,7 +129,13 @@ class TrainStep:
 
     def _step_body(self):
         self.opt.zero_grad(set_to_none=True)
-        pose, par = self.model(self.images)
+        F_._state["defer_bn_counters"] = counters = []  # BatchNorm num_batches_tracked += 1: one launch, not 432
+        try:
+            pose, par = self.model(self.images)
+        finally:
+            F_._state["defer_bn_counters"] = None
+        if counters:
+            torch._foreach_add_(counters, 1)
         loss_par = self.cpar(par, [self.par_lab, self.edge_lab]).unsqueeze(0)
         loss_pose = self.cpose(pose, [self.pose_gt, self.pose_aux_gt]).unsqueeze(0)
         loss = (loss_par + loss_pose).mean()
@@ -147,6 +154,7 @@ class TrainStep:
                 self._step_body()
                 self.launches_per_step = _lib.launch_count() - c0
             return
+        gc.collect()  # autograd graphs of earlier steps (AccumulateGrad nodes bound to another stream) must be gone
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -11,7 +11,7 @@ from torch.autograd import Function
 from . import _lib as L
 from ._lib import call, view, stream, fptr, i32, i64, f32, f64, ref, NULL
 
-_state = {"dtype": torch.bfloat16, "sync_bn": None}
+_state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None}
 
 
 def set_compute_dtype(dtype):
@@ -99,7 +99,10 @@ class _FromInternal(Function):
 
 
 def to_internal(x, dtype=None):
-    """NCHW fp32 (any torch layout) -> internal; internal tensors pass through."""
+    """NCHW fp32 (any torch layout) -> internal; internal tensors pass through; a Pending BatchNorm output is
+    normalised (one fused pass) and cached."""
+    if isinstance(x, Pending):
+        return finish(x)
     if is_internal(x) and (dtype is None or x.dtype == dtype):
         return x
     return _ToInternal.apply(x, dtype or _state["dtype"])
@@ -107,6 +110,7 @@ def to_internal(x, dtype=None):
 
 def from_internal(x, c=None):
     """internal -> contiguous NCHW fp32 with the first c channels (drops channel padding)."""
+    x = check_raw(to_internal(x), "from_internal")
     return _FromInternal.apply(x, int(c if c is not None else x.shape[1]))
 
 
@@ -131,13 +135,34 @@ class _ReluFn(Function):
 
 
 def relu(x):
-    """nn.ReLU; the result is cached on the input tensor so that the several primitives of a cell
-    that read the same state (each starts with its own nn.ReLU, operations.py:76,212) share one pass."""
-    y = getattr(x, "_npp_relu", None)
+    """nn.ReLU; the result is cached on the input so that the several primitives of a cell that read the same
+    state (each starts with its own nn.ReLU, operations.py:76,212) share one pass — and normally it already
+    exists: the kernel that produced the state wrote relu(state) next to it (node())."""
+    if isinstance(x, Pending):
+        if x.relu is None:
+            _, x.relu = node(x, None, want_raw=False, want_relu=True)
+        return x.relu
+    y = relu_of(x)
     if y is None:
         y = _ReluFn.apply(x)
+        y._npp_is_relu = True
         x._npp_relu = y
     return y
+
+
+def relu_of(x):
+    """relu(x) if it already exists (written by the producer of x, or x is itself a ReLU output), else None."""
+    if getattr(x, "_npp_is_relu", False):
+        return x
+    return getattr(x, "_npp_relu", None)
+
+
+def check_raw(x, what):
+    """Raises when `x` is a handle that only carries relu(state) (the producer was told nobody reads the raw
+    state) but `what` needs the raw values."""
+    if getattr(x, "_npp_relu_only", False):
+        raise RuntimeError("%s needs the raw state, but its producer only materialised relu(state)" % what)
+    return x
 
 
 # ------------------------------------------------------------------------------------------------
@@ -376,6 +401,254 @@ def batch_norm(x, stats, gamma, beta, running_mean, running_var, training, momen
     return y
 
 
+
+# ------------------------------------------------------------------------------------------------
+# fused cell node: y = f_a(a) [+ f_b(b)] with f = pending BatchNorm or identity; outputs raw and/or relu
+# ------------------------------------------------------------------------------------------------
+class Pending:
+    """The input of a BatchNorm2d whose normalisation has not been applied yet: `y` (internal tensor, usually a
+    conv output), `stats` (per-channel sum / sum of squares from the conv epilogue, or None) and the BatchNorm
+    module `bn`.  Consumers fold the normalisation into their own pass (node()); anything else calls
+    to_internal() / finish(), which applies it once and caches the result."""
+    __slots__ = ("y", "stats", "bn", "raw", "relu")
+
+    def __init__(self, y, stats, bn):
+        self.y, self.stats, self.bn = y, stats, bn
+        self.raw = self.relu = None
+
+    @property
+    def shape(self):
+        return self.y.shape
+
+
+def finish(p):
+    """Normalised (raw) value of a Pending BatchNorm output."""
+    if not isinstance(p, Pending):
+        return p
+    if p.raw is None:
+        p.raw, _ = node(p, None, want_raw=True, want_relu=False)
+    return p.raw
+
+
+def alias(buf, c_off, c):
+    """Channel slice [c_off, c_off+c) of an internal tensor as a fresh tensor on the same storage (not an
+    autograd view: the node kernels write it, autograd sees an ordinary output)."""
+    n, _, h, w = buf.shape
+    sn, sc, sh, sw = buf.stride()
+    return torch.empty(0, dtype=buf.dtype, device=buf.device).set_(
+        buf.untyped_storage(), buf.storage_offset() + c_off, (n, c, h, w), (sn, sc, sh, sw))
+
+
+class _BNSide:
+    """Per-input BatchNorm bookkeeping of one node call (forward coefficients, saved statistics)."""
+    __slots__ = ("bn", "stats", "coef", "c")
+
+
+def _bn_forward_coef(y, stats, bn, sync):
+    """Batch statistics -> (scale, shift, mean, invstd) as one [4C] tensor; updates the running statistics
+    (nn.BatchNorm2d training semantics, momentum 0.1 / eps 1e-5 in operations.py:27)."""
+    n, c, h, w = y.shape
+    dev = y.device
+    training = bn.training or not bn.track_running_stats
+    gamma = pad_vec(bn.weight.detach() if bn.weight is not None else None, c, 1.0)
+    beta = pad_vec(bn.bias.detach() if bn.bias is not None else None, c, 0.0)
+    coef = torch.empty(4 * c, dtype=torch.float32, device=dev)
+    if not training:
+        rm = pad_vec(bn.running_mean, c, 0.0).contiguous()
+        rv = pad_vec(bn.running_var, c, 1.0).contiguous()
+        call("npp_bn_eval_coef", fptr(gamma.contiguous() if gamma is not None else None),
+             fptr(beta.contiguous() if beta is not None else None), fptr(rm), fptr(rv), f32(bn.eps), fptr(coef[:c]),
+             fptr(coef[c:2 * c]), i32(c), stream())
+        if torch.is_grad_enabled():  # backward through running statistics: xhat = (x - rm) * rsqrt(rv + eps)
+            coef[2 * c:3 * c] = rm
+            coef[3 * c:] = torch.rsqrt(rv + bn.eps)
+        return coef, float(n * h * w), gamma
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        if _state["defer_bn_counters"] is not None:
+            _state["defer_bn_counters"].append(bn.num_batches_tracked)  # one foreach add per step (engine.TrainStep)
+        else:
+            bn.num_batches_tracked.add_(1)
+    if stats is None or stats.numel() == 0:
+        stats = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        call("npp_bn_stats", ref(view(y)), fptr(stats), i32(L.dtype_code(y)), stream())
+    count = float(n * h * w)
+    if sync:
+        count *= _allreduce_sum(stats)
+    c_run = bn.running_mean.numel() if bn.running_mean is not None else 0
+    call("npp_bn_finalize", fptr(stats), f64(count), fptr(gamma), fptr(beta), fptr(bn.running_mean),
+         fptr(bn.running_var), f32(bn.momentum), f32(bn.eps), fptr(coef[:c]), fptr(coef[c:2 * c]), fptr(coef[2 * c:3 * c]),
+         fptr(coef[3 * c:]), i32(c), i32(c_run), stream())
+    return coef, count, gamma
+
+
+class _NodeFn(Function):
+    """y = f_a(a) [+ f_b(b)]; f = BatchNorm(batch statistics) when the side is Pending, identity otherwise.
+    Returns (raw, relu) — either may be None.  csrc/node.cu."""
+
+    @staticmethod
+    def forward(ctx, a, ga, ba, b, gb, bb, cfg):
+        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu = cfg
+        ctx.set_materialize_grads(False)
+        n, c, h, w = a.shape
+        code = L.dtype_code(a)
+        sync = _sync_group() is not None
+        ca = cb = None
+        count = float(n * h * w)
+        gam_a = gam_b = None
+        if bn_a is not None:
+            ca, count, gam_a = _bn_forward_coef(a, st_a, bn_a, sync)
+        if bn_b is not None:
+            cb, count, gam_b = _bn_forward_coef(b, st_b, bn_b, sync)
+        raw = (out_raw if out_raw is not None else empty_internal(n, c, h, w, a.dtype, a.device)) if want_raw else None
+        rel = (out_relu if out_relu is not None else empty_internal(n, c, h, w, a.dtype, a.device)) if want_relu else None
+        call("npp_node_fwd", ref(view(a)), fptr(ca[:c]) if ca is not None else NULL,
+             fptr(ca[c:2 * c]) if ca is not None else NULL, ref(view(b)) if b is not None else NULL,
+             fptr(cb[:c]) if cb is not None else NULL, fptr(cb[c:2 * c]) if cb is not None else NULL,
+             ref(view(raw)) if raw is not None else NULL, ref(view(rel)) if rel is not None else NULL, i32(code), stream())
+        eval_a = bn_a is not None and not (bn_a.training or not bn_a.track_running_stats)
+        eval_b = bn_b is not None and not (bn_b.training or not bn_b.track_running_stats)
+        ctx.flags = (bn_a is not None, bn_b is not None, b is not None, count, sync, eval_a, eval_b)
+        ctx.save_for_backward(a if bn_a is not None else None, ca, gam_a, b if bn_b is not None else None, cb, gam_b,
+                              rel)
+        return raw, rel
+
+    @staticmethod
+    def backward(ctx, g_raw, g_relu):
+        a, ca, gam_a, b, cb, gam_b, rel = ctx.saved_tensors
+        has_a, has_b, two, count, sync, eval_a, eval_b = ctx.flags
+        if g_raw is None and g_relu is None:
+            return None, None, None, None, None, None, None
+        like = rel if rel is not None else (a if a is not None else (g_raw if g_raw is not None else g_relu))
+        if g_raw is not None:
+            g_raw = as_internal_grad(g_raw, like)
+        if g_relu is not None:
+            g_relu = as_internal_grad(g_relu, like)
+        ref_t = g_raw if g_raw is not None else g_relu
+        n, c, h, w = ref_t.shape
+        code = L.dtype_code(ref_t)
+        dev = ref_t.device
+        g = g_raw
+        need_bn = has_a or has_b
+        if g_relu is not None or need_bn:
+            if g_relu is not None:
+                g = empty_internal(n, c, h, w, ref_t.dtype, dev)
+            nq = 2 * (int(has_a) + int(has_b))
+            parts = None
+            if need_bn:
+                nblk = L.lib().npp_node_bwd_blocks(i32(n), i32(h), i32(w), i32(c), i32(code))
+                parts = torch.empty(nblk * nq * c, dtype=torch.float32, device=dev)
+            call("npp_node_bwd_reduce", ref(view(g_raw)) if g_raw is not None else NULL,
+                 ref(view(g_relu)) if g_relu is not None else NULL, ref(view(rel)) if g_relu is not None else NULL,
+                 ref(view(a)) if has_a else NULL, fptr(ca[2 * c:3 * c]) if has_a else NULL,
+                 fptr(ca[3 * c:]) if has_a else NULL, ref(view(b)) if has_b else NULL,
+                 fptr(cb[2 * c:3 * c]) if has_b else NULL, fptr(cb[3 * c:]) if has_b else NULL,
+                 ref(view(g)) if g_relu is not None else NULL, fptr(parts), i32(code), stream())
+        da = db = dga = dba = dgb = dbb = None
+        if need_bn:
+            sums = torch.empty(nq * c, dtype=torch.float32, device=dev)
+            call("npp_reduce_partials", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), stream())
+            local = sums
+            if sync:
+                local = sums.clone()  # parameter gradients stay local (the gradient all-reduce averages them)
+                _allreduce_sum(sums)
+            sa = sums[:2 * c] if has_a else None
+            sb = sums[2 * c * int(has_a):] if has_b else None
+            if eval_a or eval_b:  # running statistics do not depend on the batch: d_in = gamma * invstd * g
+                if local is sums:
+                    local = sums.clone()
+                if eval_a:
+                    sa.zero_()
+                if eval_b:
+                    sb.zero_()
+            if has_a:
+                da = torch.empty_like(a)
+                dba, dga = local[:c], local[c:2 * c]
+            if has_b:
+                db = torch.empty_like(b)
+                o = 2 * c * int(has_a)
+                dbb, dgb = local[o:o + c], local[o + c:o + 2 * c]
+            call("npp_node_bwd_apply", ref(view(g)), ref(view(a)) if has_a else NULL, fptr(gam_a) if has_a else NULL,
+                 fptr(ca[2 * c:3 * c]) if has_a else NULL, fptr(ca[3 * c:]) if has_a else NULL, fptr(sa),
+                 ref(view(da)) if has_a else NULL, ref(view(b)) if has_b else NULL, fptr(gam_b) if has_b else NULL,
+                 fptr(cb[2 * c:3 * c]) if has_b else NULL, fptr(cb[3 * c:]) if has_b else NULL, fptr(sb),
+                 ref(view(db)) if has_b else NULL, f64(count), i32(code), stream())
+        if not has_a:
+            da = g
+        if two and not has_b:
+            db = g
+        ni = ctx.needs_input_grad
+        return (da if ni[0] else None, dga if ni[1] else None, dba if ni[2] else None, db if (two and ni[3]) else None,
+                dgb if ni[4] else None, dbb if ni[5] else None, None)
+
+
+def _side(x):
+    if isinstance(x, Pending):
+        return x.y, x.bn, x.stats
+    return check_raw(x, "node"), None, None
+
+
+def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None):
+    """One fused pass for a cell node (model_augment.py:48-62): a and b are internal tensors or Pending BatchNorm
+    outputs; returns (raw, relu) — either None when not wanted — with `raw._npp_relu = relu` when both exist.
+    out_raw / out_relu: preallocated destinations (channel slices of a concat buffer, see alias())."""
+    if b is not None and not isinstance(a, Pending) and isinstance(b, Pending):
+        a, b = b, a  # keep a BatchNorm side first (the kernels take either layout; this just normalises)
+    ya, bn_a, st_a = _side(a)
+    yb, bn_b, st_b = _side(b) if b is not None else (None, None, None)
+    if yb is not None and ya.shape != yb.shape:
+        raise RuntimeError("node: shape mismatch %s vs %s" % (tuple(ya.shape), tuple(yb.shape)))
+    if not (want_raw or want_relu):
+        raise RuntimeError("node: nothing to produce")
+    c = ya.shape[1]
+
+    def affine(bn):
+        if bn is None:
+            return None, None
+        return pad_vec(bn.weight, c, 1.0), pad_vec(bn.bias, c, 0.0)
+
+    ga, ba = affine(bn_a)
+    gb, bb = affine(bn_b)
+    raw, rel = _NodeFn.apply(ya, ga, ba, yb, gb, bb, (bn_a, st_a, bn_b, st_b, bool(want_raw), bool(want_relu), out_raw,
+                                                       out_relu))
+    if rel is not None:
+        rel._npp_is_relu = True   # relu(rel) is rel (no tensor ever references itself: that would leak the graph)
+        if raw is not None:
+            raw._npp_relu = rel
+    return raw, rel
+
+
+def state_handle(raw, rel):
+    """What a cell passes on as `the state`: the raw tensor (with relu attached when it exists), or — when the
+    producer was told that every consumer starts with nn.ReLU — relu(state) flagged so that any raw use raises."""
+    if raw is not None:
+        return raw
+    h = rel.detach()          # a distinct handle on the same storage; its only legitimate use is relu(h) -> rel
+    h._npp_relu = rel
+    h._npp_relu_only = True
+    return h
+
+
+class _AssembleFn(Function):
+    """The concat buffer whose channel slices the node kernels have already written (torch.cat of
+    model_augment.py:62 without a copy); backward hands the gradient out as channel slices."""
+
+    @staticmethod
+    def forward(ctx, holder, *slices):
+        ctx.cs = [t.shape[1] for t in slices]
+        return holder[0]
+
+    @staticmethod
+    def backward(ctx, dy):
+        outs, off = [None], 0
+        for c in ctx.cs:
+            outs.append(dy[:, off:off + c])
+            off += c
+        return tuple(outs)
+
+
+def assemble(buf, slices):
+    return _AssembleFn.apply([buf], *slices)
+
 # ------------------------------------------------------------------------------------------------
 # add / concat
 # ------------------------------------------------------------------------------------------------
@@ -392,6 +665,11 @@ class _AddFn(Function):
 
 
 def add(a, b):
+    """a + b where either side may still be a Pending BatchNorm output (normalised inside the same pass)."""
+    if isinstance(a, Pending) or isinstance(b, Pending):
+        return node(a, b)[0]
+    check_raw(a, "add")
+    check_raw(b, "add")
     if a.shape != b.shape:
         raise RuntimeError("add: shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
     return _AddFn.apply(a, b)
@@ -422,10 +700,24 @@ class _CatFn(Function):
 
 def cat(ts):
     """torch.cat(dim=1) of internal tensors (model_augment.py:62); backward hands out channel slices."""
-    ts = list(ts)
+    ts = [check_raw(to_internal(t), "cat") for t in ts]
     if len(ts) == 1:
         return ts[0]
     return _CatFn.apply(*ts)
+
+
+def cat_relu(ts):
+    """relu(torch.cat(ts, dim=1)) written directly (one pass per input, no intermediate concat); returns a state
+    handle that only ReLU-first consumers may read."""
+    ts = [check_raw(to_internal(t), "cat") for t in ts]
+    n, _, h, w = ts[0].shape
+    buf = empty_internal(n, sum(t.shape[1] for t in ts), h, w, ts[0].dtype, ts[0].device)
+    outs, off = [], 0
+    for t in ts:
+        c = t.shape[1]
+        outs.append(node(t, None, want_raw=False, want_relu=True, out_relu=alias(buf, off, c))[1])
+        off += c
+    return state_handle(None, assemble(buf, outs))
 
 
 # ------------------------------------------------------------------------------------------------

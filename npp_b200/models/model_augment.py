@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as F_
-from ..nn import BatchNorm2d, Conv2d, ReLU, Sequential
+from ..nn import BatchNorm2d, Conv2d, ReLU, Sequential, call_lazy
 from . import genotypes as gt
 from .operations import OPS, FactorizedReduce, ReLUConvBN
 
@@ -68,12 +68,102 @@ class _StepCell(nn.Module):
     def _stride_for(self, index):
         return 1
 
+    # Which of {state, relu(state)} the cell's output concat(s) carry is chosen per call: `cell(s0, s1)` returns the
+    # raw concat like the reference; Network.forward passes out_raw / out_relu when it knows that the consumers start
+    # with nn.ReLU (cells feeding only preprocess layers / heads), so the raw concat is never written.
+
     def _run_steps(self, states):
+        """Plain evaluation (one tensor per state)."""
         for i in range(self._steps):
             a = self._ops[2 * i](states[self._indices[2 * i]])
             b = self._ops[2 * i + 1](states[self._indices[2 * i + 1]])
             states.append(F_.add(a, b))
         return states
+
+    @staticmethod
+    def _kind(op):
+        k = getattr(op, "input_kind", None)
+        if k is None and isinstance(op, nn.Sequential) and len(op) > 0:
+            return _StepCell._kind(op[0])
+        return k or "raw"
+
+    def _needs(self, nstates, concats, out_raw=True, out_relu=False):
+        """Per state: (raw needed, relu needed, (concat id, slot) or None) from the primitives that read it and
+        from its concat membership."""
+        kinds = [set() for _ in range(nstates)]
+        for op, idx in zip(self._ops, self._indices):
+            kinds[idx].add(self._kind(op))
+        member = {}
+        for cid, cat in enumerate(concats):
+            for slot, k in enumerate(cat):
+                if k in member:
+                    return None  # a state in two concats: not expressible as slices, use the plain path
+                member[k] = (cid, slot)
+        out = []
+        for k in range(nstates):
+            raw = "raw" in kinds[k] or (k in member and out_raw)
+            rel = "relu" in kinds[k] or (k in member and out_relu)
+            if "relu_ok" in kinds[k] and not rel:
+                raw = True  # the depthwise kernel applies the ReLU inside its own loads
+            if not (raw or rel):
+                raw = True
+            out.append((raw, rel, member.get(k)))
+        return out
+
+    def _run_fused(self, pre, concats, out_raw=True, out_relu=False):
+        """Evaluates the cell with one fused pass per state (functional.node): BatchNorm-apply of both operands,
+        the add, the ReLU of the consumers and the write into the output concat buffer(s).
+        pre: outputs of the preprocess layers (Pending BatchNorm outputs); returns one handle per concat."""
+        nstates = len(pre) + self._steps
+        if not (out_raw or out_relu):
+            raise ValueError("a cell must produce its output raw, through ReLU, or both")
+        needs = self._needs(nstates, concats, out_raw, out_relu)
+        if needs is None:
+            states = self._run_steps([F_.finish(p) for p in pre])
+            return [F_.cat([states[i] for i in cat]) for cat in concats]
+        bufs = {}      # (concat id, "raw" | "relu") -> buffer
+        slices = {}    # same key -> list of slice tensors in slot order
+        handles = []
+
+        def emit(k, a, b):
+            raw_w, rel_w, mem = needs[k]
+            ya = a.y if isinstance(a, F_.Pending) else a
+            n, c, h, w = ya.shape
+            o_raw = o_rel = None
+            if mem is not None:
+                cid, slot = mem
+                for key, wanted in (("raw", raw_w and out_raw), ("relu", rel_w and out_relu)):
+                    if not wanted:
+                        continue
+                    if (cid, key) not in bufs:
+                        bufs[(cid, key)] = F_.empty_internal(n, c * len(concats[cid]), h, w, ya.dtype, ya.device)
+                        slices[(cid, key)] = [None] * len(concats[cid])
+                    t = F_.alias(bufs[(cid, key)], slot * c, c)
+                    if key == "raw":
+                        o_raw = t
+                    else:
+                        o_rel = t
+            raw, rel = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel)
+            if o_raw is not None:
+                slices[(mem[0], "raw")][mem[1]] = raw
+            if o_rel is not None:
+                slices[(mem[0], "relu")][mem[1]] = rel
+            handles.append(F_.state_handle(raw, rel))
+
+        for k, p in enumerate(pre):
+            emit(k, p, None)
+        for i in range(self._steps):
+            a = call_lazy(self._ops[2 * i], handles[self._indices[2 * i]])
+            b = call_lazy(self._ops[2 * i + 1], handles[self._indices[2 * i + 1]])
+            emit(len(pre) + i, a, b)
+        outs = []
+        for cid in range(len(concats)):
+            raw = F_.assemble(bufs[(cid, "raw")], slices[(cid, "raw")]) if (cid, "raw") in bufs else None
+            rel = F_.assemble(bufs[(cid, "relu")], slices[(cid, "relu")]) if (cid, "relu") in bufs else None
+            if raw is not None and rel is not None:
+                raw._npp_relu = rel
+            outs.append(F_.state_handle(raw, rel))
+        return outs
 
 
 class Cell(_StepCell):
@@ -98,9 +188,9 @@ class Cell(_StepCell):
     def _stride_for(self, index):
         return 2 if self._reduction and index < 2 else 1
 
-    def forward(self, s0, s1):
-        states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1)])
-        return F_.cat([states[i] for i in self._concat])
+    def forward(self, s0, s1, out_raw=True, out_relu=False):
+        return self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1)],
+                               [list(self._concat)], out_raw, out_relu)[0]
 
 
 class Upsample(_StepCell):
@@ -116,9 +206,9 @@ class Upsample(_StepCell):
         self._build_ops(C_prev // 4, upsample,
                         wrap=lambda op, index: Sequential(op, Interpolate(scale_factor=2)) if index == 0 else op)
 
-    def forward(self, s0, s1):
-        states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1)])
-        return F_.cat([states[i] for i in self._concat])
+    def forward(self, s0, s1, out_raw=True, out_relu=False):
+        return self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1)],
+                               [list(self._concat)], out_raw, out_relu)[0]
 
 
 class _FusionCell(_StepCell):
@@ -147,12 +237,16 @@ class _FusionCell(_StepCell):
 
         self._build_ops(C_cur, edges, wrap=wrap)
 
-    def forward(self, s0, s1, s2):
-        states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1), self.preprocess2(s2)])
-        if self.order == 0:  # model_augment.py:164-166: default-mode (nearest) F.interpolate
+    def forward(self, s0, s1, s2, out_raw=True, out_relu=False):
+        if self.order == 0:  # model_augment.py:164-166: default-mode (nearest) F.interpolate; unused by Network
+            states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1), self.preprocess2(s2)])
             states[0] = F_.interpolate(states[0], scale_factor=4)
             states[1] = F_.interpolate(states[1], scale_factor=2)
-        return F_.cat(states[0:3]), F_.cat([states[i] for i in self._concat])
+            return F_.cat(states[0:3]), F_.cat([states[i] for i in self._concat])
+        fea1, fea2 = self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1),
+                                      call_lazy(self.preprocess2, s2)], [[0, 1, 2], list(self._concat)],
+                                     out_raw, out_relu)
+        return fea1, fea2
 
 
 class PoseCell1(_FusionCell):
@@ -323,7 +417,7 @@ class Network(nn.Module):
         """sum_j ops[cursor+j](feats[idx[j]]) — the cross-task message (:429-436)."""
         z = None
         for j, src in enumerate(idx):
-            y = ops[cursor + j](feats[src])
+            y = call_lazy(ops[cursor + j], feats[src])
             z = y if z is None else F_.add(z, y)
         return z, cursor + len(idx)
 
@@ -336,16 +430,19 @@ class Network(nn.Module):
         f1, f2 = [], []           # per-stream feature pyramids (fine -> coarse, then decoder outputs)
         c1 = c2 = stage = 0
         for i, (cell1, cell2) in enumerate(zip(self.cells1, self.cells2)):
-            s0, s1 = s1, cell1(s0, s1)
-            s2, s3 = s3, cell2(s2, s3)
+            # every encoder cell feeds the next two cells' preprocess layers (nn.ReLU first); only the tapped ones
+            # are also read raw (interaction ops, decoder, multi-scale concat)
+            tap = i in self._tap_layers
+            s0, s1 = s1, cell1(s0, s1, out_raw=tap, out_relu=True)
+            s2, s3 = s3, cell2(s2, s3, out_raw=tap, out_relu=True)
             if i in self._tap_layers:
                 f1.append(s1)
                 f2.append(s3)
                 z1, c1 = self._exchange(self._ops1, c1, self._indices1[stage], f2)
                 z2, c2 = self._exchange(self._ops2, c2, self._indices2[stage], f1)
                 stage += 1
-                s1 = F_.add(s1, z1)
-                s3 = F_.add(s3, z2)
+                s1 = F_.node(s1, z1, want_raw=True, want_relu=True)[0]  # read raw (f1) and through nn.ReLU (cells)
+                s3 = F_.node(s3, z2, want_raw=True, want_relu=True)[0]
                 f1[-1], f2[-1] = s1, s3
 
         # decoder: three upsample cells per stream with interaction after each (:453-533)
@@ -358,21 +455,23 @@ class Network(nn.Module):
             f2.append(o2)
             z1, c1 = self._exchange(self.up_ops1, c1, self.up_indices1[d], f2)
             z2, c2 = self._exchange(self.up_ops2, c2, self.up_indices2[d], f1)
-            o1 = F_.add(o1, z1)
-            o2 = F_.add(o2, z2)
+            o1 = F_.node(o1, z1, want_raw=True, want_relu=True)[0]
+            o2 = F_.node(o2, z2, want_raw=True, want_relu=True)[0]
             f1[-1], f2[-1] = o1, o2
             prev1, prev2 = o1, o2
 
-        def pyramid(f):  # (:538-543)
-            return F_.cat([f[0], f[6],
-                           F_.interpolate(f[5], scale_factor=2, mode="bilinear", align_corners=True),
-                           F_.interpolate(f[4], scale_factor=4, mode="bilinear", align_corners=True)])
+        def pyramid(f):  # (:538-543); only read through the nn.ReLU of the four 1x1 layers: relu(cat) is written directly
+            return F_.cat_relu([f[0], f[6],
+                                F_.interpolate(f[5], scale_factor=2, mode="bilinear", align_corners=True),
+                                F_.interpolate(f[4], scale_factor=4, mode="bilinear", align_corners=True)])
 
         x1, x2 = pyramid(f1), pyramid(f2)
-        in1 = self.pose_auxlayer(x1)
-        in2 = self.edge_layer(x2)
-        in3 = self.pose_layer(x1)
-        in4 = self.par_layer(x2)
+        # Pending BatchNorm outputs: the heads and refinement cells all start with nn.ReLU, so relu(bn(.)) is
+        # produced once per tensor and the raw values are never materialised
+        in1 = self.pose_auxlayer.lazy(x1)
+        in2 = self.edge_layer.lazy(x2)
+        in3 = self.pose_layer.lazy(x1)
+        in4 = self.par_layer.lazy(x2)
 
         pose_list, par_list = [], []
 
@@ -387,8 +486,9 @@ class Network(nn.Module):
         emit(0)
         for i in range(1, self.refine_layers + 1):
             for j in range(3):
-                in1, tmp = self.pose_net[2 * (i - 1) + j](in1, in3, in4)
-                in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4)
+                # refinement-cell outputs are read by preprocess layers and heads only (nn.ReLU first)
+                in1, tmp = self.pose_net[2 * (i - 1) + j](in1, in3, in4, out_raw=False, out_relu=True)
+                in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4, out_raw=False, out_relu=True)
                 in3 = tmp
             emit(i)
         return pose_list, par_list

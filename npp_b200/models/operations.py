@@ -9,7 +9,12 @@ primitive follows the cited reference lines; the execution is ours (npp_b200.nn 
 import torch.nn as nn
 
 from .. import functional as F_
-from ..nn import AvgPool2d, BatchNorm2d, Conv2d, MaxPool2d, ReLU, Sequential, UpsamplingBilinear2d
+from ..nn import AvgPool2d, BatchNorm2d, Conv2d, MaxPool2d, ReLU, Sequential, UpsamplingBilinear2d, call_lazy
+
+# What a primitive reads from the state it is applied to (used by the cells to decide which of {state, relu(state)}
+# the producing node kernel must write):  "relu" = starts with nn.ReLU feeding a dense conv (operations.py:76,95,146),
+# "relu_ok" = starts with nn.ReLU feeding a depthwise conv, which can also apply the ReLU inside its own loads,
+# "raw" = reads the state itself.
 
 BN_MOMENTUM = 0.1  # operations.py:27
 
@@ -48,6 +53,7 @@ def _bn(C, affine=True):
 
 class Zero(nn.Module):
     """x * 0 (strided subsample first when stride > 1) — operations.py:31-41."""
+    input_kind = "raw"
 
     def __init__(self, stride):
         super().__init__()
@@ -61,6 +67,8 @@ class Zero(nn.Module):
 
 
 class Identity(nn.Module):
+    input_kind = "raw"
+
     def forward(self, x):
         return x
 
@@ -79,17 +87,27 @@ class PoolBN(nn.Module):
             raise ValueError(pool_type)
         self.bn = _bn(C, affine)
 
+    input_kind = "raw"
+
+    def lazy(self, x):
+        return self.bn.pending(self.pool(F_.check_raw(F_.to_internal(x), "pool")))
+
     def forward(self, x):
-        return self.bn(self.pool(x))
+        return F_.finish(self.lazy(x))
 
 
 class _ReLUConvBNBase(nn.Module):
+    input_kind = "relu"
+
     def __init__(self, C_in, C_out, kernel_size, stride, padding, dilation=1, affine=True):
         super().__init__()
         self.net = Sequential(
             ReLU(),
             Conv2d(C_in, C_out, kernel_size, stride, padding, dilation=dilation, bias=False),
             _bn(C_out, affine))
+
+    def lazy(self, x):
+        return self.net.lazy(x)
 
     def forward(self, x):
         return self.net(x)
@@ -124,6 +142,11 @@ class DilConvS(nn.Module):
             Conv2d(C_in, C_out, 1, stride=1, padding=0, bias=False),
             _bn(C_out, affine))
 
+    input_kind = "relu_ok"
+
+    def lazy(self, x):
+        return self.net.lazy(x)
+
     def forward(self, x):
         return self.net(x)
 
@@ -136,6 +159,11 @@ class Sep_Conv(nn.Module):
         self.net = Sequential(
             DilConvS(C_in, C_in, kernel_size, stride, padding, dilation=1, affine=affine),
             DilConvS(C_in, C_out, kernel_size, 1, padding, dilation=1, affine=affine))
+
+    input_kind = "relu_ok"
+
+    def lazy(self, x):
+        return self.net.lazy(x)
 
     def forward(self, x):
         return self.net(x)
@@ -156,12 +184,17 @@ class SE_Block(nn.Module):
         self.pool2 = AvgPool2d(2)
         self.bn = BatchNorm2d(C_in, momentum=BN_MOMENTUM)
 
-    def forward(self, x):
-        x = F_.to_internal(x)
+    input_kind = "raw"
+
+    def lazy(self, x):
+        x = F_.check_raw(F_.to_internal(x), "se_connect")
         out = F_.se_scale(x, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias)
         if self.stride == 1:
             return out
-        return self.bn(self.pool2(out))
+        return self.bn.pending(self.pool2(out))
+
+    def forward(self, x):
+        return F_.finish(self.lazy(x))
 
 
 class FactorizedReduce(nn.Module):
@@ -176,11 +209,16 @@ class FactorizedReduce(nn.Module):
         self.conv2 = Conv2d(C_in, C_out // 2, 1, stride=2, padding=0, bias=False)
         self.bn = _bn(C_out, affine)
 
-    def forward(self, x):
+    input_kind = "relu"
+
+    def lazy(self, x):
         x = self.relu(x)
         a, _ = self.conv1.run(x)
         b, _ = self.conv2.run(x, hoff=1, woff=1)
-        return self.bn(F_.cat([a, b]))
+        return self.bn.pending(F_.cat([a, b]))
+
+    def forward(self, x):
+        return F_.finish(self.lazy(x))
 
 
 class Pooled_Conv(nn.Module):
@@ -196,6 +234,11 @@ class Pooled_Conv(nn.Module):
         if conv_nums == 2 and stride == 2:
             layers.append(UpsamplingBilinear2d(scale_factor=2))
         self.net = Sequential(*layers)
+
+    input_kind = "raw"
+
+    def lazy(self, x):
+        return self.net.lazy(F_.check_raw(F_.to_internal(x), "poled_conv"))
 
     def forward(self, x):
         return self.net(x)

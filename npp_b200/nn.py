@@ -23,7 +23,7 @@ class ReLU(nn.Module):
         self.inplace = inplace  # kept for repr parity; kernels are out-of-place
 
     def forward(self, x):
-        return F_.relu(F_.to_internal(x))
+        return F_.relu(x if isinstance(x, F_.Pending) else F_.to_internal(x))
 
 
 class Conv2d(nn.Conv2d):
@@ -42,16 +42,25 @@ class Conv2d(nn.Conv2d):
 
     def run(self, x, relu_in=False, want_stats=False, hoff=0, woff=0):
         self._check()
+        if isinstance(x, F_.Pending) and relu_in:
+            x, relu_in = F_.relu(x), False   # one pass writes relu(bn(.)); nothing else reads the raw value
         x = F_.to_internal(x)
         if self.is_depthwise:
             if self.bias is not None or hoff or woff:
                 raise RuntimeError("depthwise conv with bias/offset is not implemented")
+            r = F_.relu_of(x)
+            if relu_in and r is not None:   # the producer already wrote relu(x): read that, no mask needed
+                x, relu_in = r, False
+            elif not relu_in:
+                F_.check_raw(x, "depthwise conv")
             y = F_.dwconv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0], relu_in)
             return y, None
         if self.groups != 1:
             raise RuntimeError("grouped convolution (groups=%d) is not implemented" % self.groups)
         if relu_in:
             x = F_.relu(x)
+        else:
+            F_.check_raw(x, "conv")
         y, stats = F_.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], self.dilation[0], hoff, woff,
                              want_stats)
         return y, (stats if stats.numel() else None)
@@ -89,13 +98,13 @@ class BatchNorm2d(nn.Module):
     def extra_repr(self):
         return "{num_features}, eps={eps}, momentum={momentum}, affine={affine}".format(**self.__dict__)
 
-    def run(self, x, stats=None, relu=False, residual=None):
-        x = F_.to_internal(x)
-        training = self.training or not self.track_running_stats
-        if training and self.track_running_stats and self.num_batches_tracked is not None:
-            self.num_batches_tracked.add_(1)
-        return F_.batch_norm(x, stats, self.weight, self.bias, self.running_mean, self.running_var, training,
-                             self.momentum, self.eps, relu=relu, residual=residual)
+    def pending(self, x, stats=None):
+        """The not-yet-normalised output: consumers (functional.node) fold scale/shift into their own pass."""
+        return F_.Pending(F_.check_raw(F_.to_internal(x), "BatchNorm2d"), stats, self)
+
+    def run(self, x, stats=None, relu=False):
+        p = self.pending(x, stats)
+        return F_.relu(p) if relu else F_.finish(p)
 
     def forward(self, x):
         return self.run(x)
@@ -140,9 +149,14 @@ class UpsamplingBilinear2d(nn.Module):
 
 
 class Sequential(nn.Sequential):
-    """nn.Sequential whose forward fuses neighbouring leaves (see module docstring)."""
+    """nn.Sequential whose forward fuses neighbouring leaves (see module docstring).  `lazy(x)` is the same
+    chain but may return a functional.Pending when it ends in a BatchNorm2d, so that the caller (a cell node)
+    applies the normalisation inside its own pass; `forward(x)` always returns a tensor."""
 
     def forward(self, x):
+        return F_.finish(self.lazy(x))
+
+    def lazy(self, x):
         mods = list(self)
         i, n = 0, len(mods)
         while i < n:
@@ -158,10 +172,19 @@ class Sequential(nn.Sequential):
                 x, i = _maybe_bn(mods, i, x, stats)
             elif isinstance(m, BatchNorm2d):
                 x, i = _maybe_bn(mods, i, x, None)
+            elif isinstance(m, ReLU):
+                x = F_.relu(x)
+                i += 1
             else:
-                x = m(x)
+                x = call_lazy(m, x)
                 i += 1
         return x
+
+
+def call_lazy(m, x):
+    """m(x), allowing a Pending BatchNorm output where the module supports it."""
+    f = getattr(m, "lazy", None)
+    return f(x) if f is not None else m(x)
 
 
 def _bn_follows(mods, i):
@@ -170,7 +193,8 @@ def _bn_follows(mods, i):
 
 def _maybe_bn(mods, i, x, stats):
     if i < len(mods) and isinstance(mods[i], BatchNorm2d):
-        relu = i + 1 < len(mods) and isinstance(mods[i + 1], ReLU)
-        x = mods[i].run(x, stats=stats, relu=relu)
-        i += 2 if relu else 1
+        p = mods[i].pending(x, stats)
+        if i + 1 < len(mods) and isinstance(mods[i + 1], ReLU) and i + 2 < len(mods):
+            return F_.relu(p), i + 2   # BN -> ReLU -> more layers: one pass writes relu(bn(x)) only
+        return p, i + 1
     return x, i
