@@ -355,6 +355,48 @@ int npp_interleave2_fwd(const npp_view4* a, const npp_view4* b, const npp_view4*
 int npp_interleave2_bwd(const npp_view4* dy, const npp_view4* da, const npp_view4* db,
                         int dtype, npp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Search supernet: MixedOp weighted sum and beta-weighted node sums (csrc/mix.cu).
+ * models/model_search_interact.py:56-74 MixedOp.forward: temp1 = sum_k w_k*op_k(x[:, :C/2]);
+ * ans = channel_shuffle(cat(temp1, x[:, C/2:]), 2), i.e. ans[2c] = temp1[c], ans[2c+1] = x[C/2+c];
+ * :352-356, :648-654 node sums  s = base + sum_j beta_j * MixedOp_j(h_j, alpha_j).
+ * A branch is either a plain tensor or the not-yet-normalised input of a BatchNorm2d (every
+ * candidate primitive ends in one, operations.py:61,79,215,240; model_search_interact.py:48-49)
+ * described by scale/shift (forward) and mean/invstd/gamma (backward).
+ *   mix_fwd:        out[.., c] = sum_k w[k]*(y_k*scale_k + shift_k)[c]; with desc.interleave the
+ *                   output has 2C channels: out[.., 2c] = that sum, out[.., 2c+1] = pass[.., c].
+ *                   w: device fp32 [k] (NULL = all ones: plain n-ary sum).
+ *   mix_bwd_reduce: per-block partials [blocks][k+1][C] of S_0 = sum g and S_{1+k} = sum g*xhat_k
+ *                   (BatchNorm branch) / sum g*y_k (plain); g = dout[.., 2c] when interleaved;
+ *                   blocks = npp_node_bwd_blocks(n,h,w,C,dtype); fold with npp_reduce_partials.
+ *   mix_dw:         dw[k] = sum_c gamma_k[c]*S_{1+k}[c] + beta_k[c]*S_0[c]  (= <g, branch_k>, the
+ *                   architecture-weight gradient); beta: host array of k device pointers or NULL.
+ *   mix_bwd_apply:  desc.dy[k] = w[k]*gamma_k*invstd_k*(g - S_0/count - xhat_k*S_{1+k}/count)
+ *                   (BatchNorm) or w[k]*g (plain) for every k with dy[k].ptr != NULL, and
+ *                   dpass = dout[.., 2c+1]; sums = [k+1][C] (all-reduced over ranks for SyncBN).
+ * ---------------------------------------------------------------------------------------- */
+#define NPP_MIX_MAX 8
+typedef struct {
+  int32_t k;          /* number of branches, 1..NPP_MIX_MAX */
+  int32_t interleave; /* 1: the mixed half is interleaved with a pass-through half */
+  npp_view4 y[NPP_MIX_MAX];
+  const float* scale[NPP_MIX_MAX]; /* forward:  NULL = plain branch */
+  const float* shift[NPP_MIX_MAX];
+  const float* mean[NPP_MIX_MAX];  /* backward: NULL = plain branch */
+  const float* invstd[NPP_MIX_MAX];
+  const float* gamma[NPP_MIX_MAX]; /* backward: NULL = 1 */
+  npp_view4 dy[NPP_MIX_MAX];       /* backward outputs; ptr NULL = not wanted */
+} npp_mix_desc;
+
+int npp_mix_fwd(const npp_mix_desc* d, const float* w, const npp_view4* pass, const npp_view4* out,
+                int dtype, npp_stream_t stream);
+int npp_mix_bwd_reduce(const npp_mix_desc* d, const npp_view4* g, float* partials, int dtype,
+                       npp_stream_t stream);
+int npp_mix_dw(const npp_mix_desc* d, const float* sums, const float* const* beta, float* dw,
+               npp_stream_t stream);
+int npp_mix_bwd_apply(const npp_mix_desc* d, const npp_view4* g, const float* w, const float* sums,
+                      double count, const npp_view4* dpass, int dtype, npp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,17 @@ class View4(ctypes.Structure):
                 ("c", ctypes.c_int32), ("sn", ctypes.c_int64), ("sh", ctypes.c_int64), ("sw", ctypes.c_int64)]
 
 
+NPP_MIX_MAX = 8
+
+
+class MixDesc(ctypes.Structure):
+    """Mirror of `npp_mix_desc` (include/npp_b200.h)."""
+    _fields_ = [("k", ctypes.c_int32), ("interleave", ctypes.c_int32), ("y", View4 * NPP_MIX_MAX),
+                ("scale", ctypes.c_void_p * NPP_MIX_MAX), ("shift", ctypes.c_void_p * NPP_MIX_MAX),
+                ("mean", ctypes.c_void_p * NPP_MIX_MAX), ("invstd", ctypes.c_void_p * NPP_MIX_MAX),
+                ("gamma", ctypes.c_void_p * NPP_MIX_MAX), ("dy", View4 * NPP_MIX_MAX)]
+
+
 _lib = None
 
 

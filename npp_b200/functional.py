@@ -909,3 +909,241 @@ class _ZeroFn(Function):
 def zeros_like_internal(x):
     """`x * 0.` of the Zero primitive (operations.py:31-41): zero output, zero gradient."""
     return _ZeroFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# search supernet: weighted n-ary sums (MixedOp, beta-weighted nodes), fan-out, channel halves   (csrc/mix.cu)
+# ------------------------------------------------------------------------------------------------
+MIX_MAX = L.NPP_MIX_MAX
+
+
+def _mix_desc(ys, interleave):
+    d = L.MixDesc()
+    d.k = len(ys)
+    d.interleave = int(bool(interleave))
+    for j, y in enumerate(ys):
+        d.y[j] = view(y)
+    return d
+
+
+class _MixFn(Function):
+    """out = sum_k w[k] * f_k(y_k), f_k = BatchNorm(batch statistics, affine=False) for Pending branches, identity
+    otherwise; with `pass_` the result is interleaved with it (cat + channel_shuffle(2),
+    model_search_interact.py:70-71).  Gradients: d w (the architecture weights), d pass, d y_k."""
+
+    @staticmethod
+    def forward(ctx, wts, pass_, cfg, *ys):
+        bns, stats = cfg
+        ctx.set_materialize_grads(False)
+        k = len(ys)
+        n, c, h, w = ys[0].shape
+        code = L.dtype_code(ys[0])
+        dev = ys[0].device
+        sync = _sync_group() is not None
+        interleave = pass_ is not None
+        count = float(n * h * w)
+        coefs = []
+        for y, bn, st in zip(ys, bns, stats):
+            if bn is None:
+                coefs.append(None)
+            else:
+                cf, count, _ = _bn_forward_coef(y, st, bn, sync)
+                coefs.append(cf)
+        d = _mix_desc(ys, interleave)
+        for j, cf in enumerate(coefs):
+            if cf is not None:
+                d.scale[j] = cf[:c].data_ptr()
+                d.shift[j] = cf[c:2 * c].data_ptr()
+        out = empty_internal(n, 2 * c if interleave else c, h, w, ys[0].dtype, dev)
+        wv = wts.detach().float().contiguous() if wts is not None else None
+        call("npp_mix_fwd", ref(d), fptr(wv), ref(view(pass_)) if interleave else NULL, ref(view(out)), i32(code),
+             stream())
+        ctx.meta = (k, interleave, count, sync, [cf is not None for cf in coefs], wts is not None,
+                    pass_.shape if interleave else None)
+        ctx.save_for_backward(wv, *ys, *[cf for cf in coefs if cf is not None])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k, interleave, count, sync, is_bn, has_w, pass_shape = ctx.meta
+        none = (None,) * (3 + k)
+        if g is None:
+            return none
+        saved = ctx.saved_tensors
+        wv, ys, cfs = saved[0], saved[1:1 + k], list(saved[1 + k:])
+        coefs = [cfs.pop(0) if b else None for b in is_bn]
+        n, c, h, w = ys[0].shape
+        code = L.dtype_code(ys[0])
+        dev = ys[0].device
+        g = as_internal_grad(g, ys[0])
+        ni = ctx.needs_input_grad
+        d = _mix_desc(ys, interleave)
+        for j, cf in enumerate(coefs):
+            if cf is not None:
+                d.mean[j] = cf[2 * c:3 * c].data_ptr()
+                d.invstd[j] = cf[3 * c:].data_ptr()
+        nblk = L.lib().npp_node_bwd_blocks(i32(n), i32(h), i32(w), i32(c), i32(code))
+        parts = torch.empty(nblk * (k + 1) * c, dtype=torch.float32, device=dev)
+        call("npp_mix_bwd_reduce", ref(d), ref(view(g)), fptr(parts), i32(code), stream())
+        sums = torch.empty((k + 1) * c, dtype=torch.float32, device=dev)
+        call("npp_reduce_partials", fptr(parts), i32(nblk), i32((k + 1) * c), fptr(sums), stream())
+        dw = None
+        if has_w and ni[0]:
+            dw = torch.empty(k, dtype=torch.float32, device=dev)
+            call("npp_mix_dw", ref(d), fptr(sums), NULL, fptr(dw), stream())   # from the LOCAL sums (DDP averages them)
+        if sync and any(is_bn):
+            _allreduce_sum(sums)
+        dys = []
+        keep = []
+        for j in range(k):
+            if ni[3 + j]:
+                t = torch.empty_like(ys[j])
+                d.dy[j] = view(t)
+                dys.append(t)
+            else:
+                dys.append(None)
+        dpass = None
+        if interleave and ni[1]:
+            dpass = empty_internal(pass_shape[0], pass_shape[1], pass_shape[2], pass_shape[3], ys[0].dtype, dev)
+        call("npp_mix_bwd_apply", ref(d), ref(view(g)), fptr(wv), fptr(sums), f64(count),
+             ref(view(dpass)) if dpass is not None else NULL, i32(code), stream())
+        del keep
+        return (dw, dpass, None) + tuple(dys)
+
+
+def mix(branches, weights=None, pass_=None):
+    """sum_k weights[k] * branch_k  (branch: internal tensor or Pending BatchNorm output), optionally interleaved
+    channel-wise with `pass_` (out[2c] = sum, out[2c+1] = pass_[c]).  weights: 1-D fp32 device tensor or None (ones)."""
+    if not 1 <= len(branches) <= MIX_MAX:
+        raise RuntimeError("mix: between 1 and %d branches, got %d" % (MIX_MAX, len(branches)))
+    ys, bns, stats = [], [], []
+    for b in branches:
+        if isinstance(b, Pending):
+            bn = b.bn
+            if bn.affine or not (bn.training or not bn.track_running_stats):
+                b = finish(b)       # affine / eval-mode BatchNorm: normalised in its own pass
+        if isinstance(b, Pending):
+            ys.append(b.y), bns.append(b.bn), stats.append(b.stats)
+        else:
+            ys.append(check_raw(to_internal(b), "mix")), bns.append(None), stats.append(None)
+    for y in ys[1:]:
+        if y.shape != ys[0].shape:
+            raise RuntimeError("mix: shape mismatch %s vs %s" % (tuple(y.shape), tuple(ys[0].shape)))
+    if weights is not None and (weights.dim() != 1 or weights.numel() != len(ys)):
+        raise RuntimeError("mix: need one weight per branch")
+    if pass_ is not None and tuple(pass_.shape) != tuple(ys[0].shape):
+        raise RuntimeError("mix: pass-through half has shape %s, branches %s" % (tuple(pass_.shape), tuple(ys[0].shape)))
+    return _MixFn.apply(weights, pass_, (bns, stats), *ys)
+
+
+def sum_n(ts):
+    """Plain sum of internal tensors in one pass (groups of MIX_MAX)."""
+    ts = list(ts)
+    while len(ts) > 1:
+        ts = [mix(ts[:MIX_MAX])] + ts[MIX_MAX:]
+    return ts[0]
+
+
+class _SplitFanFn(Function):
+    """x -> (n_lo aliases of x[:, :C/2], x[:, C/2:]) without copies (MixedOp's xtemp / xtemp2,
+    model_search_interact.py:59-60; xtemp is read by every candidate primitive).  Backward: the n_lo gradients are
+    summed in ONE pass straight into the low half of dx, the high half is copied next to it."""
+
+    @staticmethod
+    def forward(ctx, x, n_lo):
+        ctx.set_materialize_grads(False)
+        c = x.shape[1]
+        ctx.shape, ctx.dtype = tuple(x.shape), x.dtype
+        return tuple(alias(x, 0, c // 2) for _ in range(n_lo)) + (alias(x, c // 2, c // 2),)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        n, c, h, w = ctx.shape
+        los = [g for g in gs[:-1] if g is not None]
+        hi = gs[-1]
+        if not los and hi is None:
+            return None, None
+        ref_t = los[0] if los else hi
+        dx = empty_internal(n, c, h, w, ctx.dtype, ref_t.device)
+        code = L.dtype_code(dx)
+        lo_v, hi_v = alias(dx, 0, c // 2), alias(dx, c // 2, c // 2)
+        if los:
+            los = [as_internal_grad(g, dx) for g in los]
+            while len(los) > MIX_MAX:
+                los = [sum_n(los[:MIX_MAX])] + los[MIX_MAX:]
+            d = _mix_desc(los, False)
+            call("npp_mix_fwd", ref(d), NULL, NULL, ref(view(lo_v)), i32(code), stream())
+        else:
+            call("npp_fill_zero", ref(view(lo_v)), i32(code), stream())
+        if hi is not None:
+            call("npp_add", ref(view(as_internal_grad(hi, dx))), NULL, ref(view(hi_v)), i32(code), stream())
+        else:
+            call("npp_fill_zero", ref(view(hi_v)), i32(code), stream())
+        return dx, None
+
+
+def split_halves(x, n_lo=1):
+    """([n_lo handles on x[:, :C/2]], x[:, C/2:]) as channel-slice views of an internal tensor."""
+    x = check_raw(to_internal(x), "split_halves")
+    if x.shape[1] % 16:
+        raise RuntimeError("split_halves: %d channels cannot be halved into 16-byte vectors" % x.shape[1])
+    outs = _SplitFanFn.apply(x, int(n_lo))
+    return list(outs[:-1]), outs[-1]
+
+
+class _FanoutFn(Function):
+    """n handles on one tensor; backward sums the n gradients in one pass instead of n-1 separate adds."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.set_materialize_grads(False)
+        return tuple(alias(x, 0, x.shape[1]) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        gs = [as_internal_grad(g, g) for g in gs]
+        return sum_n(gs), None
+
+
+def fanout(x, n):
+    x = to_internal(x)
+    if n <= 1 or not torch.is_grad_enabled() or not x.requires_grad:
+        return [x] * max(n, 1)
+    outs = list(_FanoutFn.apply(x, int(n)))
+    for o in outs:
+        for attr in ("_npp_is_relu", "_npp_relu_only"):
+            if getattr(x, attr, False):
+                setattr(o, attr, True)
+    return outs
+
+
+class _InterleaveFn(Function):
+    """cat(a, b) + channel_shuffle(groups=2): out[2c] = a[c], out[2c+1] = b[c] (model_search_interact.py:22-36)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        n, c, h, w = a.shape
+        y = empty_internal(n, 2 * c, h, w, a.dtype, a.device)
+        call("npp_interleave2_fwd", ref(view(a)), ref(view(b)), ref(view(y)), i32(L.dtype_code(a)), stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_internal_grad(dy, dy)
+        n, c2, h, w = dy.shape
+        da = empty_internal(n, c2 // 2, h, w, dy.dtype, dy.device)
+        db = empty_internal(n, c2 // 2, h, w, dy.dtype, dy.device)
+        call("npp_interleave2_bwd", ref(view(dy)), ref(view(da)), ref(view(db)), i32(L.dtype_code(dy)), stream())
+        return da, db
+
+
+def interleave2(a, b):
+    a, b = check_raw(to_internal(a), "interleave2"), check_raw(to_internal(b), "interleave2")
+    if a.shape != b.shape:
+        raise RuntimeError("interleave2: shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+    return _InterleaveFn.apply(a, b)

@@ -330,6 +330,164 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
     return pose_list, par_list
 
 
+# ---- search supernet (models/model_search_interact.py) ----------------------------------------------
+PRIMITIVES_INTER = ["std_conv_3x3", "dil_conv_3x3_4", "se_connect", "max_pool_3x3", "dil_conv_3x3_2", "std_conv_1x1",
+                    "poled_conv_x1"]  # genotypes.py:20-28
+
+
+def mixed_op(p, x, weights, up_scale=None, has_extra=False):
+    """MixedOp.forward, model_search_interact.py:56-74 (stride 1): candidates at C/2 with affine=False BatchNorm,
+    pooling gets a second BatchNorm (:48-49), every candidate is followed by Interpolate(up_scale) when rescaling
+    (:50-51, bilinear align_corners=True) while the pass-through half is resampled in nearest mode (:63-64);
+    cat + channel_shuffle(groups=2) (:70-71); optional 1x1 extra_conv."""
+    c = x.shape[1]
+    lo, hi = x[:, :c // 2], x[:, c // 2:]
+    total = 0
+    for k, name in enumerate(PRIMITIVES_INTER):
+        q = p.sub("_ops").sub(k)
+        if up_scale:
+            q = q.sub(0)
+        if "pool" in name:
+            y = bn(q.sub(1), primitive(name, q.sub(0), lo, 1))
+        else:
+            y = primitive(name, q, lo, 1)
+        if up_scale:
+            y = up(y, up_scale)
+        total = total + weights[k] * y
+    total = rnd(total)
+    if up_scale:
+        hi = F.interpolate(hi, scale_factor=up_scale)
+    ans = torch.cat([total, hi], dim=1)
+    b, ch, h, w = ans.shape
+    ans = ans.view(b, 2, ch // 2, h, w).transpose(1, 2).contiguous().view(b, ch, h, w)
+    if has_extra:
+        ans = conv(p.sub("extra_conv"), ans)
+    return ans
+
+
+def beta_weights(n_input, steps, betas):
+    """Network.btw, model_search_interact.py:1054-1065."""
+    out, start = [], 0
+    for i in range(steps):
+        out.append(torch.softmax(betas[start:start + n_input + i], dim=-1))
+        start += n_input + i
+    return torch.cat(out)
+
+
+def search_fusion_cell(p, s0, s1, s2, weights, weights2, steps=4, multiplier=4):
+    """PoseCell / ParCell with order == 1, model_search_interact.py:332-429."""
+    st = [relu_conv_bn(p.sub("preprocess%d" % i), s, 1, 1, 0) for i, s in enumerate((s0, s1, s2))]
+    offset = 0
+    for _ in range(steps):
+        s = 0
+        for j, h in enumerate(st):
+            s = s + weights2[offset + j] * mixed_op(p.sub("_ops").sub(offset + j), h, weights[offset + j])
+        offset += len(st)
+        st.append(rnd(s))
+    return torch.cat(st[0:3], dim=1), torch.cat(st[-multiplier:], dim=1)
+
+
+def search_forward(sd, x, layers=16, refine_layers=1, training=True, steps=4):
+    """models/model_search_interact.py:626-770 Network.forward on a reference-format state_dict (which holds the
+    twelve architecture tensors under alphas1.. / betas1.. as well)."""
+    p = Params(sd, training)
+    L = layers
+    taps = [L // 4 - 1, 2 * L // 4 - 1, 3 * L // 4 - 1, 4 * L // 4 - 1]
+    reduces = [L // 4, 2 * L // 4, 3 * L // 4]
+
+    def stem(name, x, stride, relu_out):
+        return _seq_conv_bn(p.sub(name), x, 0, 1, pad=1, stride=stride, relu_out=relu_out)
+
+    def interact(list_name, offset, feats, alphas, betas, scale_of, extra_of):
+        wa = torch.softmax(sd[alphas][offset:offset + len(feats)], dim=-1)
+        wb = torch.softmax(sd[betas][offset:offset + len(feats)], dim=-1)
+        z = 0
+        for j, h in enumerate(feats):
+            z = z + wb[j] * mixed_op(p.sub(list_name).sub(offset + j), h, wa[j], scale_of(j), extra_of(j))
+        return z
+
+    s0 = stem("stem1", stem("stem0", x, 2, True), 2, True)
+    s1 = stem("stem2", s0, 1, False)
+    s2 = stem("stem4", stem("stem3", x, 2, True), 2, True)
+    s3 = stem("stem5", s2, 1, False)
+    f1, f2 = [], []
+    offset = stage = 0
+    red_prev = False
+    for i in range(L):
+        red = i in reduces
+        s0, s1 = s1, encoder_cell(p.sub("cells1").sub(i), s0, s1, red, red_prev)
+        s2, s3 = s3, encoder_cell(p.sub("cells2").sub(i), s2, s3, red, red_prev)
+        red_prev = red
+        if i in taps:
+            f1.append(s1)
+            f2.append(s3)
+            sc = lambda j, i_=stage: 1 / 2 ** (i_ - j)      # :513 (1.0 on the diagonal: a truthy identity resample)
+            ex = lambda j, i_=stage: j != i_
+            z1 = interact("_ops1", offset, f2, "alphas1", "betas1", sc, ex)
+            z2 = interact("_ops2", offset, f1, "alphas2", "betas2", sc, ex)
+            s1, s3 = rnd(s1 + z1), rnd(s3 + z2)
+            f1[-1], f2[-1] = s1, s3
+            offset += len(f1)
+            stage += 1
+
+    res = [1, 1 / 2, 1 / 4, 1 / 8, 1 / 4, 1 / 2, 1]
+    cont = 0
+    prev1, prev2 = f1[3], f2[3]
+    for d in range(3):
+        o1 = upsample_cell(p.sub("upsamples1").sub(d), prev1, f1[2 - d], DECODER_UP1)
+        o2 = upsample_cell(p.sub("upsamples2").sub(d), prev2, f2[2 - d], DECODER_UP2)
+        f1.append(o1)
+        f2.append(o2)
+        sc = lambda j, d=d: res[4 + d] / res[j]
+        ex = lambda j, d=d: j != 4 + d
+        z1 = interact("up_ops1", cont, f2, "alphas3", "betas3", sc, ex)
+        z2 = interact("up_ops2", cont, f1, "alphas4", "betas4", sc, ex)
+        o1, o2 = rnd(o1 + z1), rnd(o2 + z2)
+        f1[-1], f2[-1] = o1, o2
+        prev1, prev2 = o1, o2
+        cont += len(f1)
+
+    x1 = torch.cat((f1[0], f1[6], up(f1[5], 2), up(f1[4], 4)), dim=1)
+    x2 = torch.cat((f2[0], f2[6], up(f2[5], 2), up(f2[4], 4)), dim=1)
+    in1 = _seq_conv_bn(p.sub("pose_auxlayer"), x1, 1, 2, relu_in=True)
+    in2 = _seq_conv_bn(p.sub("edge_layer"), x2, 1, 2, relu_in=True)
+    in3 = _seq_conv_bn(p.sub("pose_layer"), x1, 1, 2, relu_in=True)
+    in4 = _seq_conv_bn(p.sub("par_layer"), x2, 1, 2, relu_in=True)
+    pose_list, par_list = [], []
+
+    def emit(i):
+        edge = head(p.sub("edge_head").sub(i), in2, 3)
+        pose_aux = head(p.sub("pose_auxnet").sub(i), in1, 3)
+        pose_map = head(p.sub("pose_head").sub(i), in3, 1)
+        par_map = head(p.sub("par_head").sub(i), in4, 1)
+        pose_list.append([pose_map, pose_aux])
+        par_list.append([par_map, edge])
+
+    emit(0)
+    w_pose = torch.softmax(sd["alphas_pose"], dim=-1)
+    w_pose2 = beta_weights(3, steps, sd["betas_pose"])
+    w_par = torch.softmax(sd["alphas_par"], dim=-1)
+    w_par2 = beta_weights(3, steps, sd["betas_par"])
+    for i in range(1, refine_layers + 1):
+        for j in range(3):
+            k = 2 * (i - 1) + j
+            in1, tmp = search_fusion_cell(p.sub("pose_net").sub(k), in1, in3, in4, w_pose, w_pose2, steps)
+            in2, in4 = search_fusion_cell(p.sub("par_net").sub(k), in2, in3, in4, w_par, w_par2, steps)
+            in3 = tmp
+        emit(i)
+    return pose_list, par_list
+
+
+def loss_entropy(alphas, n_arch=12):
+    """Network.loss_entropy, model_search_interact.py:881-896: normalised row entropy of softmax(alpha)."""
+    total = 0.
+    for a in alphas:
+        w = torch.softmax(a, dim=-1)
+        ent = torch.distributions.Categorical(probs=w).entropy() / math.log(w.shape[1])
+        total = total + ent.mean(dim=0)
+    return 0.25 * 2 * total / n_arch
+
+
 # ---- losses (core/criterion.py) ---------------------------------------------------------------------
 WEIGHTS_LIP = [0.7602572, 0.94236198, 0.85644457, 1.04346266, 1.10627293, 0.80980162, 0.95168713, 0.8403769,
                1.05798412, 0.85746254, 1.01274366, 1.05854692, 1.03430773, 0.84867818, 0.88027721, 0.87580925,

@@ -190,6 +190,51 @@ def golden_eval(ref):
     np.savez_compressed(os.path.join(HERE, "eval_golden.npz"), **out)
 
 
+SEARCH_GRAD_KEYS = ["stem0.0.weight", "cells1.3._ops.0.net.1.weight", "_ops1.0._ops.0.0.net.1.weight",
+                    "_ops2.1.extra_conv.weight", "up_ops1.7._ops.4.0.net.2.weight", "pose_net.0._ops.5._ops.5.net.1.weight",
+                    "par_net.2.preprocess1.net.1.weight", "par_head.1.4.bias"]
+
+
+def golden_search(ref):
+    """Search supernet (model_search_interact.py) at L=8, C=16, 2x3x128x128 with random architecture tensors:
+    outputs, d(alphas/betas) and a few weight gradients of  sum_i <out_i, r_i>  (r_i seeded)."""
+    import importlib
+    rs = importlib.import_module("models.model_search_interact")
+    cfg = _refshim.cfg(layers=8, init_channels=16)
+    torch.manual_seed(0)
+    net = rs.Network(cfg)
+    net.train()
+    g = torch.Generator().manual_seed(123)
+    arch_names = ["alphas1", "alphas2", "alphas3", "alphas4", "alphas_pose", "alphas_par", "betas1", "betas2",
+                  "betas3", "betas4", "betas_pose", "betas_par"]
+    out = {"layers": np.array(8), "channels": np.array(16), "seed": np.array(0)}
+    for n_, pa in zip(arch_names, net.arch_parameters()):
+        pa.data.copy_(torch.randn(pa.shape, generator=g) * 0.5)
+        out["arch/" + n_] = pa.detach().numpy().copy()
+    x = torch.randn(2, 3, 128, 128, generator=g).bfloat16().float()
+    out["x"] = x.numpy()
+    pose_list, par_list = net(x)
+    names = ["pose0", "poseaux0", "pose1", "poseaux1", "par0", "edge0", "par1", "edge1"]
+    tensors = [t for pair in pose_list + par_list for t in pair]
+    gr = torch.Generator().manual_seed(321)
+    loss = 0
+    for n_, t in zip(names, tensors):
+        out["out/" + n_] = t.detach().numpy()
+        loss = loss + (t * torch.randn(t.shape, generator=gr)).sum()
+    loss = loss + 3.0 * net.loss_entropy()
+    loss.backward()
+    out["loss"] = np.array([float(loss)])
+    out["entropy"] = np.array([float(net.loss_entropy())])
+    for n_, pa in zip(arch_names, net.arch_parameters()):
+        out["grad/" + n_] = pa.grad.numpy().copy()
+    sd = dict(net.named_parameters())
+    for k in SEARCH_GRAD_KEYS:
+        out["wgrad/" + k] = sd[k].grad.numpy().copy()
+    gi, gf = net.genotype()
+    out["genotype"] = np.array([repr((gi, [list(gf.pose), list(gf.par)]))])
+    np.savez_compressed(os.path.join(HERE, "search_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert _refshim.have_reference(), "needs /root/reference"
     ref = _refshim.import_reference()
@@ -198,6 +243,7 @@ if __name__ == "__main__":
     golden_network(ref)
     golden_eval(ref)
     golden_loss(ref)
+    golden_search(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

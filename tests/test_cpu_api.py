@@ -117,3 +117,57 @@ def test_genotypes_fields():
     assert gt.Genotype._fields == ("normal", "normal_concat", "reduce", "reduce_concat")
     assert len(gt.ENCODER.normal) == 8 and len(gt.FUSION.pose) == 8 and list(gt.FUSION.par_concat) == [3, 4, 5, 6]
     assert gt.PRIMITIVES_PC[0] == "std_conv_3x3" and len(gt.PRIMITIVES_INTER) == 7
+
+
+@pytest.mark.skipif(not _refshim.have_reference(), reason="needs /root/reference (build container only)")
+def test_search_supernet_host_parity_with_reference():
+    """model_search_interact.Network: state_dict keys + seeded init, btw(), loss_entropy() and genotype() are
+    identical to the reference's (host-side logic only: no kernel is launched)."""
+    import importlib
+    _refshim.import_reference()
+    rs = importlib.import_module("models.model_search_interact")
+    from npp_b200.models import model_search_interact as ms
+    cfg = _refshim.cfg(layers=8, init_channels=16)
+    torch.manual_seed(0)
+    rn = rs.Network(cfg)
+    torch.manual_seed(0)
+    mn = ms.Network(cfg)
+    rsd, msd = rn.state_dict(), mn.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    for k in rsd:
+        assert rsd[k].shape == msd[k].shape and torch.equal(rsd[k], msd[k]), k
+    assert len(mn.arch_parameters()) == 12
+    g = torch.Generator().manual_seed(1)
+    for pa, pb in zip(rn.arch_parameters(), mn.arch_parameters()):
+        assert pa.shape == pb.shape
+        v = torch.randn(pa.shape, generator=g)
+        pa.data.copy_(v)
+        pb.data.copy_(v)
+    assert torch.equal(rn.btw(3, 4, rn.betas_pose), mn.btw(3, 4, mn.betas_pose))
+    assert torch.equal(rn.btw(5, 3, rn.betas3), mn.btw(5, 3, mn.betas3))
+    assert abs(float(rn.loss_entropy().detach()) - float(mn.loss_entropy().detach())) < 1e-7
+    (ri, rf), (mi, mf) = rn.genotype(), mn.genotype()
+    assert ri == mi and list(rf.pose) == list(mf.pose) and list(rf.par) == list(mf.par)
+    assert list(mf.pose_concat) == list(rf.pose_concat) == [3, 4, 5, 6]
+
+
+@pytest.mark.skipif(not _refshim.have_reference(), reason="needs /root/reference (build container only)")
+def test_oracle_matches_reference_supernet():
+    import importlib
+    _refshim.import_reference()
+    rs = importlib.import_module("models.model_search_interact")
+    from oracle import nppnet_ref as O
+    cfg = _refshim.cfg(layers=8, init_channels=16)
+    torch.manual_seed(2)
+    rn = rs.Network(cfg).train()
+    g = torch.Generator().manual_seed(3)
+    for pa in rn.arch_parameters():
+        pa.data.copy_(torch.randn(pa.shape, generator=g) * 0.5)
+    sd = {k: v.detach().clone() for k, v in rn.state_dict().items()}
+    x = torch.randn(2, 3, 128, 128, generator=g)
+    with torch.no_grad():
+        pl, par = rn(x)
+        opl, opar = O.search_forward(sd, x, layers=8, training=True)
+    for a, b in zip([t for p in pl + par for t in p], [t for p in opl + opar for t in p]):
+        assert torch.equal(a, b)
+    assert abs(float(rn.loss_entropy()) - float(O.loss_entropy(rn.arch_parameters()[:6]))) < 1e-7

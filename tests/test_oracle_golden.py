@@ -111,3 +111,34 @@ def test_pckh_known_answer():
     pred = gt + 3.0
     hit, valid = E.pckh_counts(pred, gt)
     assert (hit == valid).all() and valid.sum() > 0
+
+
+def test_search_supernet_golden():
+    """Oracle restatement of model_search_interact.Network.forward + loss_entropy vs the fixture generated from the
+    reference: outputs, and the architecture gradients of sum_i <out_i, r_i> + 3*loss_entropy."""
+    from npp_b200.models.model_search_interact import Network
+    from oracle import nppnet_ref as O
+    g = G("search_golden.npz")
+    ns = types.SimpleNamespace
+    L, C = int(g["layers"]), int(g["channels"])
+    cfg = ns(DATASET=ns(NUM_CLASSES=20, NUM_JOINTS=16), SEARCH=ns(LAYERS=L, INIT_CHANNELS=C),
+             MODEL=ns(DECONV_WITH_BIAS=False, HEAD="PSP", REFINE_LAYERS=1))
+    torch.manual_seed(int(g["seed"]))
+    net = Network(cfg)     # parameters only: same seeded init as the reference (tests/test_cpu_api.py)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    arch = [k[5:] for k in g.files if k.startswith("arch/")]
+    assert len(arch) == 12
+    for k in arch:
+        sd[k] = torch.from_numpy(g["arch/" + k].copy()).requires_grad_(True)
+    pl, par = O.search_forward(sd, torch.from_numpy(g["x"]), layers=L, training=True)
+    names = ["pose0", "poseaux0", "pose1", "poseaux1", "par0", "edge0", "par1", "edge1"]
+    gr = torch.Generator().manual_seed(321)
+    loss = 0
+    for n, t in zip(names, [t for pair in pl + par for t in pair]):
+        assert _close(t.detach().numpy(), g["out/" + n], 1e-5), n
+        loss = loss + (t * torch.randn(t.shape, generator=gr)).sum()
+    ent = O.loss_entropy([sd[k] for k in ("alphas1", "alphas2", "alphas3", "alphas4", "alphas_pose", "alphas_par")])
+    assert abs(float(ent) - float(g["entropy"][0])) < 1e-6
+    (loss + 3.0 * ent).backward()
+    for k in arch:
+        assert _close(sd[k].grad.numpy(), g["grad/" + k], 1e-3), k
