@@ -342,6 +342,12 @@ int npp_node_bwd_reduce(const npp_view4* g_raw, const npp_view4* g_relu, const n
                         const npp_view4* b, const float* mean_b, const float* invstd_b,
                         const npp_view4* g_out, float* partials, int dtype, npp_stream_t stream);
 int npp_reduce_partials(const float* partials, int rows, int len, float* out, npp_stream_t stream);
+/* reduce_partials that also accumulates segment s = columns [s*seg_len,(s+1)*seg_len) of the folded row into
+ * acc[s][0:acc_valid[s]] (+=; NULL = skip): BatchNorm d beta / d gamma go straight into the optimizer's flat
+ * gradient buffer.  acc / acc_valid: HOST arrays of len/seg_len (<= NPP_ACC_MAX) entries. */
+#define NPP_ACC_MAX 16
+int npp_reduce_partials_acc(const float* partials, int rows, int len, float* out, int seg_len,
+                            float* const* acc, const int* acc_valid, npp_stream_t stream);
 int npp_node_bwd_apply(const npp_view4* g, const npp_view4* a, const float* gamma_a,
                        const float* mean_a, const float* invstd_a, const float* sums_a,
                        const npp_view4* da, const npp_view4* b, const float* gamma_b,

@@ -290,6 +290,32 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   }
 }
 
+// reduce_partials + parameter-gradient accumulation: segment s = columns [s*seg_len, (s+1)*seg_len) of the folded
+// row is additionally added into acc[s].ptr[0:valid] (BatchNorm d beta / d gamma written straight into the
+// optimizer's flat gradient buffer instead of going through one autograd accumulation kernel per parameter).
+struct AccSeg { float* ptr; int valid; };
+struct AccSegs { AccSeg s[NPP_ACC_MAX]; };
+__global__ void __launch_bounds__(256) reduce_partials_acc_kernel(const float* __restrict__ partials, int rows, int len,
+                                                                  float* __restrict__ out, int seg_len, AccSegs acc) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < len) {
+    for (int r = rg; r < rows; r += 8) s += partials[(int64_t)r * len + col];
+  }
+  red[rg][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rg == 0 && col < len) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[col] = t;
+    const int seg = col / seg_len, off = col - seg * seg_len;
+    if (seg < NPP_ACC_MAX && acc.s[seg].ptr && off < acc.s[seg].valid) acc.s[seg].ptr[off] += t;
+  }
+}
+
 static int node_bwd_blocks(int64_t npix, int C, int V) {
   const VecGeom g = vec_geom(C, V);
   return stream_grid(npix, g, 8, 4);
@@ -469,6 +495,23 @@ int npp_reduce_partials(const float* partials, int rows, int len, float* out, np
   if (!partials || !out || rows <= 0 || len <= 0) return NPP_E_INVALID;
   reduce_partials_kernel<<<(len + 31) / 32, 256, 0, as_stream(s)>>>(partials, rows, len, out);
   NPP_CHECK_LAUNCH("reduce_partials_kernel");
+  return NPP_OK;
+}
+
+int npp_reduce_partials_acc(const float* partials, int rows, int len, float* out, int seg_len, float* const* acc,
+                            const int* acc_valid, npp_stream_t s) {
+  if (!partials || !out || rows <= 0 || len <= 0 || seg_len <= 0 || len % seg_len || len / seg_len > NPP_ACC_MAX || !acc ||
+      !acc_valid)
+    return NPP_E_INVALID;
+  AccSegs A;
+  for (int i = 0; i < NPP_ACC_MAX; ++i) {
+    const bool on = i < len / seg_len;
+    A.s[i].ptr = on ? acc[i] : nullptr;
+    A.s[i].valid = on ? acc_valid[i] : 0;
+    if (on && (acc_valid[i] < 0 || acc_valid[i] > seg_len)) return NPP_E_INVALID;
+  }
+  reduce_partials_acc_kernel<<<(len + 31) / 32, 256, 0, as_stream(s)>>>(partials, rows, len, out, seg_len, A);
+  NPP_CHECK_LAUNCH("reduce_partials_acc_kernel");
   return NPP_OK;
 }
 

@@ -129,17 +129,20 @@ class TrainStep:
 
     def _step_body(self):
         self.opt.zero_grad(set_to_none=True)
+        F_._arena.begin(self.images.device)             # every zero-initialised accumulator of the step: one memset
         F_._state["defer_bn_counters"] = counters = []  # BatchNorm num_batches_tracked += 1: one launch, not 432
         try:
             pose, par = self.model(self.images)
+            F_._state["defer_bn_counters"] = None
+            if counters:
+                torch._foreach_add_(counters, 1)
+            loss_par = self.cpar(par, [self.par_lab, self.edge_lab]).unsqueeze(0)
+            loss_pose = self.cpose(pose, [self.pose_gt, self.pose_aux_gt]).unsqueeze(0)
+            loss = (loss_par + loss_pose).mean()
+            loss.backward()
         finally:
             F_._state["defer_bn_counters"] = None
-        if counters:
-            torch._foreach_add_(counters, 1)
-        loss_par = self.cpar(par, [self.par_lab, self.edge_lab]).unsqueeze(0)
-        loss_pose = self.cpose(pose, [self.pose_gt, self.pose_aux_gt]).unsqueeze(0)
-        loss = (loss_par + loss_pose).mean()
-        loss.backward()
+            F_._arena.end()
         if self.world_size > 1:
             self._allreduce_grads()
         self.opt.step()

@@ -5,6 +5,8 @@ channels_last strides (physical NHWC), dtype bf16 (product path) or fp32 (valida
 C padded to a multiple of 8 with zero channels.  Every Function below launches hand-written
 kernels on torch's current CUDA stream through the C ABI; torch only owns the memory.
 """
+import ctypes
+
 import torch
 from torch.autograd import Function
 
@@ -56,6 +58,62 @@ def pad_vec(p, n, value=0.0):
     if p is None or p.numel() == n:
         return p
     return torch.cat([p, p.new_full((n - p.numel(),), value)])
+
+
+# ------------------------------------------------------------------------------------------------
+# per-step scratch: zero-initialised fp32 accumulators and direct parameter-gradient slots
+# ------------------------------------------------------------------------------------------------
+class ZeroArena:
+    """One persistent fp32 buffer handing out the zero-initialised accumulators a step needs (BatchNorm statistic
+    vectors, per-image SE sums, ...): ONE memset per step instead of one fill kernel per accumulator.  The step
+    driver (engine.TrainStep) calls begin() before and end() after every step; slices are handed out in call order,
+    anything that does not fit falls back to torch.zeros and grows the buffer for the next (eager) step."""
+
+    def __init__(self):
+        self.buf, self.cursor, self.need, self.active = None, 0, 0, False
+
+    def begin(self, device):
+        if self.buf is None or self.buf.numel() < self.need:
+            if torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("ZeroArena must be sized by an eager step before CUDA-graph capture")
+            self.buf = torch.zeros(max(self.need, 1 << 16), dtype=torch.float32, device=device)
+        else:
+            self.buf.zero_()
+        self.cursor, self.need, self.active = 0, 0, True
+
+    def end(self):
+        self.active = False
+
+    def take(self, n):
+        n4 = (n + 3) // 4 * 4          # keep every slice 16-byte aligned (float4 loads)
+        self.need += n4
+        if self.buf is not None and self.cursor + n4 <= self.buf.numel():
+            t = self.buf[self.cursor:self.cursor + n]
+            self.cursor += n4
+            return t
+        return None
+
+
+_arena = ZeroArena()
+
+
+def zeros_f32(n, device):
+    """fp32 zeros of n elements: an arena slice inside a TrainStep, torch.zeros otherwise."""
+    if _arena.active:
+        t = _arena.take(int(n))
+        if t is not None:
+            return t
+    return torch.zeros(int(n), dtype=torch.float32, device=device)
+
+
+def grad_slot(p):
+    """The persistent gradient slot of a parameter when the optimizer installed one (FusedAdam.use_flat_grads):
+    backward kernels accumulate into it directly and autograd gets no gradient to add (one kernel launch per
+    parameter less).  None when gradients are ordinary autograd-managed tensors."""
+    if p is None or not torch.is_grad_enabled():
+        return None
+    s = getattr(p, "_npp_grad_slot", None)
+    return s if (s is not None and p.grad is s) else None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -183,7 +241,7 @@ def _conv_work(n, ho, wo, cout, cin, kh, kw, x, y):
 
 class _ConvFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, dil, hoff, woff, want_stats):
+    def forward(ctx, x, weight, bias, stride, pad, dil, hoff, woff, want_stats, slots):
         n, cx, h, w = x.shape
         cout, cin, kh, kw = weight.shape
         if cx != pad8(cin):
@@ -205,7 +263,7 @@ class _ConvFn(Function):
         stats = None
         if bf16:
             if want_stats:
-                stats = torch.zeros(2 * cop, dtype=torch.float32, device=x.device)
+                stats = zeros_f32(2 * cop, x.device)
             call("npp_conv2d_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw), i32(stride),
                  i32(pad), i32(dil), i32(hoff), i32(woff), fptr(stats), stream(),
                  work=_conv_work(n, ho, wo, cout, cin, kh, kw, x, y), keep=(x, wp, bp, y, stats))
@@ -213,6 +271,7 @@ class _ConvFn(Function):
             call("npp_conv2d_direct_fwd", ref(view(x)), fptr(wp), fptr(bp), ref(view(y)), i32(kh), i32(kw),
                  i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
         ctx.cfg = (stride, pad, dil, hoff, woff, cout, cin, kh, kw, bias is not None)
+        ctx.slots = slots if slots is not None else (None, None)
         ctx.work = _conv_work(n, ho, wo, cout, cin, kh, kw, x, y)
         ctx.save_for_backward(x, wt if bf16 else wp)
         if stats is None:
@@ -236,8 +295,10 @@ class _ConvFn(Function):
             else:
                 call("npp_conv2d_direct_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw),
                      i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
+        wslot, bslot = ctx.slots
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+            # wgrad accumulates (+=): into the parameter's own gradient slot when there is one, else into zeros
+            dw = wslot if wslot is not None else torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
             if bf16:
                 call("npp_conv2d_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
                      i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work,
@@ -245,17 +306,24 @@ class _ConvFn(Function):
             else:
                 call("npp_conv2d_direct_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh),
                      i32(kw), i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
+            if wslot is not None:
+                dw = None
         if has_bias and ctx.needs_input_grad[2]:
-            dbp = torch.zeros(dy.shape[1], dtype=torch.float32, device=x.device)
-            call("npp_colsum", ref(view(dy)), fptr(dbp), i32(code), stream())
-            db = dbp[:cout]
-        return dx, dw, db, None, None, None, None, None, None
+            if bslot is not None and dy.shape[1] == cout:
+                call("npp_colsum", ref(view(dy)), fptr(bslot), i32(code), stream())
+            else:
+                dbp = zeros_f32(dy.shape[1], x.device)
+                call("npp_colsum", ref(view(dy)), fptr(dbp), i32(code), stream())
+                db = dbp[:cout]
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_stats=False):
     """Dense conv on an internal tensor.  Returns (y, stats) where stats is the fused per-channel
     (sum, sum of squares) of y from the tcgen05 epilogue (empty when not requested / fp32 mode)."""
-    return _ConvFn.apply(x, weight, bias, int(stride), int(pad), int(dil), int(hoff), int(woff), bool(want_stats))
+    slots = (grad_slot(weight), grad_slot(bias))
+    return _ConvFn.apply(x, weight, bias, int(stride), int(pad), int(dil), int(hoff), int(woff), bool(want_stats),
+                         slots if (slots[0] is not None or slots[1] is not None) else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,9 +331,10 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_st
 # ------------------------------------------------------------------------------------------------
 class _DwConvFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, stride, pad, dil, relu_in):
+    def forward(ctx, x, weight, stride, pad, dil, relu_in, wslot):
         n, c, h, w = x.shape
         k = weight.shape[-1]
+        ctx.wslot = wslot
         if weight.shape[0] != c or weight.shape[1] != 1:
             raise RuntimeError("depthwise weight %s does not match %d channels" % (tuple(weight.shape), c))
         ho, wo = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
@@ -283,14 +352,16 @@ class _DwConvFn(Function):
         k, stride, pad, dil, relu_in = ctx.cfg
         dy = as_internal_grad(dy, x)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros_like(w32) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(w32)
         call("npp_dwconv_bwd", ref(view(x)), fptr(w32), ref(view(dy)), ref(view(dx)) if dx is not None else NULL,
              fptr(dw), i32(k), i32(stride), i32(pad), i32(dil), i32(relu_in), i32(L.dtype_code(x)), stream())
-        return dx, dw, None, None, None, None
+        return dx, (None if ctx.wslot is not None else dw), None, None, None, None, None
 
 
 def dwconv2d(x, weight, stride, pad, dil, relu_in):
-    return _DwConvFn.apply(x, weight, int(stride), int(pad), int(dil), int(bool(relu_in)))
+    return _DwConvFn.apply(x, weight, int(stride), int(pad), int(dil), int(bool(relu_in)), grad_slot(weight))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -469,7 +540,7 @@ def _bn_forward_coef(y, stats, bn, sync):
         else:
             bn.num_batches_tracked.add_(1)
     if stats is None or stats.numel() == 0:
-        stats = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        stats = zeros_f32(2 * c, dev)
         call("npp_bn_stats", ref(view(y)), fptr(stats), i32(L.dtype_code(y)), stream())
     count = float(n * h * w)
     if sync:
@@ -487,8 +558,9 @@ class _NodeFn(Function):
 
     @staticmethod
     def forward(ctx, a, ga, ba, b, gb, bb, cfg):
-        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu = cfg
+        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu, pslots = cfg
         ctx.set_materialize_grads(False)
+        ctx.pslots = pslots
         n, c, h, w = a.shape
         code = L.dtype_code(a)
         sync = _sync_group() is not None
@@ -546,10 +618,24 @@ class _NodeFn(Function):
         da = db = dga = dba = dgb = dbb = None
         if need_bn:
             sums = torch.empty(nq * c, dtype=torch.float32, device=dev)
-            call("npp_reduce_partials", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), stream())
+            sl_a, sl_b = ctx.pslots
+            if (has_a and sl_a is not None) or (has_b and sl_b is not None):
+                segs = []
+                if has_a:
+                    segs += list(sl_a) if sl_a is not None else [None, None]
+                if has_b:
+                    segs += list(sl_b) if sl_b is not None else [None, None]
+                accp = (ctypes.c_void_p * len(segs))(*[t.data_ptr() if t is not None else None for t in segs])
+                accv = (ctypes.c_int * len(segs))(*[min(t.numel(), c) if t is not None else 0 for t in segs])
+                call("npp_reduce_partials_acc", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), i32(c), accp, accv,
+                     stream())
+            else:
+                call("npp_reduce_partials", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), stream())
             local = sums
             if sync:
-                local = sums.clone()  # parameter gradients stay local (the gradient all-reduce averages them)
+                returns_grads = (has_a and ctx.pslots[0] is None) or (has_b and ctx.pslots[1] is None)
+                if returns_grads:
+                    local = sums.clone()  # parameter gradients stay local (the gradient all-reduce averages them)
                 _allreduce_sum(sums)
             sa = sums[:2 * c] if has_a else None
             sb = sums[2 * c * int(has_a):] if has_b else None
@@ -577,6 +663,11 @@ class _NodeFn(Function):
         if two and not has_b:
             db = g
         ni = ctx.needs_input_grad
+        if need_bn:
+            if has_a and ctx.pslots[0] is not None:
+                dga = dba = None   # already accumulated into the parameters' gradient slots
+            if has_b and ctx.pslots[1] is not None:
+                dgb = dbb = None
         return (da if ni[0] else None, dga if ni[1] else None, dba if ni[2] else None, db if (two and ni[3]) else None,
                 dgb if ni[4] else None, dbb if ni[5] else None, None)
 
@@ -608,8 +699,17 @@ def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None)
 
     ga, ba = affine(bn_a)
     gb, bb = affine(bn_b)
+    # direct parameter-gradient slots (d beta, d gamma) per BatchNorm side; all-or-nothing per side
+    pslots = []
+    for bn in (bn_a, bn_b):
+        sl = None
+        if bn is not None and bn.affine and (bn.training or not bn.track_running_stats):
+            sl = (grad_slot(bn.bias), grad_slot(bn.weight))
+            if sl[0] is None or sl[1] is None:
+                sl = None
+        pslots.append(sl)
     raw, rel = _NodeFn.apply(ya, ga, ba, yb, gb, bb, (bn_a, st_a, bn_b, st_b, bool(want_raw), bool(want_relu), out_raw,
-                                                       out_relu))
+                                                       out_relu, pslots))
     if rel is not None:
         rel._npp_is_relu = True   # relu(rel) is rel (no tensor ever references itself: that would leak the graph)
         if raw is not None:
@@ -800,10 +900,11 @@ def avg_pool2x2(x):
 # ------------------------------------------------------------------------------------------------
 class _SEFn(Function):
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, w1, b1, w2, b2, slots):
         n, c, h, w = x.shape
         dev, code = x.device, L.dtype_code(x)
-        g = torch.zeros((n, c), dtype=torch.float32, device=dev)
+        ctx.slots = slots
+        g = zeros_f32(n * c, dev).view(n, c)
         call("npp_gap_fwd", ref(view(x)), fptr(g), i32(code), stream())
         w1c, w2c = w1.detach().reshape(c // 2, c).contiguous(), w2.detach().reshape(c, c // 2).contiguous()
         b1c = b1.detach().contiguous() if b1 is not None else None
@@ -825,22 +926,29 @@ class _SEFn(Function):
         dy = as_internal_grad(dy, x)
         n, c, h, w = x.shape
         dev, code = x.device, L.dtype_code(x)
-        ds = torch.zeros((n, c), dtype=torch.float32, device=dev)
+        ds = zeros_f32(n * c, dev).view(n, c)
         call("npp_se_bwd_reduce", ref(view(x)), ref(view(dy)), fptr(ds), i32(code), stream())
-        dw1, dw2 = torch.zeros_like(w1c), torch.zeros_like(w2c)
-        db1 = torch.zeros(c // 2, dtype=torch.float32, device=dev)
-        db2 = torch.zeros(c, dtype=torch.float32, device=dev)
+        direct = ctx.slots is not None
+        if direct:   # se_fc_bwd accumulates (+=): straight into the four parameters' gradient slots
+            dw1, db1, dw2, db2 = ctx.slots
+        else:
+            dw1, dw2 = torch.zeros_like(w1c), torch.zeros_like(w2c)
+            db1 = zeros_f32(c // 2, dev)
+            db2 = zeros_f32(c, dev)
         dg = torch.empty((n, c), dtype=torch.float32, device=dev)
         call("npp_se_fc_bwd", fptr(g), fptr(hbuf), fptr(s), fptr(ds), fptr(w1c), fptr(w2c), fptr(dw1), fptr(db1),
              fptr(dw2), fptr(db2), fptr(dg), i32(n), i32(c), stream())
         dx = torch.empty_like(x)
         call("npp_se_bwd_apply", ref(view(dy)), fptr(s), fptr(dg), ref(view(dx)), i32(code), stream())
+        if direct:
+            return dx, None, None, None, None, None
         return (dx, dw1.reshape(ctx.wshapes[0]), db1 if ctx.has_bias[0] else None, dw2.reshape(ctx.wshapes[1]),
-                db2 if ctx.has_bias[1] else None)
+                db2 if ctx.has_bias[1] else None, None)
 
 
 def se_scale(x, w1, b1, w2, b2):
-    return _SEFn.apply(x, w1, b1, w2, b2)
+    slots = tuple(grad_slot(p) for p in (w1, b1, w2, b2))
+    return _SEFn.apply(x, w1, b1, w2, b2, slots if all(t is not None for t in slots) else None)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat_views = [(p, self.flat_grads[o:o + p.numel()].view_as(p)) for p, o in zip(params, offs)]
         for p, v in self._flat_views:
             p.grad = v
+            p._npp_grad_slot = v   # functional.grad_slot(): backward kernels accumulate here directly
         self._key = None
         return self.flat_grads
 

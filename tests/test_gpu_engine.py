@@ -77,3 +77,55 @@ def test_fused_adam_in_train_step_updates_every_used_parameter(lib_built):
     used = [k for k, p in model.named_parameters() if k not in unused]
     moved = sum(int(not torch.equal(before[k], p.detach())) for k, p in model.named_parameters() if k in used)
     assert moved >= 0.95 * len(used), (moved, len(used))
+
+
+def test_direct_gradient_slots_match_autograd_accumulation(lib_built):
+    """With FusedAdam.use_flat_grads() the backward kernels accumulate parameter gradients straight into the flat
+    buffer (functional.grad_slot) and the zero-initialised accumulators come from the per-step arena; the result
+    must equal ordinary autograd-accumulated gradients (fp32 validation mode, same weights and input)."""
+    from npp_b200 import engine
+    from npp_b200 import functional as F_
+    from npp_b200.models.model_augment import Network
+    from npp_b200.optim import FusedAdam
+    F_.set_compute_dtype(torch.float32)
+    try:
+        torch.manual_seed(4)
+        model = Network(engine.make_cfg(layers=8, init_channels=16)).cuda().train()
+        gen = torch.Generator().manual_seed(8)
+        x = torch.randn(2, 3, 128, 128, generator=gen).cuda()
+
+        def run():
+            pl, par = model(x)
+            outs = [t for p in pl + par for t in p]
+            g2 = torch.Generator().manual_seed(9)
+            sum((t * torch.randn(t.shape, generator=g2).cuda()).sum() for t in outs).backward()
+            torch.cuda.synchronize()
+
+        run()
+        plain = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        for p in model.parameters():
+            p.grad = None
+        opt = FusedAdam([p for p in model.parameters()], lr=0.0)
+        flat = opt.use_flat_grads()
+        opt.zero_grad()
+        F_._arena.begin(x.device)
+        try:
+            run()
+        finally:
+            F_._arena.end()
+        assert F_._arena.need > 0
+        worst = 0.0
+        for k, p in model.named_parameters():
+            assert p.grad is p._npp_grad_slot
+            if k not in plain:
+                assert not p.grad.any(), k
+                continue
+            denom = plain[k].norm().item()
+            if denom < 1e-6:
+                continue
+            worst = max(worst, ((p.grad - plain[k]).norm() / denom).item())
+        print("direct-slot vs autograd gradient mismatch (worst tensor):", worst)
+        assert worst < 2e-3, worst
+        assert flat.abs().sum() > 0
+    finally:
+        F_.set_compute_dtype(torch.bfloat16)
