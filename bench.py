@@ -332,8 +332,13 @@ def main():
                                         "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Leave without tearing the NCCL communicator down: the captured CUDA graphs still reference it, and
+        # destroy_process_group() / interpreter teardown was observed to block for minutes on that.  Every rank has
+        # finished its timed work (the timing all-reduce above is the last collective); exit code 0 for torchrun.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

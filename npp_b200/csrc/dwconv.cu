@@ -123,6 +123,17 @@ static int dw_bwd_weight_t(const npp_view4* x, const npp_view4* dy, float* dw, i
   return NPP_OK;
 }
 
+// dwconv_tile.cu: shared-memory halo-staged 3x3 kernels; NPP_E_UNSUPPORTED = use the gather kernels above
+template <typename T>
+int dw_tile_fwd(const npp_view4* x, const float* w, const npp_view4* y, int stride, int pad, int dil, int relu_in,
+                cudaStream_t st);
+template <typename T>
+int dw_tile_dgrad(const npp_view4* x, const float* w, const npp_view4* dy, const npp_view4* dx, int stride, int pad,
+                  int dil, int relu_in, cudaStream_t st);
+template <typename T>
+int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride, int pad, int dil, int relu_in,
+                  cudaStream_t st);
+
 }  // namespace npp
 
 using namespace npp;
@@ -140,8 +151,13 @@ int npp_dwconv_fwd(const npp_view4* x, const float* w, const npp_view4* y, int k
                    int relu_in, int dtype, npp_stream_t s) {
   if (!view_ok(x, dtype) || !view_ok(y, dtype) || !w) return NPP_E_INVALID;
   if (!dw_shapes_ok(x, y, k, stride, pad, dil)) return NPP_E_UNSUPPORTED;
-  NPP_DISPATCH_DTYPE(dtype, if (k == 3) return dw_fwd_t<T, 3>(x, w, y, stride, pad, dil, relu_in, as_stream(s));
-                     return dw_fwd_t<T, 5>(x, w, y, stride, pad, dil, relu_in, as_stream(s)););
+  NPP_DISPATCH_DTYPE(
+      dtype,
+      if (k == 3) {
+        const int rc = dw_tile_fwd<T>(x, w, y, stride, pad, dil, relu_in, as_stream(s));
+        if (rc != NPP_E_UNSUPPORTED) return rc;
+        return dw_fwd_t<T, 3>(x, w, y, stride, pad, dil, relu_in, as_stream(s));
+      } return dw_fwd_t<T, 5>(x, w, y, stride, pad, dil, relu_in, as_stream(s)););
 }
 
 int npp_dwconv_bwd(const npp_view4* x, const float* w, const npp_view4* dy, const npp_view4* dx, float* dw, int k,
@@ -154,12 +170,16 @@ int npp_dwconv_bwd(const npp_view4* x, const float* w, const npp_view4* dy, cons
   NPP_DISPATCH_DTYPE(
       dtype,
       if (dx) {
-        rc = (k == 3) ? dw_bwd_data_t<T, 3>(x, w, dy, dx, stride, pad, dil, relu_in, st)
-                      : dw_bwd_data_t<T, 5>(x, w, dy, dx, stride, pad, dil, relu_in, st);
+        rc = (k == 3) ? dw_tile_dgrad<T>(x, w, dy, dx, stride, pad, dil, relu_in, st) : NPP_E_UNSUPPORTED;
+        if (rc == NPP_E_UNSUPPORTED)
+          rc = (k == 3) ? dw_bwd_data_t<T, 3>(x, w, dy, dx, stride, pad, dil, relu_in, st)
+                        : dw_bwd_data_t<T, 5>(x, w, dy, dx, stride, pad, dil, relu_in, st);
         if (rc) return rc;
       } if (dw) {
-        rc = (k == 3) ? dw_bwd_weight_t<T, 3>(x, dy, dw, stride, pad, dil, relu_in, st)
-                      : dw_bwd_weight_t<T, 5>(x, dy, dw, stride, pad, dil, relu_in, st);
+        rc = (k == 3) ? dw_tile_wgrad<T>(x, dy, dw, stride, pad, dil, relu_in, st) : NPP_E_UNSUPPORTED;
+        if (rc == NPP_E_UNSUPPORTED)
+          rc = (k == 3) ? dw_bwd_weight_t<T, 3>(x, dy, dw, stride, pad, dil, relu_in, st)
+                        : dw_bwd_weight_t<T, 5>(x, dy, dw, stride, pad, dil, relu_in, st);
       } return rc;);
 }
 

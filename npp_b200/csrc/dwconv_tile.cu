@@ -1,0 +1,296 @@
+// Depthwise dilated 3x3 convolution with shared-memory halo staging — DilConvS.net[1]
+// (models/operations.py:213) forward, data gradient and weight gradient.
+//
+// The gather kernels in dwconv.cu read every input element nine times through L1/L2 (dilation 2/4 spreads the taps
+// over rows that never share a cache line), which caps them near 25 % of HBM bandwidth.  Here a CTA stages the
+// input tile of its TH x TW output pixels (+ halo of `dil` pixels per side) for 8 channel vectors (64 bf16 / 32
+// fp32 channels = one 128-byte row per pixel) in shared memory with fully coalesced 16-byte loads — the leading
+// nn.ReLU (:212) is applied once while staging — and every tap is then a conflict-free LDS.128: each input
+// element crosses the L2 -> SM link (TH+2d)(TW+2d)/(TH*TW) times instead of nine.
+//
+//   fwd   : y[p]  = sum_t relu(x)[p*stride - pad + t*dil] * w[t]
+//   dgrad : dx[p] = [x[p] > 0] * sum_t dy[p + pad - t*dil] * w[t]            (stride 1; same kernel, flipped taps)
+//   wgrad : dw[c,t] += sum_p dy[p] * relu(x)[p*stride - pad + t*dil]         persistent CTAs keep the 9 x 8
+//           accumulators of their channel vector in registers over all their tiles, one atomic per (CTA, c, t).
+#include "view.cuh"
+
+namespace npp {
+
+struct DwTileGeom {
+  int Hi, Wi, Ho, Wo, C, N;   // staged-tensor extents, produced-tensor extents
+  int stride, dil, off_h, off_w;  // staged row of tap r for produced row h: h*stride + off + r*dil
+  int TW, TH, RPP, PPT;       // produced tile, rows per pass (32 / TW), pixels per thread
+  int IH, IW;                 // staged tile extents
+  int tiles_w, tiles_h, cblocks, ntiles, slots;
+};
+
+template <typename T>
+__device__ __forceinline__ uint4 relu_packed(uint4 v);
+template <>
+__device__ __forceinline__ uint4 relu_packed<float>(uint4 v) {
+  v.x = (v.x & 0x80000000u) ? 0u : v.x; v.y = (v.y & 0x80000000u) ? 0u : v.y;
+  v.z = (v.z & 0x80000000u) ? 0u : v.z; v.w = (v.w & 0x80000000u) ? 0u : v.w;
+  return v;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t u) {
+  if (u & 0x00008000u) u &= 0xffff0000u;
+  if (u & 0x80000000u) u &= 0x0000ffffu;
+  return u;
+}
+template <>
+__device__ __forceinline__ uint4 relu_packed<__nv_bfloat16>(uint4 v) {
+  v.x = relu_bf16x2(v.x); v.y = relu_bf16x2(v.y); v.z = relu_bf16x2(v.z); v.w = relu_bf16x2(v.w);
+  return v;
+}
+
+// stage the input tile of (n, th, tw, channel block) into shared memory (zero outside the tensor = zero padding)
+template <typename T>
+__device__ __forceinline__ void dw_stage(uint4* tile, const DView<const T>& X, const DwTileGeom& g, int n, int ih0,
+                                         int iw0, int c0, int cvn, bool relu) {
+  constexpr int V = Pack<T>::N;
+  const int total = g.IH * g.IW * 8;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int cv = i & 7;
+    const int p = i >> 3;
+    const int pw = p % g.IW, ph = p / g.IW;
+    const int h = ih0 + ph, w = iw0 + pw;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (cv < cvn && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi) {
+      v = ldraw(X.at(n, h, w, c0 + cv * V));
+      if (relu) v = relu_packed<T>(v);
+    }
+    tile[i] = v;
+  }
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, const float* __restrict__ wgt,
+                                                      const DView<T> Y, const DView<const T> M, const DwTileGeom g,
+                                                      int relu_in) {
+  constexpr int V = Pack<T>::N;
+  extern __shared__ uint4 dw_tile_smem[];
+  uint4* tile = dw_tile_smem;
+  int b = blockIdx.x;
+  const int cb = b % g.cblocks; b /= g.cblocks;
+  const int tw = b % g.tiles_w; b /= g.tiles_w;
+  const int th = b % g.tiles_h;
+  const int n = b / g.tiles_h;
+  const int c0 = cb * 8 * V;
+  int cvn = (g.C - c0) / V;
+  if (cvn > 8) cvn = 8;
+  const int oh0 = th * g.TH, ow0 = tw * g.TW;
+  dw_stage<T>(tile, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn, !BWD && relu_in);
+  __syncthreads();
+  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  if (cv >= cvn) return;
+  const int c = c0 + cv * V;
+  float wr[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < V; ++i) wr[t][i] = __ldg(wgt + (c + i) * 9 + (BWD ? 8 - t : t));
+  const int pw = lane % g.TW, pr = lane / g.TW;
+  const int ow = ow0 + pw;
+  if (ow >= g.Wo) return;
+  for (int k = 0; k < g.PPT; ++k) {
+    const int ph = pr + k * g.RPP;
+    const int oh = oh0 + ph;
+    if (ph >= g.TH || oh >= g.Ho) break;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float v[V];
+        Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = fmaf(v[i], wr[r * 3 + q][i], acc[i]);
+      }
+    if (BWD && relu_in) {
+      float xv[V];
+      Pack<T>::load(M.at(n, oh, ow, c), xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = xv[i] > 0.f ? acc[i] : 0.f;
+    }
+    Pack<T>::store(Y.at(n, oh, ow, c), acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T> X, const DView<const T> DY,
+                                                            float* __restrict__ dw, const DwTileGeom g, int relu_in) {
+  constexpr int V = Pack<T>::N;
+  extern __shared__ uint4 dw_tile_smem[];
+  uint4* tile = dw_tile_smem;
+  const int cb = blockIdx.x % g.cblocks;
+  const int slot = blockIdx.x / g.cblocks;
+  const int c0 = cb * 8 * V;
+  int cvn = (g.C - c0) / V;
+  if (cvn > 8) cvn = 8;
+  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = c0 + cv * V;
+  const int pw = lane % g.TW, pr = lane / g.TW;
+  float acc[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[t][i] = 0.f;
+  for (int tix = slot; tix < g.ntiles; tix += g.slots) {
+    int b = tix;
+    const int tw = b % g.tiles_w; b /= g.tiles_w;
+    const int th = b % g.tiles_h;
+    const int n = b / g.tiles_h;
+    const int oh0 = th * g.TH, ow0 = tw * g.TW;
+    __syncthreads();  // the previous tile's readers are done
+    dw_stage<T>(tile, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn, relu_in != 0);
+    __syncthreads();
+    const int ow = ow0 + pw;
+    if (cv < cvn && ow < g.Wo) {
+      for (int k = 0; k < g.PPT; ++k) {
+        const int ph = pr + k * g.RPP;
+        const int oh = oh0 + ph;
+        if (ph >= g.TH || oh >= g.Ho) break;
+        float d[V];
+        Pack<T>::load(DY.at(n, oh, ow, c), d);
+        const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float v[V];
+            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[r * 3 + q][i] = fmaf(d[i], v[i], acc[r * 3 + q][i]);
+          }
+      }
+    }
+  }
+  // fold the 32 pixel lanes of every channel vector, one atomic per (CTA, channel, tap)
+  float* red = reinterpret_cast<float*>(tile);  // 256 * V floats <= the staged tile
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = acc[t][i];
+    __syncthreads();
+    if (threadIdx.x < 8 * V) {
+      const int cvj = threadIdx.x / V, ij = threadIdx.x % V;
+      if (cvj < cvn) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) s += red[((l * 8) + cvj) * V + ij];
+        atomicAdd(dw + (int64_t)(c0 + threadIdx.x) * 9 + t, s);
+      }
+    }
+  }
+}
+
+// Tile geometry; returns false when the shape should stay on the gather kernels (stride-2 tiles that would not fit).
+static bool dw_tile_geom(DwTileGeom& g, int N, int Hi, int Wi, int Ho, int Wo, int C, int V, int stride, int dil,
+                         int off_h, int off_w, size_t* smem) {
+  g.N = N; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo; g.C = C;
+  g.stride = stride; g.dil = dil; g.off_h = off_h; g.off_w = off_w;
+  int best = 32;
+  int64_t best_pad = -1;
+  for (int tw = 32; tw >= 8; tw >>= 1) {
+    const int64_t padded = cdiv64(Wo, tw) * tw;
+    if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = tw; }
+  }
+  g.TW = best;
+  g.RPP = 32 / g.TW;
+  int th = 256 / g.TW;
+  const int hround = (int)(cdiv64(Ho, g.RPP) * g.RPP);
+  if (th > hround) th = hround;
+  g.TH = th;
+  g.PPT = g.TH / g.RPP;
+  g.IH = (g.TH - 1) * stride + 2 * dil + 1;
+  g.IW = (g.TW - 1) * stride + 2 * dil + 1;
+  g.tiles_w = (int)cdiv64(Wo, g.TW);
+  g.tiles_h = (int)cdiv64(Ho, g.TH);
+  g.cblocks = (int)cdiv64(C, 8 * V);
+  const int64_t ntiles = (int64_t)N * g.tiles_h * g.tiles_w;
+  if (ntiles * g.cblocks > 0x7fffffff) return false;
+  g.ntiles = (int)ntiles;
+  g.slots = 1;
+  *smem = (size_t)g.IH * g.IW * 8 * 16;
+  if (*smem < (size_t)256 * V * 4) *smem = (size_t)256 * V * 4;
+  return *smem <= 100 * 1024;
+}
+
+// opt-in to > 48 KB dynamic shared memory, once per kernel instantiation (K is a distinct type per instantiation
+// only through TAG)
+template <int TAG, typename K>
+static int dw_set_smem(K kernel, const char* name) {
+  static bool done = false;
+  if (done) return NPP_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) { set_error(name, e); return NPP_E_CUDA; }
+  done = true;
+  return NPP_OK;
+}
+
+// returns NPP_E_UNSUPPORTED when the caller should use the gather kernels instead
+template <typename T>
+int dw_tile_fwd(const npp_view4* x, const float* w, const npp_view4* y, int stride, int pad, int dil, int relu_in,
+                cudaStream_t st) {
+  DwTileGeom g;
+  size_t smem;
+  if (!dw_tile_geom(g, y->n, x->h, x->w, y->h, y->w, y->c, Pack<T>::N, stride, dil, -pad, -pad, &smem))
+    return NPP_E_UNSUPPORTED;
+  int rc = dw_set_smem<sizeof(T) * 10 + 0>(dw_tile_kernel<T, false>, "cudaFuncSetAttribute(dw_tile_fwd)");
+  if (rc) return rc;
+  const auto X = dview<const T>(x);
+  dw_tile_kernel<T, false><<<g.ntiles * g.cblocks, 256, smem, st>>>(X, w, dview<T>(y), X, g, relu_in);
+  NPP_CHECK_LAUNCH("dw_tile_fwd");
+  return NPP_OK;
+}
+
+template <typename T>
+int dw_tile_dgrad(const npp_view4* x, const float* w, const npp_view4* dy, const npp_view4* dx, int stride, int pad,
+                  int dil, int relu_in, cudaStream_t st) {
+  if (stride != 1) return NPP_E_UNSUPPORTED;
+  DwTileGeom g;
+  size_t smem;
+  // dx[h] = sum_t dy[h + pad - t*dil] w[t] = sum_t' dy[h + pad - 2*dil + t'*dil] w[2 - t']
+  if (!dw_tile_geom(g, dx->n, dy->h, dy->w, dx->h, dx->w, dx->c, Pack<T>::N, 1, dil, pad - 2 * dil, pad - 2 * dil, &smem))
+    return NPP_E_UNSUPPORTED;
+  int rc = dw_set_smem<sizeof(T) * 10 + 1>(dw_tile_kernel<T, true>, "cudaFuncSetAttribute(dw_tile_dgrad)");
+  if (rc) return rc;
+  dw_tile_kernel<T, true><<<g.ntiles * g.cblocks, 256, smem, st>>>(dview<const T>(dy), w, dview<T>(dx),
+                                                                    dview<const T>(x), g, relu_in);
+  NPP_CHECK_LAUNCH("dw_tile_dgrad");
+  return NPP_OK;
+}
+
+template <typename T>
+int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride, int pad, int dil, int relu_in,
+                  cudaStream_t st) {
+  DwTileGeom g;
+  size_t smem;
+  if (!dw_tile_geom(g, dy->n, x->h, x->w, dy->h, dy->w, dy->c, Pack<T>::N, stride, dil, -pad, -pad, &smem))
+    return NPP_E_UNSUPPORTED;
+  int rc = dw_set_smem<sizeof(T) * 10 + 2>(dw_tile_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_tile_wgrad)");
+  if (rc) return rc;
+  int slots = (2 * sm_count()) / g.cblocks;
+  if (slots < 1) slots = 1;
+  if (slots > g.ntiles) slots = g.ntiles;
+  g.slots = slots;
+  dw_tile_wgrad_kernel<T><<<slots * g.cblocks, 256, smem, st>>>(dview<const T>(x), dview<const T>(dy), dw, g, relu_in);
+  NPP_CHECK_LAUNCH("dw_tile_wgrad");
+  return NPP_OK;
+}
+
+template int dw_tile_fwd<float>(const npp_view4*, const float*, const npp_view4*, int, int, int, int, cudaStream_t);
+template int dw_tile_fwd<__nv_bfloat16>(const npp_view4*, const float*, const npp_view4*, int, int, int, int,
+                                        cudaStream_t);
+template int dw_tile_dgrad<float>(const npp_view4*, const float*, const npp_view4*, const npp_view4*, int, int, int,
+                                  int, cudaStream_t);
+template int dw_tile_dgrad<__nv_bfloat16>(const npp_view4*, const float*, const npp_view4*, const npp_view4*, int, int,
+                                          int, int, cudaStream_t);
+template int dw_tile_wgrad<float>(const npp_view4*, const npp_view4*, float*, int, int, int, int, cudaStream_t);
+template int dw_tile_wgrad<__nv_bfloat16>(const npp_view4*, const npp_view4*, float*, int, int, int, int, cudaStream_t);
+
+}  // namespace npp

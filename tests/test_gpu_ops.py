@@ -156,3 +156,55 @@ def test_maxpool_ties_route_to_first_max(dtype, lib_built):
     ym.sum().backward()
     assert torch.equal(ym.cpu(), yo)
     assert torch.equal(xm.grad.cpu(), xo.grad)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 128, 96, 96, 2, 1), (2, 64, 48, 48, 4, 1), (3, 32, 24, 24, 2, 1),
+                                   (2, 256, 12, 12, 4, 1), (2, 64, 48, 48, 2, 2), (2, 40, 23, 17, 2, 1),
+                                   (1, 72, 33, 50, 4, 2), (2, 32, 96, 96, 1, 1)],
+                         ids=lambda s: "n%dc%d_%dx%d_d%ds%d" % s)
+@pytest.mark.parametrize("relu_in", [0, 1])
+def test_depthwise_conv_vs_torch(shape, relu_in, dtype, lib_built):
+    """Depthwise dilated 3x3 (DilConvS.net[1], operations.py:213) at the network's real shapes — the shared-memory
+    tiled kernels (multi-tile images, partial channel blocks, ragged tiles) and the gather fallback (stride 2) —
+    forward, input gradient and weight gradient against torch's grouped convolution on the same rounded inputs."""
+    import torch.nn.functional as TF
+    from npp_b200 import functional as F_
+    n, c, h, w, dil, stride = shape
+    gen = torch.Generator().manual_seed(h * 131 + c + dil)
+    x = torch.randn(n, c, h, w, generator=gen)
+    wt = torch.randn(c, 1, 3, 3, generator=gen) * 0.3
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    xr = x.double().requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
+    yr = TF.conv2d(torch.relu(xr) if relu_in else xr, wr, None, stride, dil, dil, groups=c)
+    go = torch.randn(yr.shape, generator=gen)
+    if dtype == torch.bfloat16:
+        go = go.bfloat16().float()
+    (yr * go.double()).sum().backward()
+    xm = F_.to_internal(x.cuda(), dtype).detach().requires_grad_(True)
+    wm = wt.cuda().requires_grad_(True)
+    ym = F_.dwconv2d(xm, wm, stride, dil, dil, relu_in)
+    ym.backward(F_.to_internal(go.cuda(), dtype))
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    assert rel_err(F_.from_internal(ym), yr) < tol
+    assert rel_err(F_.from_internal(xm.grad), xr.grad) < tol
+    assert rel_err(wm.grad, wr.grad) < (1e-4 if dtype == torch.float32 else 2e-3)
+
+
+def test_depthwise_conv_on_channel_slice(lib_built):
+    """The supernet's MixedOp feeds depthwise convs a channel-slice view (model_search_interact.py:59)."""
+    import torch.nn.functional as TF
+    from npp_b200 import functional as F_
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 40, 40, generator=gen).bfloat16().float()
+    wt = torch.randn(32, 1, 3, 3, generator=gen) * 0.3
+    xm = F_.to_internal(x.cuda(), torch.bfloat16)
+    lo = F_.alias(xm, 0, 32)
+    hi = F_.alias(xm, 32, 32)
+    for view, ref in ((lo, x[:, :32]), (hi, x[:, 32:])):
+        y = F_.dwconv2d(view, wt.cuda(), 1, 2, 2, 1)
+        want = TF.conv2d(torch.relu(ref), wt, None, 1, 2, 2, groups=32)
+        assert rel_err(F_.from_internal(y), want) < 6e-3
