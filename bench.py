@@ -199,19 +199,19 @@ def main():
     eager = engine.TrainStep(model, cpose, cpar, opt, args.batch, args.size, use_graph=False, world_size=world)
     eager.images, eager.par_lab, eager.edge_lab = step.images, step.par_lab, step.edge_lab
     eager.pose_gt, eager.pose_aux_gt = step.pose_gt, step.pose_aux_gt
+    torch.cuda.reset_peak_memory_stats()
     eager.run()
     torch.cuda.synchronize()
-    torch.cuda.reset_peak_memory_stats()
+    peak_mem = torch.cuda.max_memory_allocated()
     _lib.trace_begin()
     eager.run()
     trace = _lib.trace_end()
     torch.cuda.synchronize()
-    peak_mem = torch.cuda.max_memory_allocated()
 
     def time_class(names, reps=3):
         calls = [t for t in trace if t[0] in names]
         if not calls:
-            return {"calls": 0, "ms": 0.0, "flops": 0.0}
+            return {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0}
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -229,10 +229,18 @@ def main():
             g.replay()
         e1.record()
         torch.cuda.synchronize()
-        return {"calls": len(calls), "ms": e0.elapsed_time(e1) / reps, "flops": sum(t[2][0] for t in calls)}
+        return {"calls": len(calls), "ms": e0.elapsed_time(e1) / reps, "flops": sum(t[2][0] for t in calls),
+                "bytes": sum(t[2][1] for t in calls)}
 
     prof = {"conv_gemm(fprop+dgrad)": time_class(("npp_conv2d_fwd", "npp_conv2d_dgrad")),
-            "conv_wgrad": time_class(("npp_conv2d_wgrad",))}
+            "conv_wgrad": time_class(("npp_conv2d_wgrad", "npp_conv2d_wgrad_ws"))}
+    # every other kernel class of the step (all HBM-bound), same method: the class's launches of one step re-issued
+    # back to back inside a CUDA graph; algorithmic bytes = what the call's NHWC views span (each view once; no credit
+    # for halos, re-reads, fp32 coefficient vectors or workspaces).  Not replayed: the optimizer update and the
+    # BatchNorm finalize (they would advance parameters / running statistics), NCCL.
+    skip = {"npp_conv2d_fwd", "npp_conv2d_dgrad", "npp_conv2d_wgrad", "npp_conv2d_wgrad_ws", "npp_adam_step", "npp_bn_finalize"}
+    for name in sorted(set(t[0] for t in trace) - skip):
+        prof[name] = time_class((name,))
     del trace
     torch.cuda.empty_cache()
 
@@ -293,9 +301,19 @@ def main():
         gemm = prof["conv_gemm(fprop+dgrad)"]
         achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
         kernels = {}
-        for name, d in prof.items():
-            kernels[name] = {"launches_per_step": d["calls"], "ms_per_step": round(d["ms"], 3),
-                             "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] and d["ms"] else None}
+        for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            if d["ms"] < 0.05:
+                continue
+            k = {"launches_per_step": d["calls"], "ms_per_step": round(d["ms"], 3)}
+            if d["flops"]:
+                k["tflops"] = round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1)
+                k["tensor_frac"] = round(k["tflops"] / tf_peak, 3)
+            elif d["bytes"]:
+                k["gbs"] = round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1)
+                k["hbm_frac"] = round(k["gbs"] / hbm_peak, 3)
+            kernels[name] = k
+        bw = [d for n_, d in prof.items() if not d["flops"] and d["bytes"]]
+        bw_ms, bw_bytes = sum(d["ms"] for d in bw), sum(d["bytes"] for d in bw)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -318,6 +336,10 @@ def main():
                          "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["calls"]), "peak_source": peak_src,
                          "share_of_step": gemm["ms"] / (ms_total / args.steps)},
             "kernels": kernels,
+            "kernel_ms_total": round(sum(d["ms"] for d in prof.values()), 3),
+            "hbm_class": {"ms_per_step": round(bw_ms, 3), "gbs": round(bw_bytes / (bw_ms * 1e-3) / 1e9, 1) if bw_ms else None,
+                          "frac": round(bw_bytes / (bw_ms * 1e-3) / 1e9 / hbm_peak, 3) if bw_ms else None,
+                          "what": "all bandwidth-bound kernel classes of the step together (algorithmic bytes / time)"},
             "hbm_peak_gbs": hbm_peak,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -83,6 +83,14 @@ int npp_conv2d_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_
                      int kh, int kw, int stride, int pad, int dil, int in_h_off, int in_w_off,
                      npp_stream_t stream);
 
+/* Same, with a caller-provided workspace (npp_conv2d_wgrad_workspace_bytes() bytes, 16-byte aligned, reusable by
+ * every call on one stream): the split-K partial tiles are written there with plain stores and folded into dw (+=)
+ * by a second kernel instead of millions of scattered fp32 atomics.  Too small / NULL = the atomic path. */
+int64_t npp_conv2d_wgrad_workspace_bytes(void);
+int npp_conv2d_wgrad_ws(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin,
+                        int kh, int kw, int stride, int pad, int dil, int in_h_off, int in_w_off,
+                        void* workspace, int64_t workspace_bytes, npp_stream_t stream);
+
 /* fp32 master weight in torch OIHW order [cout,cin,taps] -> packed OHWI [cout_pad,taps,cin_pad]
  * (w) and/or its transpose [cin_pad,taps,cout_pad] (wt), zero padded, stored as out_dtype
  * (NPP_BF16 for the tcgen05 path, NPP_F32 for validation mode); either output may be NULL.

@@ -62,8 +62,15 @@ def dtype_code(t):
     raise RuntimeError("npp_b200 kernels take bf16 or fp32 activations, got %s" % t.dtype)
 
 
+_pending = []        # while tracing: tensors behind the views / pointers of the ABI call being assembled
+_pending_bytes = [0]  # ... and the bytes its NHWC views span (algorithmic traffic: every view once)
+
+
 def view(t):
     """npp_view4 over a 4-D tensor with logical shape [N, C, H, W] and channel stride 1 (channels_last)."""
+    if _trace is not None:
+        _pending.append(t)
+        _pending_bytes[0] += t.numel() * t.element_size()
     if t.dim() != 4:
         raise RuntimeError("expected a 4-D NCHW-shaped tensor, got %s" % (tuple(t.shape),))
     n, c, h, w = t.shape
@@ -87,6 +94,8 @@ def fptr(t):
         return ctypes.c_void_p(0)
     if not t.is_contiguous():
         raise RuntimeError("expected a contiguous tensor")
+    if _trace is not None:
+        _pending.append(t)
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -106,8 +115,11 @@ def call(name, *args, work=None, keep=None):
     tensors behind its pointer arguments; both are only used by bench.py's live roofline measurement (event
     profiler / call trace that is replayed back-to-back)."""
     fn = getattr(lib(), name)
-    if _trace is not None and keep is not None:
-        _trace.append((name, args, work or (0.0, 0.0), keep))
+    if _trace is not None:
+        w = work or (0.0, float(_pending_bytes[0]))
+        _trace.append((name, args, w, (tuple(_pending), keep)))
+        del _pending[:]
+        _pending_bytes[0] = 0
     if _prof is None:
         check(fn(*args), name)
         return
@@ -119,9 +131,12 @@ def call(name, *args, work=None, keep=None):
 
 
 def trace_begin():
-    """Starts recording every traced ABI call (those passing keep=) with its arguments kept alive."""
+    """Starts recording every ABI call with the tensors behind its arguments kept alive: (name, args, (flops,
+    bytes), keep).  bytes = what the call's NHWC views span unless the caller passed work=."""
     global _trace
     _trace = []
+    del _pending[:]
+    _pending_bytes[0] = 0
 
 
 def trace_end():

@@ -144,7 +144,7 @@ int conv_fwd(const npp_view4* x, const void* w, const float* bias, const npp_vie
 int conv_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, int kh, int kw, int stride, int pad, int dil,
                int hoff, int woff, cudaStream_t st);
 int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, int kh, int kw, int stride,
-               int pad, int dil, int hoff, int woff, cudaStream_t st);
+               int pad, int dil, int hoff, int woff, float* ws, size_t ws_bytes, cudaStream_t st);
 int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
                 int out_dtype, cudaStream_t st);
 }  // namespace tc
@@ -168,7 +168,19 @@ int npp_conv2d_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, i
 int npp_conv2d_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, int kh, int kw,
                      int stride, int pad, int dil, int in_h_off, int in_w_off, npp_stream_t stream) {
   if (!x || !dy) return NPP_E_INVALID;
-  return tc::conv_wgrad(x, dy, dw, dw_cout, dw_cin, kh, kw, stride, pad, dil, in_h_off, in_w_off, as_stream(stream));
+  return tc::conv_wgrad(x, dy, dw, dw_cout, dw_cin, kh, kw, stride, pad, dil, in_h_off, in_w_off, nullptr, 0,
+                        as_stream(stream));
+}
+int64_t npp_conv2d_wgrad_workspace_bytes(void) {
+  // one fp32 partial tile set per CTA: <= sm_count CTAs x max(3 x 128 x 128, 128 x 256) floats
+  return (int64_t)sm_count() * 3 * 128 * 128 * (int64_t)sizeof(float);
+}
+int npp_conv2d_wgrad_ws(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, int kh, int kw,
+                        int stride, int pad, int dil, int in_h_off, int in_w_off, void* workspace,
+                        int64_t workspace_bytes, npp_stream_t stream) {
+  if (!x || !dy || workspace_bytes < 0) return NPP_E_INVALID;
+  return tc::conv_wgrad(x, dy, dw, dw_cout, dw_cin, kh, kw, stride, pad, dil, in_h_off, in_w_off,
+                        static_cast<float*>(workspace), (size_t)workspace_bytes, as_stream(stream));
 }
 int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
                     int out_dtype, npp_stream_t stream) {

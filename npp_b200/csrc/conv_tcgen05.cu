@@ -22,6 +22,7 @@
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace npp {
 namespace tc {
@@ -353,7 +354,7 @@ struct WgradCfg {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTable taps,
-                  float* __restrict__ dw) {
+                  float* __restrict__ dw, float* __restrict__ ws) {
   using Cfg = WgradCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int SLAB = Cfg::KP * 128;  // bytes of one [64 pixels x 64 channels] slab
@@ -457,19 +458,33 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
       const int bt = taps.btap[tap];
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
+      // split-K partial of this CTA: plain coalesced stores into the workspace [k slice][tile][128][BN] (folded by
+      // wgrad_reduce_kernel) — or, without a workspace, fp32 atomics straight into dW
+      float* part = ws ? ws + ((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 128 + (q * 32 + lane)) * BN
+                       : nullptr;
 #pragma unroll 1
       for (int c32 = 0; c32 < BN / 32; ++c32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c32 * 32, r);
         tmem_ld_wait();
+        if (part) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int ci = ci_blk * BN + c32 * 32 + j;
-          if (co < g.cout && ci < g.cin)
-            atomicAdd(dw + (static_cast<int64_t>(co) * g.cin + ci) * g.num_taps + bt, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(part + c32 * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = ci_blk * BN + c32 * 32 + j;
+            if (co < g.cout && ci < g.cin)
+              atomicAdd(dw + (static_cast<int64_t>(co) * g.cin + ci) * g.num_taps + bt, __uint_as_float(r[j]));
+          }
         }
       }
     }
+  } else if (ws && warp >= kEpiWarp0) {
+    // no pixels for this k slice: its partial is zero
+    float* part = ws + ((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 128 + ((warp & 3) * 32 + lane)) * BN;
+    for (int j = 0; j < BN; j += 4) *reinterpret_cast<uint4*>(part + j) = make_uint4(0u, 0u, 0u, 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -479,6 +494,243 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
   }
 }
 
+
+
+// =================================================================================================
+// wgrad for 3x3 / stride 1 / dilation 1 convolutions (62 % of the network's FLOPs): one CTA owns a COLUMN of three
+// vertical taps.  The per-tap kernel above re-reads dY and X once per tap — 18 operand tiles per 9 taps, which made
+// it L2->SM-bandwidth bound (ncu: 620 TFLOP/s at 64 flop/byte).  Here the X box carries one halo row above and
+// below (th+2 rows of tw pixels), so the three taps are the SAME shared-memory tile read at row offsets
+// 0 / tw / 2*tw pixels — multiples of 1024 bytes, i.e. whole SWIZZLE_128B atoms, so the UMMA descriptor just starts
+// later — and dY is loaded once for all three: 3 MMAs groups per (dY + X-with-halo) load, three 128 x BN fp32
+// accumulators in TMEM.  Grid: (3 tap columns x Cout blocks x Cin blocks, split-K over pixel tiles).
+// =================================================================================================
+struct W3Geom {
+  int tw, th;                // pixel tile of one k-block: tw * th == 64 pixels of one image
+  int tiles_w, tiles_h;      // tiles per image
+  int total_ptiles;          // tiles_w * tiles_h * N
+  int co_blocks, ci_blocks;  // of 128 / BN
+  int cout, cin;
+  int ksplit, stages;
+  int bslab;                 // bytes of one 64-channel X slab: (th + 2) * tw * 128
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                   const W3Geom g, float* __restrict__ dw, float* __restrict__ ws) {
+  constexpr int A_BYTES = 2 * 64 * 128;  // two 64-channel slabs of dY, 64 pixels each
+  constexpr int ASLAB = 64 * 128;
+  constexpr int TMEM_COLS = (3 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full_bar = smem_base;            // 8 x 8 B
+  const uint32_t empty_bar = smem_base + 64;      // 8 x 8 B
+  const uint32_t tfull_bar = smem_base + 128;
+  const uint32_t tmem_slot = smem_base + 136;
+  const uint32_t ring = smem_base + 1024;
+  const uint32_t b_bytes = (BN / 64) * g.bslab;
+  const uint32_t stage_bytes = A_BYTES + b_bytes;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int ot = blockIdx.x;
+  const int ci_blk = ot % g.ci_blocks;
+  ot /= g.ci_blocks;
+  const int co_blk = ot % g.co_blocks;
+  const int q = ot / g.co_blocks;  // horizontal tap index 0..2 of this CTA's tap column
+  const int p_begin = static_cast<int>((static_cast<int64_t>(g.total_ptiles) * blockIdx.y) / g.ksplit);
+  const int p_end = static_cast<int>((static_cast<int64_t>(g.total_ptiles) * (blockIdx.y + 1)) / g.ksplit);
+  const int num_k = p_end - p_begin;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_dy);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int p = p_begin; p < p_end; ++p) {
+          int pt = p;
+          const int w0 = (pt % g.tiles_w) * g.tw;
+          pt /= g.tiles_w;
+          const int h0 = (pt % g.tiles_h) * g.th;
+          const int n0 = pt / g.tiles_h;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(full_bar + 8 * stage, stage_bytes);
+          const uint32_t sa = ring + stage * stage_bytes;
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            tma_load_4d(sa + s * ASLAB, &map_dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
+#pragma unroll
+          for (int s = 0; s < BN / 64; ++s)
+            tma_load_4d(sb + s * g.bslab, &map_x, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + q - 1, h0 - 1,
+                        n0);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = ring + stage * stage_bytes;
+          const uint32_t sb = sa + A_BYTES;
+          // MN-major SW128: 64-channel slabs LBO apart, 8-pixel K groups SBO = 1024 B apart
+          const uint64_t da = make_smem_desc_sw128(sa, ASLAB, 1024);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            // vertical tap r reads the X tile r image rows (r * tw pixels = r * tw * 128 bytes) further down
+            const uint64_t db = make_smem_desc_sw128(sb + r * g.tw * 128, g.bslab, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 64 pixels = 4 x K16; 16 pixels = 2048 B -> +128 in (addr >> 4)
+              umma_f16(tmem_base + r * BN, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar);
+      }
+    } else if (warp >= kEpiWarp0) {
+      const int qw = warp & 3;
+      const int co = co_blk * 128 + qw * 32 + lane;
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      // workspace layout [k slice][tile][3 vertical taps][128][BN]
+      float* part = ws ? ws + ((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 3 * 128 + (qw * 32 + lane)) * BN
+                       : nullptr;
+#pragma unroll 1
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+        for (int c32 = 0; c32 < BN / 32; ++c32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + r * BN + c32 * 32, v);
+          tmem_ld_wait();
+          if (part) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(part + static_cast<size_t>(r) * 128 * BN + c32 * 32 + j) =
+                  make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int ci = ci_blk * BN + c32 * 32 + j;
+              if (co < g.cout && ci < g.cin)
+                atomicAdd(dw + (static_cast<int64_t>(co) * g.cin + ci) * 9 + r * 3 + q, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  } else if (ws && warp >= kEpiWarp0) {
+    float* part = ws + ((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 3 * 128 + ((warp & 3) * 32 + lane)) * BN;
+    for (int r = 0; r < 3; ++r)
+      for (int j = 0; j < BN; j += 4)
+        *reinterpret_cast<uint4*>(part + static_cast<size_t>(r) * 128 * BN + j) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// Second phase of the split-K weight gradient: dW[co, ci, tap] += sum over k slices of the partial tiles the wgrad
+// CTAs stored.  ws layout [k slice][tile][R][128][BN], tile = (tap group * co_blocks + co_blk) * ci_blocks + ci_blk.
+// The first version combined partials with fp32 atomics from every CTA's epilogue: 2-7 M scattered red.global
+// operations landing at the same moment cost 30-45 us per launch, more than the MMA main loop itself.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit, int tiles, int R, int BN,
+                    int co_blocks, int ci_blocks, int cout, int cin, int num_taps, const TapTable taps, int mode3,
+                    int kgroups) {
+  // block = E consecutive elements x kgroups k groups (E * kgroups == 256): with many k slices (50-150, each
+  // per_slice floats apart) one thread per element would walk them serially, so up to 8 threads share an element
+  // and fold through shared memory; with few slices kgroups == 1 and every thread owns an element.
+  __shared__ float red[256];
+  const int E = 256 / kgroups;
+  const int el = threadIdx.x % E, kg = threadIdx.x / E;
+  const int64_t per_slice = static_cast<int64_t>(tiles) * R * 128 * BN;  // multiple of 256
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * E; base < per_slice; base += static_cast<int64_t>(gridDim.x) * E) {
+    const int64_t idx = base + el;
+    const float* p = ws + idx;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = kg;
+    for (; k + 3 * kgroups < ksplit; k += 4 * kgroups) {
+      s0 += p[k * per_slice];
+      s1 += p[(k + kgroups) * per_slice];
+      s2 += p[(k + 2 * kgroups) * per_slice];
+      s3 += p[(k + 3 * kgroups) * per_slice];
+    }
+    for (; k < ksplit; k += kgroups) s0 += p[k * per_slice];
+    float t = (s0 + s1) + (s2 + s3);
+    if (kgroups > 1) {
+      red[threadIdx.x] = t;
+      __syncthreads();
+      if (kg == 0)
+        for (int i = 1; i < kgroups; ++i) t += red[i * E + el];
+    }
+    if (kg == 0) {
+      const int ci_l = static_cast<int>(idx % BN);
+      int64_t u = idx / BN;
+      const int co_l = static_cast<int>(u % 128);
+      u /= 128;
+      const int r = static_cast<int>(u % R);
+      const int tile = static_cast<int>(u / R);
+      const int ci_blk = tile % ci_blocks;
+      const int co_blk = (tile / ci_blocks) % co_blocks;
+      const int tg = tile / (ci_blocks * co_blocks);
+      const int co = co_blk * 128 + co_l, ci = ci_blk * BN + ci_l;
+      if (co < cout && ci < cin) {
+        const int tap = mode3 ? r * 3 + tg : taps.btap[tg];
+        dw[(static_cast<int64_t>(co) * cin + ci) * num_taps + tap] += t;
+      }
+    }
+    if (kgroups > 1) __syncthreads();
+  }
+}
+
+static int launch_wgrad_reduce(const float* ws, float* dw, int ksplit, int tiles, int R, int BN, int co_blocks,
+                               int ci_blocks, int cout, int cin, int num_taps, const TapTable& taps, int mode3,
+                               cudaStream_t st) {
+  const int64_t per_slice = (int64_t)tiles * R * 128 * BN;
+  // one thread per element (1 KB contiguous per block and slice) unless that leaves most SMs without a block:
+  // then up to 8 threads share an element's k slices
+  int kgroups = 1;
+  while (kgroups < 8 && (per_slice / 256) * kgroups < 2 * 148 && kgroups * 4 <= ksplit) kgroups <<= 1;
+  const int E = 256 / kgroups;
+  int64_t blocks = per_slice / E;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dw, ksplit, tiles, R, BN, co_blocks, ci_blocks, cout, cin,
+                                                        num_taps, taps, mode3, kgroups);
+  NPP_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return NPP_OK;
+}
 
 // =================================================================================================
 // Host side: tensor maps, tile geometry, launches
@@ -756,7 +1008,8 @@ int conv_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, int kh,
 }
 
 template <int BN>
-static int launch_wgrad(const WMaps& maps, const WGeom& g, const TapTable& taps, float* dw, cudaStream_t st) {
+static int launch_wgrad(const WMaps& maps, const WGeom& g, const TapTable& taps, float* dw, float* ws, size_t ws_bytes,
+                        cudaStream_t st) {
   using Cfg = WgradCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -765,16 +1018,99 @@ static int launch_wgrad(const WMaps& maps, const WGeom& g, const TapTable& taps,
     attr_set = true;
   }
   dim3 grid(g.num_taps * g.co_blocks * g.ci_blocks, g.ksplit);
-  conv_wgrad_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, dw);
+  const size_t need = (size_t)grid.x * grid.y * 128 * BN * sizeof(float);
+  // one k slice: its atomics are the only writers anyway; narrow layers (<= 64 x 64): most of the 128 x BN tile is
+  // masked out, the few atomics are cheaper than storing and re-reading whole tiles
+  if (g.ksplit == 1 || need > ws_bytes || (g.cout <= 64 && g.cin <= 64)) ws = nullptr;
+  conv_wgrad_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, dw, ws);
   NPP_CHECK_LAUNCH("conv_wgrad_kernel");
+  if (ws)
+    return launch_wgrad_reduce(ws, dw, g.ksplit, (int)grid.x, 1, BN, g.co_blocks, g.ci_blocks, g.cout, g.cin,
+                               g.num_taps, taps, 0, st);
   return NPP_OK;
 }
 
+constexpr int kW3SmemMax = 225 * 1024;
+
+template <int BN>
+static int launch_wgrad3(const CUtensorMap& mx, const CUtensorMap& mdy, const W3Geom& g, float* dw, float* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kW3SmemMax);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_wgrad3)", e); return NPP_E_CUDA; }
+    attr_set = true;
+  }
+  const int stage_bytes = 2 * 64 * 128 + (BN / 64) * g.bslab;
+  const int smem = 2048 + g.stages * stage_bytes;
+  dim3 grid(3 * g.co_blocks * g.ci_blocks, g.ksplit);
+  const size_t need = (size_t)grid.x * grid.y * 3 * 128 * BN * sizeof(float);
+  if (g.ksplit == 1 || need > ws_bytes || (g.cout <= 64 && g.cin <= 64)) ws = nullptr;
+  conv_wgrad3_kernel<BN><<<grid, kThreads, smem, st>>>(mx, mdy, g, dw, ws);
+  NPP_CHECK_LAUNCH("conv_wgrad3_kernel");
+  if (ws) {
+    TapTable none;
+    memset(&none, 0, sizeof none);
+    return launch_wgrad_reduce(ws, dw, g.ksplit, (int)grid.x, 3, BN, g.co_blocks, g.ci_blocks, g.cout, g.cin, 9, none,
+                               1, st);
+  }
+  return NPP_OK;
+}
+
+// 3x3 / stride 1 / dilation 1 / pad 1 weight gradient with vertical-tap sharing; NPP_E_UNSUPPORTED = not this shape.
+static int conv_wgrad3(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, float* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  if (x->h != dy->h || x->w != dy->w) return NPP_E_UNSUPPORTED;
+  // pixel tile (tw, th), tw * th == 64, tw >= 8 so that a one-row shift is a whole number of 1024-byte swizzle atoms
+  int best_tw = 0, best_th = 0;
+  double best_cost = 1e300;
+  for (int tw = 8; tw <= 64; tw <<= 1) {
+    const int th = 64 / tw;
+    const double cost = (double)(cdiv64(dy->w, tw) * tw) * (double)(cdiv64(dy->h, th) * th);
+    if (cost < best_cost || (cost == best_cost && th > best_th)) { best_cost = cost; best_tw = tw; best_th = th; }
+  }
+  W3Geom g;
+  memset(&g, 0, sizeof g);
+  g.tw = best_tw; g.th = best_th;
+  g.tiles_w = (int)cdiv64(dy->w, g.tw);
+  g.tiles_h = (int)cdiv64(dy->h, g.th);
+  const int64_t ptiles = (int64_t)g.tiles_w * g.tiles_h * dy->n;
+  if (ptiles > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  g.total_ptiles = (int)ptiles;
+  const int bn = dw_cin <= 64 ? 64 : 128;
+  g.co_blocks = (int)cdiv64(dw_cout, 128);
+  g.ci_blocks = (int)cdiv64(dw_cin, bn);
+  g.cout = dw_cout; g.cin = dw_cin;
+  g.bslab = (g.th + 2) * g.tw * 128;
+  const int stage_bytes = 2 * 64 * 128 + (bn / 64) * g.bslab;
+  int stages = (kW3SmemMax - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return NPP_E_UNSUPPORTED;
+  g.stages = stages;
+  const int out_tiles = 3 * g.co_blocks * g.ci_blocks;
+  int ks = sm_count() / out_tiles;
+  if (ks > g.total_ptiles / 2) ks = g.total_ptiles / 2;
+  if (ks < 1) ks = 1;
+  g.ksplit = ks;
+  CUtensorMap mx, mdy;
+  int rc = encode_act_map(&mx, x->ptr, x->c, x->w, x->h, x->n, x->sw, x->sh, x->sn, g.tw, g.th + 2, 1);
+  if (rc) return rc;
+  rc = encode_act_map(&mdy, dy->ptr, dy->c, dy->w, dy->h, dy->n, dy->sw, dy->sh, dy->sn, g.tw, g.th, 1);
+  if (rc) return rc;
+  return bn == 64 ? launch_wgrad3<64>(mx, mdy, g, dw, ws, ws_bytes, st)
+                  : launch_wgrad3<128>(mx, mdy, g, dw, ws, ws_bytes, st);
+}
+
 int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, int dw_cin, int kh, int kw,
-               int stride, int pad, int dil, int hoff, int woff, cudaStream_t st) {
+               int stride, int pad, int dil, int hoff, int woff, float* ws, size_t ws_bytes, cudaStream_t st) {
   int rc = check_conv_args(x, dy, kh, kw, stride, pad, dil);
   if (rc) return rc;
   if (!dw || dw_cout <= 0 || dw_cin <= 0 || dw_cout > dy->c || dw_cin > x->c) return NPP_E_INVALID;
+  if (ws && (reinterpret_cast<uintptr_t>(ws) & 15)) return NPP_E_INVALID;
+  if (kh == 3 && kw == 3 && stride == 1 && dil == 1 && pad == 1 && hoff == 0 && woff == 0) {
+    rc = conv_wgrad3(x, dy, dw, dw_cout, dw_cin, ws, ws_bytes, st);
+    if (rc != NPP_E_UNSUPPORTED) return rc;
+  }
   TapTable taps;
   memset(&taps, 0, sizeof taps);
   npp_view4 av[4];
@@ -838,9 +1174,9 @@ int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, 
   if (ks < 1) ks = 1;
   g.ksplit = ks;
   switch (bn) {
-    case 64: return launch_wgrad<64>(maps, g, taps, dw, st);
-    case 128: return launch_wgrad<128>(maps, g, taps, dw, st);
-    default: return launch_wgrad<256>(maps, g, taps, dw, st);
+    case 64: return launch_wgrad<64>(maps, g, taps, dw, ws, ws_bytes, st);
+    case 128: return launch_wgrad<128>(maps, g, taps, dw, ws, ws_bytes, st);
+    default: return launch_wgrad<256>(maps, g, taps, dw, ws, ws_bytes, st);
   }
 }
 

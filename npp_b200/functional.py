@@ -226,6 +226,19 @@ def check_raw(x, what):
 # ------------------------------------------------------------------------------------------------
 # dense convolution
 # ------------------------------------------------------------------------------------------------
+def _wgrad_workspace(device):
+    """One persistent fp32 workspace per device for the split-K partial tiles of npp_conv2d_wgrad_ws (every wgrad
+    call of a stream reuses it; stream order keeps the calls apart)."""
+    key = ("wgrad_ws", torch.device(device).index)
+    ws = _state.get(key)
+    if ws is None:
+        L.lib().npp_conv2d_wgrad_workspace_bytes.restype = ctypes.c_int64
+        nbytes = int(L.lib().npp_conv2d_wgrad_workspace_bytes())
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        _state[key] = ws
+    return ws
+
+
 def conv_out_size(size, k, stride, pad, dil, off=0):
     return (size - off + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
@@ -300,9 +313,10 @@ class _ConvFn(Function):
             # wgrad accumulates (+=): into the parameter's own gradient slot when there is one, else into zeros
             dw = wslot if wslot is not None else torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
             if bf16:
-                call("npp_conv2d_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
-                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), stream(), work=ctx.work,
-                     keep=(x, dy, dw))
+                ws = _wgrad_workspace(x.device)
+                call("npp_conv2d_wgrad_ws", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
+                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), fptr(ws), i64(ws.numel() * 4), stream(),
+                     work=ctx.work, keep=(x, dy, dw))
             else:
                 call("npp_conv2d_direct_wgrad", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh),
                      i32(kw), i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())

@@ -51,6 +51,12 @@ static const Case cases[] = {
     {"1x1 1024->512 bias 96x96 n32 (bench shape)", 32, 96, 96, 1024, 512, 1, 1, 0, 1, 0, 0, 0, 0, 1},
     {"3x3 32->32 96x96 n32 (bench shape)", 32, 96, 96, 32, 32, 3, 1, 1, 1, 0, 0, 0, 0, 0},
     {"3x3 256->256 48x48 n32 (bench shape)", 32, 48, 48, 256, 256, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 64->64 48x48 n32 (bench shape)", 32, 48, 48, 64, 64, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 128->128 24x24 n32 (bench shape)", 32, 24, 24, 128, 128, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 256->256 12x12 n32 (bench shape)", 32, 12, 12, 256, 256, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 384->128 96x96 n4 (three cin blocks)", 4, 96, 96, 384, 128, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 40->24 20x36 n3 (ragged, odd channels)", 3, 20, 36, 40, 24, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 1024->1024 12x12 n8 (wide)", 8, 12, 12, 1024, 1024, 3, 1, 1, 1, 0, 0, 0, 0, 0},
 };
 
 static uint32_t rng_state = 12345;
@@ -198,8 +204,12 @@ int main(int argc, char** argv) {
     fails += !ok;
   }
 
-  // ---------------- wgrad
-  rc = npp_conv2d_wgrad(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, 0);
+  // ---------------- wgrad (workspace path: split-K partials + reduce kernel; the atomic path is checked below)
+  void* wsp = nullptr;
+  const int64_t ws_bytes = npp_conv2d_wgrad_workspace_bytes();
+  CK(cudaMalloc(&wsp, ws_bytes));
+  rc = npp_conv2d_wgrad_ws(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, wsp,
+                           ws_bytes, 0);
   if (rc) { printf("  wgrad rc=%d %s\n", rc, npp_last_error()); return 1; }
   rc = npp_conv2d_direct_wgrad(&vx, &vdy, dw_ref, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff,
                                NPP_BF16, 0);
@@ -213,6 +223,21 @@ int main(int argc, char** argv) {
     const bool ok = m.max_abs <= 2e-3 * (m.max_ref + 1e-6);
     printf("  wgrad : max_abs=%.5f max_ref=%.4f mean_abs=%.6f %s\n", m.max_abs, m.max_ref, m.mean_abs, ok ? "PASS" : "FAIL");
     fails += !ok;
+    // the atomic path (no workspace) must agree too; and a second accumulating call must double the result (+=)
+    CK(cudaMemset(dw_tc, 0, hw.size() * 4));
+    rc = npp_conv2d_wgrad(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, 0);
+    if (rc) { printf("  wgrad(atomic) rc=%d %s\n", rc, npp_last_error()); return 1; }
+    rc = npp_conv2d_wgrad_ws(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, wsp,
+                             ws_bytes, 0);
+    if (rc) { printf("  wgrad(ws, accumulate) rc=%d %s\n", rc, npp_last_error()); return 1; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ga.data(), dw_tc, hw.size() * 4, cudaMemcpyDeviceToHost));
+    for (auto& e : gb) e *= 2.f;
+    Cmp m2 = compare_f32(ga, gb);
+    const bool ok2 = m2.max_abs <= 2e-3 * (m2.max_ref + 1e-6);
+    printf("  wgrad : atomic + workspace accumulate == 2x: max_abs=%.5f max_ref=%.4f %s\n", m2.max_abs, m2.max_ref,
+           ok2 ? "PASS" : "FAIL");
+    fails += !ok2;
   }
 
   // ---------------- timing of the tcgen05 kernels (warm, 10 iterations each)
@@ -234,9 +259,13 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("  dgrad %.1f us (%.1f TFLOP/s)", ms * 100, flops / (ms * 1e-4) / 1e12);
     CK(cudaEventRecord(e0));
+    for (int i = 0; i < 10; ++i) npp_conv2d_wgrad_ws(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, wsp, ws_bytes, 0);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("  wgrad %.1f us (%.1f TFLOP/s)", ms * 100, flops / (ms * 1e-4) / 1e12);
+    CK(cudaEventRecord(e0));
     for (int i = 0; i < 10; ++i) npp_conv2d_wgrad(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, 0);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
-    printf("  wgrad %.1f us (%.1f TFLOP/s)\n", ms * 100, flops / (ms * 1e-4) / 1e12);
+    printf("  wgrad(atomic) %.1f us\n", ms * 100);
   }
   printf("[case %d] %s\n", idx, fails ? "FAILED" : "OK");
   return fails ? 1 : 0;
