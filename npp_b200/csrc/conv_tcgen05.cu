@@ -879,7 +879,13 @@ static int run_gemm(const npp_view4* a_views, int n_a, const npp_view4* d, const
   else
     rc = encode_act_map(&maps.d, d->ptr, d->c, d->w, d->h, d->n, d->sw, d->sh, d->sn, t.tw, t.th, t.tn);
   if (rc) return rc;
-  const int bn = pick_bn(wRows);
+  int bn = pick_bn(wRows);
+  {
+    // few pixel tiles (12x12 maps): a wide BN leaves most SMs without a CTA; narrower channel blocks share the pixel
+    // tile through L2 and fill the machine
+    const int64_t pt = cdiv64(ps.W, t.tw) * cdiv64(ps.H, t.th) * cdiv64(ps.N, t.tn);
+    while (bn > 64 && pt * cdiv64(wRows, bn) * 2 <= sm_count()) bn >>= 1;
+  }
   rc = encode_w_map(&maps.b, wmat, wK, wTaps, wRows, bn);
   if (rc) return rc;
   g.num_taps = num_taps;
