@@ -99,6 +99,13 @@ int npp_conv2d_wgrad_ws(const npp_view4* x, const npp_view4* dy, float* dw, int 
 int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin,
                     int cout_pad, int cin_pad, int out_dtype, npp_stream_t stream);
 
+/* Every dense-conv weight of a model in one launch (bf16 outputs).  table: device array of ntensors x
+ * {const float* w32; bf16* w; bf16* wt; int32 cout, taps, cin, cout_pad, cin_pad, pad} (48 bytes each, either
+ * output may be NULL); chunk_tensor / chunk_index: for every block, which tensor and which chunk of chunk_elems
+ * packed elements it converts. */
+int npp_pack_weights_multi(const void* table, int ntensors, const int32_t* chunk_tensor,
+                           const int32_t* chunk_index, int nchunks, int chunk_elems, npp_stream_t stream);
+
 /* Validation-mode / cross-check convolution on CUDA cores (fp32 accumulate, dtype-templated).
  * Same arithmetic as the three functions above, any dtype, groups==1. w/dw are fp32 OHWI
  * when dtype==NPP_F32 and bf16 (w) / fp32 (dw) when dtype==NPP_BF16. */
@@ -350,6 +357,15 @@ int npp_node_bwd_reduce(const npp_view4* g_raw, const npp_view4* g_relu, const n
                         const npp_view4* b, const float* mean_b, const float* invstd_b,
                         const npp_view4* g_out, float* partials, int dtype, npp_stream_t stream);
 int npp_reduce_partials(const float* partials, int rows, int len, float* out, npp_stream_t stream);
+/* node_bwd_reduce without the partials buffer / second kernel: every block adds its per-channel sums with fp32
+ * atomics into sums = [sum g, sum g*xhat_a, sum g, sum g*xhat_b] ([nq][C], zeroed by the caller) and, when
+ * acc[i] != NULL, also into acc[i][0:acc_valid[i]] (the BatchNorm parameters' gradient slots: d beta, d gamma per
+ * side).  acc / acc_valid: HOST arrays of nq entries, or NULL.  Summation order is not deterministic. */
+int npp_node_bwd_reduce_atomic(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
+                               const npp_view4* a, const float* mean_a, const float* invstd_a,
+                               const npp_view4* b, const float* mean_b, const float* invstd_b,
+                               const npp_view4* g_out, float* sums, float* const* acc,
+                               const int* acc_valid, int dtype, npp_stream_t stream);
 /* reduce_partials that also accumulates segment s = columns [s*seg_len,(s+1)*seg_len) of the folded row into
  * acc[s][0:acc_valid[s]] (+=; NULL = skip): BatchNorm d beta / d gamma go straight into the optimizer's flat
  * gradient buffer.  acc / acc_valid: HOST arrays of len/seg_len (<= NPP_ACC_MAX) entries. */

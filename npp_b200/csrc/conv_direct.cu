@@ -147,6 +147,8 @@ int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, 
                int pad, int dil, int hoff, int woff, float* ws, size_t ws_bytes, cudaStream_t st);
 int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
                 int out_dtype, cudaStream_t st);
+int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
+                       int chunk_elems, cudaStream_t st);
 }  // namespace tc
 
 }  // namespace npp
@@ -181,6 +183,10 @@ int npp_conv2d_wgrad_ws(const npp_view4* x, const npp_view4* dy, float* dw, int 
   if (!x || !dy || workspace_bytes < 0) return NPP_E_INVALID;
   return tc::conv_wgrad(x, dy, dw, dw_cout, dw_cin, kh, kw, stride, pad, dil, in_h_off, in_w_off,
                         static_cast<float*>(workspace), (size_t)workspace_bytes, as_stream(stream));
+}
+int npp_pack_weights_multi(const void* table, int ntensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                           int nchunks, int chunk_elems, npp_stream_t stream) {
+  return tc::pack_weights_multi(table, ntensors, chunk_tensor, chunk_index, nchunks, chunk_elems, as_stream(stream));
 }
 int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
                     int out_dtype, npp_stream_t stream) {

@@ -1203,6 +1203,45 @@ __global__ void pack_weight_kernel(const float* __restrict__ w32, D* __restrict_
   }
 }
 
+// All dense-conv weights of a model in ONE launch (the per-conv pack_weight launches were 412 tiny kernels per
+// step): a device table of tensor descriptors, one block per chunk of chunk_elems packed elements.
+struct PackTensor {
+  const float* w32;
+  __nv_bfloat16* w;
+  __nv_bfloat16* wt;
+  int cout, taps, cin, cout_pad, cin_pad, pad_;
+};
+static_assert(sizeof(PackTensor) == 48, "table layout is part of the ABI (npp_b200/engine.py mirrors it)");
+
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const PackTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
+                          const int* __restrict__ chunk_index, int chunk_elems) {
+  const PackTensor t = tensors[chunk_tensor[blockIdx.x]];
+  const int64_t total = (int64_t)t.cout_pad * t.taps * t.cin_pad;
+  const int64_t begin = (int64_t)chunk_index[blockIdx.x] * chunk_elems;
+  int64_t end = begin + chunk_elems;
+  if (end > total) end = total;
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const int ci = (int)(i % t.cin_pad);
+    const int tp = (int)((i / t.cin_pad) % t.taps);
+    const int co = (int)(i / ((int64_t)t.cin_pad * t.taps));
+    const float v = (co < t.cout && ci < t.cin) ? t.w32[((int64_t)co * t.cin + ci) * t.taps + tp] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (t.w) t.w[i] = h;
+    if (t.wt) t.wt[((int64_t)ci * t.taps + tp) * t.cout_pad + co] = h;
+  }
+}
+
+int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
+                       int chunk_elems, cudaStream_t st) {
+  if (!table || !chunk_tensor || !chunk_index || ntensors <= 0 || nchunks < 0 || chunk_elems <= 0) return NPP_E_INVALID;
+  if (nchunks == 0) return NPP_OK;
+  pack_weights_multi_kernel<<<nchunks, 256, 0, st>>>(static_cast<const PackTensor*>(table), chunk_tensor, chunk_index,
+                                                     chunk_elems);
+  NPP_CHECK_LAUNCH("pack_weights_multi_kernel");
+  return NPP_OK;
+}
+
 int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin, int cout_pad, int cin_pad,
                 int out_dtype, cudaStream_t st) {
   if (!w32 || (!w && !wt) || cout <= 0 || taps <= 0 || cin <= 0 || cout_pad < cout || cin_pad < cin)

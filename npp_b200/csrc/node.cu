@@ -16,6 +16,7 @@
 // coefficients loaded once (a thread keeps its channel vector for its whole pixel loop), 4 (fwd) / 2 (bwd) pixels of
 // independent loads in flight per thread.
 #include "view.cuh"
+#include <string.h>
 
 namespace npp {
 
@@ -151,8 +152,13 @@ static int node_fwd_t(const npp_view4* a, const float* sa, const float* ta, cons
 }
 
 // ------------------------------------------------------------------------------------------------ backward 1/2
+struct AccSeg { float* ptr; int valid; };
+struct AccSegs { AccSeg s[NPP_ACC_MAX]; };
+
 template <typename T>
 struct NodeBwdReduceArgs {
+  float* sums;                    // atomic mode: [nq][C] zero-initialised accumulators (partials == nullptr)
+  AccSegs acc;                    // atomic mode: per-row parameter-gradient slots (d beta / d gamma), ptr may be null
   PView<const T> graw, grelu, r;  // gradients of the raw / relu outputs, relu output (mask)
   PView<const T> a, b;            // BatchNorm inputs (p == nullptr = that input has no BatchNorm)
   const float *mean_a, *invstd_a, *mean_b, *invstd_b;
@@ -231,10 +237,13 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
       }
     }
   }
-  if (A.partials == nullptr) return;
-  // block reduction over the pixel rows of the block, then one coalesced row of partials per quantity
+  if (A.partials == nullptr && A.sums == nullptr) return;
+  // block reduction over the pixel rows of the block, then one coalesced row of partials per quantity — or, in
+  // atomic mode, one fp32 atomic per (block, channel, quantity) straight into the totals and the parameters'
+  // gradient slots (no partials buffer, no second kernel)
   const int nq = (has_a ? 2 : 0) + (has_b ? 2 : 0);
-  float* out = A.partials + (int64_t)blockIdx.x * nq * A.C;
+  const bool atomic = A.partials == nullptr;
+  float* out = atomic ? A.sums : A.partials + (int64_t)blockIdx.x * nq * A.C;
   int q = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -250,13 +259,37 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
       for (int v = 0; v < V; ++v) {
         float s = 0.f;
         for (int r = 0; r < A.g.rows; ++r) s += red[(r * A.g.cvb + tcv) * V + v];
-        if (k == 0) {
-          if (has_a) out[c0 + v] = s;
-          if (has_b) out[(has_a ? 2 : 0) * A.C + c0 + v] = s;
-        } else if (k == 1) {
-          out[A.C + c0 + v] = s * A.invstd_a[c0 + v];
+        const int ch = c0 + v;
+        if (!atomic) {
+          if (k == 0) {
+            if (has_a) out[ch] = s;
+            if (has_b) out[(has_a ? 2 : 0) * A.C + ch] = s;
+          } else if (k == 1) {
+            out[A.C + ch] = s * A.invstd_a[ch];
+          } else {
+            out[((has_a ? 2 : 0) + 1) * A.C + ch] = s * A.invstd_b[ch];
+          }
         } else {
-          out[((has_a ? 2 : 0) + 1) * A.C + c0 + v] = s * A.invstd_b[c0 + v];
+          // rows: [sum g (a), sum g*xhat_a, sum g (b), sum g*xhat_b] (only the BatchNorm sides that exist)
+          const int rb = has_a ? 2 : 0;
+          if (k == 0) {
+            if (has_a) {
+              atomicAdd(out + ch, s);
+              if (A.acc.s[0].ptr && ch < A.acc.s[0].valid) atomicAdd(A.acc.s[0].ptr + ch, s);
+            }
+            if (has_b) {
+              atomicAdd(out + rb * A.C + ch, s);
+              if (A.acc.s[rb].ptr && ch < A.acc.s[rb].valid) atomicAdd(A.acc.s[rb].ptr + ch, s);
+            }
+          } else if (k == 1) {
+            const float t = s * A.invstd_a[ch];
+            atomicAdd(out + A.C + ch, t);
+            if (A.acc.s[1].ptr && ch < A.acc.s[1].valid) atomicAdd(A.acc.s[1].ptr + ch, t);
+          } else {
+            const float t = s * A.invstd_b[ch];
+            atomicAdd(out + (rb + 1) * A.C + ch, t);
+            if (A.acc.s[rb + 1].ptr && ch < A.acc.s[rb + 1].valid) atomicAdd(A.acc.s[rb + 1].ptr + ch, t);
+          }
         }
       }
     }
@@ -293,8 +326,6 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // reduce_partials + parameter-gradient accumulation: segment s = columns [s*seg_len, (s+1)*seg_len) of the folded
 // row is additionally added into acc[s].ptr[0:valid] (BatchNorm d beta / d gamma written straight into the
 // optimizer's flat gradient buffer instead of going through one autograd accumulation kernel per parameter).
-struct AccSeg { float* ptr; int valid; };
-struct AccSegs { AccSeg s[NPP_ACC_MAX]; };
 __global__ void __launch_bounds__(256) reduce_partials_acc_kernel(const float* __restrict__ partials, int rows, int len,
                                                                   float* __restrict__ out, int seg_len, AccSegs acc) {
   __shared__ float red[8][33];
@@ -324,10 +355,13 @@ static int node_bwd_blocks(int64_t npix, int C, int V) {
 template <typename T>
 static int node_bwd_reduce_t(const npp_view4* graw, const npp_view4* grelu, const npp_view4* r, const npp_view4* a,
                              const float* mean_a, const float* invstd_a, const npp_view4* b, const float* mean_b,
-                             const float* invstd_b, const npp_view4* gout, float* partials, cudaStream_t st) {
+                             const float* invstd_b, const npp_view4* gout, float* partials, float* sums,
+                             const AccSegs* acc, cudaStream_t st) {
   constexpr int V = Pack<T>::N;
   const npp_view4* ref = graw ? graw : grelu;
   NodeBwdReduceArgs<T> A;
+  A.sums = sums;
+  if (acc) A.acc = *acc; else memset(&A.acc, 0, sizeof A.acc);
   A.graw = graw ? pview<const T>(graw) : pview_null<const T>();
   A.grelu = grelu ? pview<const T>(grelu) : pview_null<const T>();
   A.r = r ? pview<const T>(r) : pview_null<const T>();
@@ -488,7 +522,35 @@ int npp_node_bwd_reduce(const npp_view4* g_raw, const npp_view4* g_relu, const n
   if ((a || b) && !partials) return NPP_E_INVALID;
   if (!a && !b && !g_out) return NPP_E_INVALID;
   NPP_DISPATCH_DTYPE(dtype, return node_bwd_reduce_t<T>(g_raw, g_relu, relu_out, a, mean_a, invstd_a, b, mean_b,
-                                                        invstd_b, g_out, (a || b) ? partials : nullptr, as_stream(s)););
+                                                        invstd_b, g_out, (a || b) ? partials : nullptr, nullptr,
+                                                        nullptr, as_stream(s)););
+}
+
+int npp_node_bwd_reduce_atomic(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
+                               const npp_view4* a, const float* mean_a, const float* invstd_a, const npp_view4* b,
+                               const float* mean_b, const float* invstd_b, const npp_view4* g_out, float* sums,
+                               float* const* acc, const int* acc_valid, int dtype, npp_stream_t s) {
+  const npp_view4* ref = g_raw ? g_raw : g_relu;
+  if (!ref || !view_ok(ref, dtype)) return NPP_E_INVALID;
+  if (g_raw && g_relu && (!view_ok(g_relu, dtype) || !same_shape(ref, g_relu))) return NPP_E_INVALID;
+  if (g_relu && (!relu_out || !view_ok(relu_out, dtype) || !same_shape(ref, relu_out))) return NPP_E_INVALID;
+  if (a && (!view_ok(a, dtype) || !same_shape(ref, a) || !mean_a || !invstd_a)) return NPP_E_INVALID;
+  if (b && (!view_ok(b, dtype) || !same_shape(ref, b) || !mean_b || !invstd_b)) return NPP_E_INVALID;
+  if (g_out && (!view_ok(g_out, dtype) || !same_shape(ref, g_out))) return NPP_E_INVALID;
+  if ((!a && !b) || !sums) return NPP_E_INVALID;
+  AccSegs A;
+  memset(&A, 0, sizeof A);
+  const int nq = (a ? 2 : 0) + (b ? 2 : 0);
+  if (acc) {
+    if (!acc_valid) return NPP_E_INVALID;
+    for (int i = 0; i < nq; ++i) {
+      A.s[i].ptr = acc[i];
+      A.s[i].valid = acc[i] ? acc_valid[i] : 0;
+      if (A.s[i].valid < 0 || A.s[i].valid > ref->c) return NPP_E_INVALID;
+    }
+  }
+  NPP_DISPATCH_DTYPE(dtype, return node_bwd_reduce_t<T>(g_raw, g_relu, relu_out, a, mean_a, invstd_a, b, mean_b,
+                                                        invstd_b, g_out, nullptr, sums, &A, as_stream(s)););
 }
 
 int npp_reduce_partials(const float* partials, int rows, int len, float* out, npp_stream_t s) {

@@ -99,6 +99,7 @@ class TrainStep:
         # persistent flat gradients: static addresses for the graph, one memset per step, all-reduce without copies
         self.flat_grads = optimizer.use_flat_grads() if hasattr(optimizer, "use_flat_grads") else None
         self.launches_per_step = None
+        self.packer = F_.WeightPacker(model) if dev.type == "cuda" else None   # all conv weights: one launch per step
 
     # ---- pieces ------------------------------------------------------------------------------------
     def load(self, images, par_lab, edge_lab, pose_gt, pose_aux_gt, non_blocking=True):
@@ -132,6 +133,8 @@ class TrainStep:
         F_._arena.begin(self.images.device)             # every zero-initialised accumulator of the step: one memset
         F_._state["defer_bn_counters"] = counters = []  # BatchNorm num_batches_tracked += 1: one launch, not 432
         try:
+            if self.packer is not None:
+                self.packer.pack()
             pose, par = self.model(self.images)
             F_._state["defer_bn_counters"] = None
             if counters:
@@ -143,6 +146,7 @@ class TrainStep:
         finally:
             F_._state["defer_bn_counters"] = None
             F_._arena.end()
+            F_.WeightPacker.release()
         if self.world_size > 1:
             self._allreduce_grads()
         self.opt.step()

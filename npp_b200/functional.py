@@ -254,7 +254,7 @@ def _conv_work(n, ho, wo, cout, cin, kh, kw, x, y):
 
 class _ConvFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, dil, hoff, woff, want_stats, slots):
+    def forward(ctx, x, weight, bias, stride, pad, dil, hoff, woff, want_stats, slots, packed):
         n, cx, h, w = x.shape
         cout, cin, kh, kw = weight.shape
         if cx != pad8(cin):
@@ -263,12 +263,15 @@ class _ConvFn(Function):
         ho, wo = conv_out_size(h, kh, stride, pad, dil, hoff), conv_out_size(w, kw, stride, pad, dil, woff)
         code = L.dtype_code(x)
         bf16 = code == L.NPP_BF16
-        w32 = weight.detach().contiguous()
-        wp = torch.empty(cop * kh * kw * cx, dtype=x.dtype, device=x.device)
         need_wt = bf16 and ctx.needs_input_grad[0]
-        wt = torch.empty_like(wp) if need_wt else None
-        call("npp_pack_weight", fptr(w32), fptr(wp), fptr(wt), i32(cout), i32(kh * kw), i32(cin), i32(cop), i32(cx),
-             i32(code), stream())
+        if packed is not None and bf16 and packed[0].numel() == cop * kh * kw * cx:
+            wp, wt = packed        # packed for the whole model by one launch at the start of the step (WeightPacker)
+        else:
+            w32 = weight.detach().contiguous()
+            wp = torch.empty(cop * kh * kw * cx, dtype=x.dtype, device=x.device)
+            wt = torch.empty_like(wp) if need_wt else None
+            call("npp_pack_weight", fptr(w32), fptr(wp), fptr(wt), i32(cout), i32(kh * kw), i32(cin), i32(cop), i32(cx),
+                 i32(code), stream())
         bp = None
         if bias is not None:
             bp = pad_vec(bias.detach().float(), cop).contiguous()
@@ -329,15 +332,68 @@ class _ConvFn(Function):
                 dbp = zeros_f32(dy.shape[1], x.device)
                 call("npp_colsum", ref(view(dy)), fptr(dbp), i32(code), stream())
                 db = dbp[:cout]
-        return dx, dw, db, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_stats=False):
     """Dense conv on an internal tensor.  Returns (y, stats) where stats is the fused per-channel
     (sum, sum of squares) of y from the tcgen05 epilogue (empty when not requested / fp32 mode)."""
     slots = (grad_slot(weight), grad_slot(bias))
+    packed = getattr(weight, "_npp_packed", None) if _state.get("packed_weights") else None
     return _ConvFn.apply(x, weight, bias, int(stride), int(pad), int(dil), int(hoff), int(woff), bool(want_stats),
-                         slots if (slots[0] is not None or slots[1] is not None) else None)
+                         slots if (slots[0] is not None or slots[1] is not None) else None, packed)
+
+
+class WeightPacker:
+    """Packs every dense-conv weight of a model (fp32 OIHW masters -> bf16 OHWI + transposed copies) with ONE launch
+    per step instead of one per convolution.  The packed buffers are persistent and hang off the parameters
+    (`_npp_packed`); conv2d() uses them while `_state["packed_weights"]` is set (engine.TrainStep brackets its step
+    body with pack() / release())."""
+    CHUNK = 16384
+
+    def __init__(self, model):
+        import struct
+        convs = [m for m in model.modules()
+                 if isinstance(m, torch.nn.Conv2d) and m.groups == 1 and m.weight.is_cuda and m.weight.dtype == torch.float32]
+        self.params = [m.weight for m in convs]
+        self.bufs = []
+        rows, ct, ci = [], [], []
+        for ti, w in enumerate(self.params):
+            cout, cin, kh, kw = w.shape
+            cop, cip = pad8(cout), pad8(cin)
+            n = cop * kh * kw * cip
+            prev = getattr(w, "_npp_packed", None)
+            if prev is not None and prev[0].numel() == n and prev[0].device == w.device:
+                wp, wt = prev      # another packer of the same model (e.g. an eager and a graphed TrainStep) owns them too
+            else:
+                wp = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                wt = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                w._npp_packed = (wp, wt)
+            self.bufs.append((wp, wt))   # the device table holds raw pointers: keep the buffers alive
+            rows.append(struct.pack("<QQQiiiiii", w.data_ptr(), wp.data_ptr(), wt.data_ptr(), cout, kh * kw, cin, cop, cip, 0))
+            nch = (n + self.CHUNK - 1) // self.CHUNK
+            ct += [ti] * nch
+            ci += list(range(nch))
+        dev = self.params[0].device if self.params else None
+        self.n = len(self.params)
+        if self.n:
+            self.table = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8).clone().to(dev)
+            self.chunk_tensor = torch.tensor(ct, dtype=torch.int32).to(dev)
+            self.chunk_index = torch.tensor(ci, dtype=torch.int32).to(dev)
+            self.ptrs = [w.data_ptr() for w in self.params]
+
+    def pack(self):
+        if not self.n or _state["dtype"] != torch.bfloat16:
+            return
+        if [w.data_ptr() for w in self.params] != self.ptrs:
+            raise RuntimeError("WeightPacker: a parameter was re-allocated; build a new packer")
+        call("npp_pack_weights_multi", fptr(self.table), i32(self.n), fptr(self.chunk_tensor), fptr(self.chunk_index),
+             i32(self.chunk_tensor.numel()), i32(self.CHUNK), stream())
+        _state["packed_weights"] = True
+
+    @staticmethod
+    def release():
+        _state["packed_weights"] = False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -619,21 +675,23 @@ class _NodeFn(Function):
             if g_relu is not None:
                 g = empty_internal(n, c, h, w, ref_t.dtype, dev)
             nq = 2 * (int(has_a) + int(has_b))
-            parts = None
-            if need_bn:
+            parts = sums = None
+            sl_a, sl_b = ctx.pslots
+            # npp_node_bwd_reduce_atomic (per-block sums added with atomics, no partials buffer / fold kernel) was
+            # measured SLOWER than partials + fold (15.7 vs 13.8 ms per step: ~600 blocks hammer the same 4C
+            # addresses), so the deterministic path stays; the switch is kept for experiments
+            atomic = need_bn and _arena.active and _state.get("node_reduce_atomics", False)
+            if need_bn and not atomic:
                 nblk = L.lib().npp_node_bwd_blocks(i32(n), i32(h), i32(w), i32(c), i32(code))
                 parts = torch.empty(nblk * nq * c, dtype=torch.float32, device=dev)
-            call("npp_node_bwd_reduce", ref(view(g_raw)) if g_raw is not None else NULL,
-                 ref(view(g_relu)) if g_relu is not None else NULL, ref(view(rel)) if g_relu is not None else NULL,
-                 ref(view(a)) if has_a else NULL, fptr(ca[2 * c:3 * c]) if has_a else NULL,
-                 fptr(ca[3 * c:]) if has_a else NULL, ref(view(b)) if has_b else NULL,
-                 fptr(cb[2 * c:3 * c]) if has_b else NULL, fptr(cb[3 * c:]) if has_b else NULL,
-                 ref(view(g)) if g_relu is not None else NULL, fptr(parts), i32(code), stream())
-        da = db = dga = dba = dgb = dbb = None
-        if need_bn:
-            sums = torch.empty(nq * c, dtype=torch.float32, device=dev)
-            sl_a, sl_b = ctx.pslots
-            if (has_a and sl_a is not None) or (has_b and sl_b is not None):
+            common = (ref(view(g_raw)) if g_raw is not None else NULL,
+                      ref(view(g_relu)) if g_relu is not None else NULL, ref(view(rel)) if g_relu is not None else NULL,
+                      ref(view(a)) if has_a else NULL, fptr(ca[2 * c:3 * c]) if has_a else NULL,
+                      fptr(ca[3 * c:]) if has_a else NULL, ref(view(b)) if has_b else NULL,
+                      fptr(cb[2 * c:3 * c]) if has_b else NULL, fptr(cb[3 * c:]) if has_b else NULL,
+                      ref(view(g)) if g_relu is not None else NULL)
+            if atomic:
+                sums = zeros_f32(nq * c, dev)
                 segs = []
                 if has_a:
                     segs += list(sl_a) if sl_a is not None else [None, None]
@@ -641,10 +699,25 @@ class _NodeFn(Function):
                     segs += list(sl_b) if sl_b is not None else [None, None]
                 accp = (ctypes.c_void_p * len(segs))(*[t.data_ptr() if t is not None else None for t in segs])
                 accv = (ctypes.c_int * len(segs))(*[min(t.numel(), c) if t is not None else 0 for t in segs])
-                call("npp_reduce_partials_acc", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), i32(c), accp, accv,
-                     stream())
+                call("npp_node_bwd_reduce_atomic", *common, fptr(sums), accp, accv, i32(code), stream())
             else:
-                call("npp_reduce_partials", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), stream())
+                call("npp_node_bwd_reduce", *common, fptr(parts), i32(code), stream())
+        da = db = dga = dba = dgb = dbb = None
+        if need_bn:
+            if sums is None:   # deterministic path: fold the per-block partials
+                sums = torch.empty(nq * c, dtype=torch.float32, device=dev)
+                if (has_a and sl_a is not None) or (has_b and sl_b is not None):
+                    segs = []
+                    if has_a:
+                        segs += list(sl_a) if sl_a is not None else [None, None]
+                    if has_b:
+                        segs += list(sl_b) if sl_b is not None else [None, None]
+                    accp = (ctypes.c_void_p * len(segs))(*[t.data_ptr() if t is not None else None for t in segs])
+                    accv = (ctypes.c_int * len(segs))(*[min(t.numel(), c) if t is not None else 0 for t in segs])
+                    call("npp_reduce_partials_acc", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), i32(c), accp,
+                         accv, stream())
+                else:
+                    call("npp_reduce_partials", fptr(parts), i32(nblk), i32(nq * c), fptr(sums), stream())
             local = sums
             if sync:
                 returns_grads = (has_a and ctx.pslots[0] is None) or (has_b and ctx.pslots[1] is None)
