@@ -324,6 +324,491 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
 }
 
 // =================================================================================================
+// Second-generation epilogue: EIGHT warps (256 threads) drain the accumulator.
+//
+// ncu on the first kernel above: for the small-K layers (1x1 convs, C = 32/64 cells — most of the 822 launches of a
+// step) the MMA loop of a tile takes a few hundred cycles and the tile time is the epilogue's: four warps, one per
+// SM sub-partition, each a serial chain tcgen05.ld -> wait -> convert -> st.shared -> barrier -> TMA store ->
+// statistics with nothing to overlap it (1x1 128->128 @96^2 x32: 35 us without / 66 us with statistics against a
+// 23 us HBM floor).  Here two warps share every TMEM lane quarter: warp (q, hf) owns rows 32q..32q+31 and the
+// 32-column half hf of each 64-column slab, the TMEM load is issued before the staging-buffer barrier so its latency
+// overlaps the wait, the accumulator is handed back to the MMA warp as soon as the last load has landed (before the
+// statistics of the last slab), and the statistics pass is spread over 256 threads (4 rows each instead of 8).
+// =================================================================================================
+constexpr int kThreads2 = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+
+struct EpiMask {   // which rows of a 128-row unit are real pixels (statistics must skip padding rows)
+  int tw, th;      // pixel box of the whole tile
+  int W, H, N;     // tensor extents
+  int w0, h0, n0;  // tile origin
+  int p_off;       // linear index (in the tile's box) of the unit's first row
+  bool full;
+};
+
+// One unit = 128 rows (TMEM lanes) x one 64-column slab (SLAB_COLS = 32 for the BN = 32 kernels) of the accumulator:
+// TMEM -> (+bias) -> bf16 -> swizzled staging slab -> TMA store; BatchNorm sums of the rounded values.
+template <int SLAB_COLS>
+__device__ __forceinline__ void epi_unit(const uint32_t taddr, uint8_t* stg, const uint32_t stg_s,
+                                         const CUtensorMap* md, const int co_base, const int c_w, const int c_h,
+                                         const int c_n, const float* __restrict__ bias, const int cout,
+                                         const uint32_t release_bar, const bool want_stats, const EpiMask& mk,
+                                         float (&as)[8], float (&aq)[8], const int q, const int hf, const int ew,
+                                         const int lane, const int etid) {
+  const bool has_cols = hf * 32 < SLAB_COLS;  // warp-uniform
+  const int row = q * 32 + lane;
+  uint32_t r[32];
+  if (has_cols) tmem_ld_32x32(taddr, r);
+  // the TMA store that last read this staging slab (two units ago) must have finished reading it
+  if (etid == 0) tma_store_wait_read<1>();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (has_cols) {
+    tmem_ld_wait_regs(r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // four 16-byte chunks (8 channels each)
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v0 = __uint_as_float(r[j * 8 + e * 2]);
+        float v1 = __uint_as_float(r[j * 8 + e * 2 + 1]);
+        if (bias != nullptr) {
+          const int c0 = co_base + hf * 32 + j * 8 + e * 2;
+          v0 += (c0 < cout) ? __ldg(bias + c0) : 0.f;
+          v1 += (c0 + 1 < cout) ? __ldg(bias + c0 + 1) : 0.f;
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        pk[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      const int chunk = hf * 4 + j;
+      *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  if (release_bar != 0u) {  // last unit of the tile: every TMEM read of this thread has completed
+    tc_fence_before();
+    mbar_arrive(release_bar);
+  }
+  fence_proxy_async_smem();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (etid == 0) {
+    tma_store_4d(md, stg_s, co_base, c_w, c_h, c_n);
+    tma_store_commit();
+  }
+  if (want_stats && ew * 8 < SLAB_COLS) {
+    // Epilogue warp ew owns the 16-byte chunk ew (8 channels) of every row; lane l adds up rows 4l..4l+3, visited
+    // in a lane-skewed order so that the 8 lanes of an LDS.128 phase hit 8 different swizzle slots (bank groups).
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = lane * 4 + ((i + (lane >> 1)) & 3);
+      bool ok = true;
+      if (!mk.full) {
+        const int p = mk.p_off + rr;
+        const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
+        ok = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
+      }
+      const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ew ^ (rr & 7)) << 4));
+      if (ok) {
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = __uint_as_float(uu[e] << 16), v1 = __uint_as_float(uu[e] & 0xffff0000u);
+          as[2 * e] += v0; aq[2 * e] = fmaf(v0, v0, aq[2 * e]);
+          as[2 * e + 1] += v1; aq[2 * e + 1] = fmaf(v1, v1, aq[2 * e + 1]);
+        }
+      }
+    }
+  }
+}
+
+// fold the 32 row groups of a warp, then one atomic per (CTA, channel, moment)
+template <int SLABS, int SLAB_COLS>
+__device__ __forceinline__ void epi_flush_stats(float (&acc_s)[SLABS][8], float (&acc_q)[SLABS][8],
+                                                float* __restrict__ stats, const int co0, const int cout, const int ew,
+                                                const int lane) {
+  if (ew * 8 >= SLAB_COLS) return;  // warp-uniform
+#pragma unroll
+  for (int sl = 0; sl < SLABS; ++sl) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = warp_sum(acc_s[sl][k]), b = warp_sum(acc_q[sl][k]);
+      const int co = co0 + sl * 64 + ew * 8 + k;
+      if (lane == 0 && co < cout) {
+        atomicAdd(stats + co, a);
+        atomicAdd(stats + cout + co, b);
+      }
+    }
+  }
+}
+
+// Same pipeline as conv_gemm_kernel (TMA producer warp, MMA warp, two TMEM accumulator stages), eight-warp epilogue.
+template <int BN>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
+                  const float* __restrict__ bias, float* __restrict__ stats) {
+  using Cfg = FpropCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t smem_out = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_out + Cfg::OUT_BYTES;
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8 * STAGES;
+  const uint32_t tfull_bar = bar_base + 16 * STAGES;
+  const uint32_t tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.a[0]);
+    prefetch_tensormap(&maps.b);
+    prefetch_tensormap(&maps.d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int num_k = g.num_taps * g.kc_blocks;
+  const int nb = blockIdx.x % g.n_blocks;
+  const int pt_start = blockIdx.x / g.n_blocks;
+  const int pt_step = gridDim.x / g.n_blocks;
+  constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
+  constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+        int pt = ptile;
+        const int w0 = (pt % g.tiles_w) * g.tw;
+        pt /= g.tiles_w;
+        const int h0 = (pt % g.tiles_h) * g.th;
+        const int n0 = (pt / g.tiles_h) * g.tn;
+        for (int t = 0; t < g.num_taps; ++t) {
+          const CUtensorMap* ma = &maps.a[taps.map[t]];
+          const int cw = w0 + taps.dw[t], ch = h0 + taps.dh[t], bt = taps.btap[t];
+          for (int kc = 0; kc < g.kc_blocks; ++kc) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+            tma_load_4d(smem_a + stage * Cfg::A_BYTES, ma, full_bar + 8 * stage, kc * BK, cw, ch, n0);
+            tma_load_3d(smem_b + stage * Cfg::B_BYTES, &maps.b, full_bar + 8 * stage, kc * BK, bt, nb * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4, q = warp & 3, hf = ew >> 2;
+    const int etid = threadIdx.x - 128;
+    int nslab = (g.cout - nb * BN + 63) / 64;  // slabs of this CTA's channel block that hold real channels
+    if (nslab > SLABS) nslab = SLABS;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int sbuf = 0;
+    float acc_s[SLABS][8], acc_q[SLABS][8];
+#pragma unroll
+    for (int sl = 0; sl < SLABS; ++sl)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc_s[sl][k] = 0.f; acc_q[sl][k] = 0.f; }
+    for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+      int pt = ptile;
+      EpiMask mk;
+      mk.tw = g.tw; mk.th = g.th; mk.W = g.W; mk.H = g.H; mk.N = g.N; mk.p_off = 0;
+      mk.w0 = (pt % g.tiles_w) * g.tw;
+      pt /= g.tiles_w;
+      mk.h0 = (pt % g.tiles_h) * g.th;
+      mk.n0 = (pt / g.tiles_h) * g.tn;
+      mk.full = (mk.w0 + g.tw <= g.W) && (mk.h0 + g.th <= g.H) && (mk.n0 + g.tn <= g.N);
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int slab = 0; slab < SLABS; ++slab) {
+        if (slab < nslab) {  // uniform across the CTA
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + slab * 64 + hf * 32);
+          epi_unit<SLAB_COLS>(taddr, smem_gen + (smem_out - smem_base) + sbuf * (BM * 128), smem_out + sbuf * (BM * 128),
+                              &maps.d, nb * BN + slab * 64, mk.w0, mk.h0, mk.n0, bias, g.cout,
+                              slab == nslab - 1 ? tempty_bar + 8 * acc : 0u, stats != nullptr, mk, acc_s[slab],
+                              acc_q[slab], q, hf, ew, lane, etid);
+          sbuf ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (stats != nullptr) epi_flush_stats<SLABS, SLAB_COLS>(acc_s, acc_q, stats, nb * BN, g.cout, ew, lane);
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// =================================================================================================
+// 3x3 / stride 1 / pad 1 fprop and dgrad with Cout <= 128: 256-pixel tiles and vertical-tap sharing.
+//
+// The kernels above fetch one activation box and one weight tile per (tap, 64-channel block): 32 KB of L2 -> SM
+// traffic per 128 x 128 x 64 MMA block = 64 flop/B, and the measured time of the dominant layer (128 -> 128 @ 96^2
+// x 32 images, 96 us) is exactly the L2 -> SM limit of the chip (~6300 B/clk, B300_MICROARCH.md) — the tensor
+// pipe idles a third of the time.  Two changes bring the tile to ~150 flop/B:
+//   * a CTA owns a TW x TH = 256-pixel tile of one image = two M=128 accumulators that share every weight tile;
+//   * the activation box carries one halo row above and below (TH + 2 rows of TW pixels, TW % 8 == 0): the three
+//     vertical taps of a kernel column are the SAME shared-memory box read 0 / TW / 2*TW pixels further down —
+//     whole 1024-byte SWIZZLE_128B atoms, so only the UMMA descriptor's start address moves.
+// Per (kernel column, 64-channel block): one box of (TH+2)*TW*128 B and three weight tiles feed 24 MMAs.
+// Activation boxes and weight tiles travel in separate mbarrier rings (different sizes, different reuse).
+// =================================================================================================
+struct C3Maps {
+  CUtensorMap a;  // input: dims (C, W, H, N), box (64, tw, th + 2, 1)
+  CUtensorMap b;  // weights: dims (K, 9, rows), box (64, 1, BN)
+  CUtensorMap d;  // output: dims (C, W, H, N), box (64, tw, th / 2, 1)
+};
+struct C3Geom {
+  int tw, th;            // tw * th == 256, tw % 8 == 0, th even
+  int tiles_w, tiles_h;  // per image
+  int num_ptiles;
+  int W, H;
+  int kc_blocks, cout;
+  int a_bytes;           // (th + 2) * tw * 128
+  int sa, sb;            // ring depths (activation boxes, weight tiles)
+  int flip;              // 0: fprop taps (x[h + r - 1][w + s - 1]); 1: dgrad taps (dy[h + 1 - r][w + 1 - s])
+};
+constexpr int kC3MaxSA = 4, kC3MaxSB = 8;
+constexpr int kC3OutBytes = 2 * 128 * 128;
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* __restrict__ bias,
+             float* __restrict__ stats) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int TMEM_COLS = 4 * BN;  // 2 accumulator stages x 2 pixel halves; 128 / 256 / 512
+  constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
+  constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + g.sa * g.a_bytes;
+  const uint32_t smem_out = smem_b + g.sb * B_BYTES;
+  const uint32_t bar_base = smem_out + kC3OutBytes;
+  const uint32_t afull_bar = bar_base;                          // kC3MaxSA x 8 B
+  const uint32_t aempty_bar = afull_bar + 8 * kC3MaxSA;
+  const uint32_t bfull_bar = aempty_bar + 8 * kC3MaxSA;         // kC3MaxSB x 8 B
+  const uint32_t bempty_bar = bfull_bar + 8 * kC3MaxSB;
+  const uint32_t tfull_bar = bempty_bar + 8 * kC3MaxSB;         // 2 x 8 B
+  const uint32_t tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.a);
+    prefetch_tensormap(&maps.b);
+    prefetch_tensormap(&maps.d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.sa; ++i) {
+      mbar_init(afull_bar + 8 * i, 1);
+      mbar_init(aempty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < g.sb; ++i) {
+      mbar_init(bfull_bar + 8 * i, 1);
+      mbar_init(bempty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t ap = 0, bp = 0;
+      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+        int pt = ptile;
+        const int w0 = (pt % g.tiles_w) * g.tw;
+        pt /= g.tiles_w;
+        const int h0 = (pt % g.tiles_h) * g.th;
+        const int n0 = pt / g.tiles_h;
+        for (int s = 0; s < 3; ++s) {
+          const int cw = w0 + (g.flip ? 1 - s : s - 1);
+          for (int kc = 0; kc < g.kc_blocks; ++kc) {
+            mbar_wait(aempty_bar + 8 * as, ap ^ 1);
+            mbar_arrive_expect_tx(afull_bar + 8 * as, g.a_bytes);
+            tma_load_4d(smem_a + as * g.a_bytes, &maps.a, afull_bar + 8 * as, kc * BK, cw, h0 - 1, n0);
+            if (++as == g.sa) { as = 0; ap ^= 1; }
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(bempty_bar + 8 * bs, bp ^ 1);
+              mbar_arrive_expect_tx(bfull_bar + 8 * bs, B_BYTES);
+              tma_load_3d(smem_b + bs * B_BYTES, &maps.b, bfull_bar + 8 * bs, kc * BK, r * 3 + s, 0);
+              if (++bs == g.sb) { bs = 0; bp ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int as = 0, bs = 0;
+      uint32_t ap = 0, bp = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int steps = 3 * g.kc_blocks;
+      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+        for (int step = 0; step < steps; ++step) {
+          mbar_wait(afull_bar + 8 * as, ap);
+          tc_fence_after();
+          const uint32_t a_s = smem_a + as * g.a_bytes;
+#pragma unroll 1
+          for (int r = 0; r < 3; ++r) {
+            // vertical tap r reads the box `ro` image rows (ro * tw pixels = ro * tw * 128 bytes) further down
+            const int ro = g.flip ? 2 - r : r;
+            mbar_wait(bfull_bar + 8 * bs, bp);
+            tc_fence_after();
+            const uint64_t db = make_smem_desc_sw128(smem_b + bs * B_BYTES, 16, 1024);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const uint64_t da = make_smem_desc_sw128(a_s + (ro * g.tw + m * 128) * 128, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_f16(tmem_d + m * BN, da + 2 * k, db + 2 * k, idesc, (step | r | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(bempty_bar + 8 * bs);
+            if (++bs == g.sb) { bs = 0; bp ^= 1; }
+          }
+          umma_commit(aempty_bar + 8 * as);
+          if (++as == g.sa) { as = 0; ap ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (eight warps)
+    const int ew = warp - 4, q = warp & 3, hf = ew >> 2;
+    const int etid = threadIdx.x - 128;
+    int nslab = (g.cout + 63) / 64;
+    if (nslab > SLABS) nslab = SLABS;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int sbuf = 0;
+    float acc_s[SLABS][8], acc_q[SLABS][8];
+#pragma unroll
+    for (int sl = 0; sl < SLABS; ++sl)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc_s[sl][k] = 0.f; acc_q[sl][k] = 0.f; }
+    for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+      int pt = ptile;
+      EpiMask mk;
+      mk.tw = g.tw; mk.th = g.th; mk.W = g.W; mk.H = g.H; mk.N = 1; mk.n0 = 0;
+      mk.w0 = (pt % g.tiles_w) * g.tw;
+      pt /= g.tiles_w;
+      mk.h0 = (pt % g.tiles_h) * g.th;
+      const int n0 = pt / g.tiles_h;
+      mk.full = (mk.w0 + g.tw <= g.W) && (mk.h0 + g.th <= g.H);
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mk.p_off = m * 128;
+#pragma unroll
+        for (int slab = 0; slab < SLABS; ++slab) {
+          if (slab < nslab) {  // uniform across the CTA
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>((acc * 2 + m) * BN + slab * 64 + hf * 32);
+            epi_unit<SLAB_COLS>(taddr, smem_gen + (smem_out - smem_base) + sbuf * (128 * 128),
+                                smem_out + sbuf * (128 * 128), &maps.d, slab * 64, mk.w0, mk.h0 + m * (g.th >> 1), n0,
+                                bias, g.cout, (m == 1 && slab == nslab - 1) ? tempty_bar + 8 * acc : 0u,
+                                stats != nullptr, mk, acc_s[slab], acc_q[slab], q, hf, ew, lane, etid);
+            sbuf ^= 1;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (stats != nullptr) epi_flush_stats<SLABS, SLAB_COLS>(acc_s, acc_q, stats, 0, g.cout, ew, lane);
+    if (etid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =================================================================================================
 // wgrad kernel: dW[co, tap, ci] += sum_{pixels in this CTA's K range} dY[p, co] * X[p + tap, ci]
 // =================================================================================================
 struct WMaps {
@@ -409,6 +894,10 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
       if (lane == 0) {
         const CUtensorMap* mx = &maps.x[taps.map[tap]];
         const int dwx = taps.dw[tap], dhx = taps.dh[tap];
+        // narrow layers (<= 64 output channels in this block): the second 64-channel dY slab would be all padding —
+        // it is not fetched (TMA cost is per box row), the MMA reads stale shared memory there and the accumulator
+        // rows it produces (co >= cout) are dropped by the epilogue / the reduce kernel
+        const int a_slabs = (g.cout - co_blk * 128 > 64) ? 2 : 1;
         int stage = 0;
         uint32_t phase = 0;
         for (int p = p_begin; p < p_end; ++p) {
@@ -418,11 +907,10 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
           const int h0 = (pt % g.tiles_h) * g.th;
           const int n0 = (pt / g.tiles_h) * g.tn;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * SLAB + Cfg::B_BYTES);
           const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
           const uint32_t sb = smem_b + stage * Cfg::B_BYTES;
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
+          for (int s = 0; s < a_slabs; ++s)
             tma_load_4d(sa + s * SLAB, &maps.dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
 #pragma unroll
           for (int s = 0; s < BN / 64; ++s)
@@ -568,6 +1056,7 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (num_k > 0) {
     if (warp == 0) {
       if (lane == 0) {
+        const int a_slabs = (g.cout - co_blk * 128 > 64) ? 2 : 1;  // see conv_wgrad_kernel
         int stage = 0;
         uint32_t phase = 0;
         for (int p = p_begin; p < p_end; ++p) {
@@ -577,11 +1066,10 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const int h0 = (pt % g.tiles_h) * g.th;
           const int n0 = pt / g.tiles_h;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * stage, stage_bytes);
+          mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * ASLAB + b_bytes);
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
+          for (int s = 0; s < a_slabs; ++s)
             tma_load_4d(sa + s * ASLAB, &map_dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
 #pragma unroll
           for (int s = 0; s < BN / 64; ++s)
@@ -795,6 +1283,16 @@ static int encode_w_map(CUtensorMap* m, const void* ptr, int64_t K, int64_t taps
   return NPP_OK;
 }
 
+// Kernel-selection switches, read once from the environment (diagnostics / A-B timing; defaults = newest kernels):
+//   NPP_CONV_EPI8=0  four-warp epilogue (conv_gemm_kernel) instead of conv_gemm2_kernel
+//   NPP_CONV3=0      no 256-pixel halo-sharing kernel for 3x3 / stride-1 fprop + dgrad
+//   NPP_CONV3_MIN_TILES=n  smallest number of 256-pixel tiles for which conv3_kernel is used (default 74)
+//   NPP_CONV3_PAD_PCT=p    largest padded / real pixel ratio (percent) conv3_kernel accepts (default 107)
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 struct PixTile { int tw, th, tn; };
 // Factor `prod` (a power of two) into a (tw, th, tn) box minimising padded work for a (W,H,N) grid.
 static PixTile choose_tile(int64_t W, int64_t H, int64_t N, int prod) {
@@ -836,6 +1334,18 @@ static int launch_fprop(const Maps& maps, const Geom& g, const TapTable& taps, c
   int per_nb = sm_count() / g.n_blocks;
   if (per_nb > g.num_ptiles) per_nb = g.num_ptiles;
   const int grid = per_nb * g.n_blocks;
+  static const int epi8 = env_flag("NPP_CONV_EPI8", 1);
+  if (epi8) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm2)", e); return NPP_E_CUDA; }
+      attr2_set = true;
+    }
+    conv_gemm2_kernel<BN><<<grid, kThreads2, Cfg::SMEM, st>>>(maps, g, taps, bias, stats);
+    NPP_CHECK_LAUNCH("conv_gemm2_kernel");
+    return NPP_OK;
+  }
   conv_gemm_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, bias, stats);
   NPP_CHECK_LAUNCH("conv_gemm_kernel");
   return NPP_OK;
@@ -908,6 +1418,76 @@ static int run_gemm(const npp_view4* a_views, int n_a, const npp_view4* d, const
   }
 }
 
+template <int BN>
+static int launch_conv3(const C3Maps& maps, const C3Geom& g, int smem, const float* bias, float* stats, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv3)", e); return NPP_E_CUDA; }
+    attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > g.num_ptiles) grid = g.num_ptiles;
+  conv3_kernel<BN><<<grid, kThreads2, smem, st>>>(maps, g, bias, stats);
+  NPP_CHECK_LAUNCH("conv3_kernel");
+  return NPP_OK;
+}
+
+// 3x3 / stride 1 / pad 1 / dilation 1 fprop (flip = 0) or dgrad (flip = 1) through conv3_kernel.
+// a: the tensor the taps read, d: the tensor produced (same N, H, W).  NPP_E_UNSUPPORTED = use the generic kernel.
+static int conv3_try(const npp_view4* a, const npp_view4* d, const void* wmat, int wK, int wRows, int flip,
+                     const float* bias, float* stats, cudaStream_t st) {
+  static const int enabled = env_flag("NPP_CONV3", 1);
+  static const int min_tiles = env_flag("NPP_CONV3_MIN_TILES", 74);
+  static const int pad_pct = env_flag("NPP_CONV3_PAD_PCT", 107);  // tests raise it to reach the ragged-tile code
+  if (!enabled) return NPP_E_UNSUPPORTED;
+  if (a->n != d->n || a->h != d->h || a->w != d->w || wRows > 128) return NPP_E_UNSUPPORTED;
+  // 256-pixel tile of one image; a one-row shift must be a whole number of 1024-byte swizzle atoms (tw % 8 == 0)
+  static const int cand[3][2] = {{16, 16}, {32, 8}, {8, 32}};
+  int tw = 0, th = 0;
+  int64_t best = -1;
+  for (int i = 0; i < 3; ++i) {
+    const int64_t cost = cdiv64(d->w, cand[i][0]) * cand[i][0] * cdiv64(d->h, cand[i][1]) * cand[i][1];
+    if (best < 0 || cost < best) { best = cost; tw = cand[i][0]; th = cand[i][1]; }
+  }
+  if (best * 100 > (int64_t)d->w * d->h * pad_pct) return NPP_E_UNSUPPORTED;  // padded work would eat the gain
+  C3Geom g;
+  memset(&g, 0, sizeof g);
+  g.tw = tw; g.th = th;
+  g.tiles_w = (int)cdiv64(d->w, tw);
+  g.tiles_h = (int)cdiv64(d->h, th);
+  const int64_t ptiles = (int64_t)g.tiles_w * g.tiles_h * d->n;
+  if (ptiles < min_tiles || ptiles > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  g.num_ptiles = (int)ptiles;
+  g.W = d->w; g.H = d->h;
+  g.kc_blocks = (int)cdiv64(wK, BK);
+  g.cout = wRows;
+  g.flip = flip;
+  g.a_bytes = (th + 2) * tw * 128;
+  const int bn = pick_bn(wRows);
+  const int b_bytes = bn * 128;
+  const int avail = 227 * 1024 - kC3OutBytes - 1024 /*barriers*/ - 1024 /*alignment slack*/;
+  g.sa = 3;
+  if (g.sa * g.a_bytes + 4 * b_bytes > avail) g.sa = 2;
+  g.sb = (avail - g.sa * g.a_bytes) / b_bytes;
+  if (g.sb > kC3MaxSB) g.sb = kC3MaxSB;
+  if (g.sb < 3) return NPP_E_UNSUPPORTED;
+  const int smem = g.sa * g.a_bytes + g.sb * b_bytes + kC3OutBytes + 1024 + 1024;
+  C3Maps maps;
+  memset(&maps, 0, sizeof maps);
+  int rc = encode_act_map(&maps.a, a->ptr, a->c, a->w, a->h, a->n, a->sw, a->sh, a->sn, tw, th + 2, 1);
+  if (rc) return rc;
+  rc = encode_act_map(&maps.d, d->ptr, d->c, d->w, d->h, d->n, d->sw, d->sh, d->sn, tw, th / 2, 1);
+  if (rc) return rc;
+  rc = encode_w_map(&maps.b, wmat, wK, 9, wRows, bn);
+  if (rc) return rc;
+  switch (bn) {
+    case 32: return launch_conv3<32>(maps, g, smem, bias, stats, st);
+    case 64: return launch_conv3<64>(maps, g, smem, bias, stats, st);
+    default: return launch_conv3<128>(maps, g, smem, bias, stats, st);
+  }
+}
+
 static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
 // phase (ph,pw) sub-view of v for stride-2 addressing
@@ -936,6 +1516,10 @@ int conv_fwd(const npp_view4* x, const void* w, const float* bias, const npp_vie
   int rc = check_conv_args(x, y, kh, kw, stride, pad, dil);
   if (rc) return rc;
   if (!w) return NPP_E_INVALID;
+  if (kh == 3 && kw == 3 && stride == 1 && dil == 1 && pad == 1 && hoff == 0 && woff == 0) {
+    rc = conv3_try(x, y, w, x->c, y->c, 0, bias, stats, st);
+    if (rc != NPP_E_UNSUPPORTED) return rc;
+  }
   TapTable taps;
   memset(&taps, 0, sizeof taps);
   npp_view4 av[4];
@@ -972,6 +1556,10 @@ int conv_dgrad(const npp_view4* dy, const void* wt, const npp_view4* dx, int kh,
   int rc = check_conv_args(dx, dy, kh, kw, stride, pad, dil);
   if (rc) return rc;
   if (!wt) return NPP_E_INVALID;
+  if (kh == 3 && kw == 3 && stride == 1 && dil == 1 && pad == 1 && hoff == 0 && woff == 0) {
+    rc = conv3_try(dy, dx, wt, dy->c, dx->c, 1, nullptr, nullptr, st);
+    if (rc != NPP_E_UNSUPPORTED) return rc;
+  }
   if (stride == 1) {
     TapTable taps;
     memset(&taps, 0, sizeof taps);

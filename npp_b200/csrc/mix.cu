@@ -218,11 +218,11 @@ __global__ void __launch_bounds__(256) mix_bwd_reduce_kernel(const MixArgs<T> A)
 #pragma unroll
       for (int v = 0; v < V; ++v) red[threadIdx.x * V + v] = (r == 0) ? s0[v] : s[j][v];
       __syncthreads();
+      block_colsum(red, A.geom.rows, A.geom.cvb * V);
       if (active && trow == 0) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          float t = 0.f;
-          for (int rr = 0; rr < A.geom.rows; ++rr) t += red[(rr * A.geom.cvb + tcv) * V + v];
+          float t = red[tcv * V + v];
           if (r > 0 && A.c0p[j]) t *= A.c1p[j][c0 + v];  // centred sum * invstd = sum g*xhat
           out[r * A.C + c0 + v] = t;
         }

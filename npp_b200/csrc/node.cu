@@ -254,11 +254,11 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
 #pragma unroll
     for (int v = 0; v < V; ++v) red[threadIdx.x * V + v] = src[v];
     __syncthreads();
+    block_colsum(red, A.g.rows, A.g.cvb * V);
     if (active && trow == 0) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        float s = 0.f;
-        for (int r = 0; r < A.g.rows; ++r) s += red[(r * A.g.cvb + tcv) * V + v];
+        const float s = red[tcv * V + v];
         const int ch = c0 + v;
         if (!atomic) {
           if (k == 0) {

@@ -76,6 +76,44 @@ static inline int foreach_vec(int N, int H, int W, int C, cudaStream_t st, const
   return NPP_OK;
 }
 
+// Column sums of a [rows][ncol] fp32 array in shared memory (ncol = channel vectors of the block x VEC), called by all
+// 256 threads after the array was written and a __syncthreads(); on return red[0..ncol) holds the sums (and a
+// __syncthreads() has been passed).  The first version let the `trow == 0` threads walk all rows serially: with few
+// channels per pixel (C = 32: 4 threads x 8 channels x 64 rows) that tail cost more than the streaming loop.
+__device__ __forceinline__ void block_colsum(float* red, int rows, int ncol) {
+  if (ncol <= 128) {
+    const int groups = 256 / ncol;  // >= 2 row groups, each thread folds rows rg, rg + groups, ...
+    const int col = threadIdx.x % ncol, rg = threadIdx.x / ncol;
+    float s = 0.f;
+    if (rg < groups)
+      for (int r = rg; r < rows; r += groups) s += red[r * ncol + col];
+    __syncthreads();
+    if (rg < groups) red[rg * ncol + col] = s;
+    __syncthreads();
+    if (threadIdx.x < ncol) {
+      float t = 0.f;
+      for (int g = 0; g < groups; ++g) t += red[g * ncol + threadIdx.x];
+      red[threadIdx.x] = t;
+    }
+  } else {
+    float t[8];  // ncol <= 256 * VEC <= 2048 columns
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = threadIdx.x + j * 256;
+      t[j] = 0.f;
+      if (col < ncol)
+        for (int r = 0; r < rows; ++r) t[j] += red[r * ncol + col];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = threadIdx.x + j * 256;
+      if (col < ncol) red[col] = t[j];
+    }
+  }
+  __syncthreads();
+}
+
 // Per-channel reduction over pixels of an [n,h,w,c] space: f(n,h,w,c0, acc[K][VEC]) accumulates K
 // quantities per channel; results are atomically added to out[k*out_kstride + (zoff + c)*out_cstride].
 // grid = (pixel chunks, channel-vector groups, Z) where Z = N if per_image else 1.
@@ -95,6 +133,7 @@ __global__ void __launch_bounds__(256) reduce_ch_kernel(int npix, int H, int W, 
   const int n_base = per_image ? blockIdx.z : 0;
   if (active) {
     const int step = gridDim.x * g.rows;
+#pragma unroll 4
     for (int p = blockIdx.x * g.rows + trow; p < npix; p += step) {
       const int w = p % W;
       const int t = p / W;
@@ -109,13 +148,12 @@ __global__ void __launch_bounds__(256) reduce_ch_kernel(int npix, int H, int W, 
 #pragma unroll
     for (int v = 0; v < VEC; ++v) red[threadIdx.x * VEC + v] = acc[k][v];
     __syncthreads();
+    block_colsum(red, g.rows, g.cvb * VEC);
     if (active && trow == 0) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float s = 0.f;
-        for (int r = 0; r < g.rows; ++r) s += red[(r * g.cvb + tcv) * VEC + v];
-        atomicAdd(out + k * out_kstride + ((per_image ? (int64_t)blockIdx.z * C : 0) + mycv * VEC + v) * out_cstride, s);
-      }
+      for (int v = 0; v < VEC; ++v)
+        atomicAdd(out + k * out_kstride + ((per_image ? (int64_t)blockIdx.z * C : 0) + mycv * VEC + v) * out_cstride,
+                  red[tcv * VEC + v]);
     }
   }
 }

@@ -57,6 +57,12 @@ static const Case cases[] = {
     {"3x3 384->128 96x96 n4 (three cin blocks)", 4, 96, 96, 384, 128, 3, 1, 1, 1, 0, 0, 0, 0, 0},
     {"3x3 40->24 20x36 n3 (ragged, odd channels)", 3, 20, 36, 40, 24, 3, 1, 1, 1, 0, 0, 0, 0, 0},
     {"3x3 1024->1024 12x12 n8 (wide)", 8, 12, 12, 1024, 1024, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 64->64 40x24 n3 (ragged 256-pixel tiles)", 3, 40, 24, 64, 64, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"3x3 128->72 bias 48x48 n4 (two slabs, second partial)", 4, 48, 48, 128, 72, 3, 1, 1, 1, 0, 0, 0, 0, 1},
+    {"3x3 slice-in 128(+64)->128(+32) 32x32 n5", 5, 32, 32, 128, 128, 3, 1, 1, 1, 0, 0, 64, 32, 0},
+    {"3x3 64->64 96x96 n32 (bench shape)", 32, 96, 96, 64, 64, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+    {"1x1 32->32 96x96 n32 (bench shape)", 32, 96, 96, 32, 32, 1, 1, 0, 1, 0, 0, 0, 0, 0},
+    {"1x1 64->64 48x48 n32 (bench shape)", 32, 48, 48, 64, 64, 1, 1, 0, 1, 0, 0, 0, 0, 0},
 };
 
 static uint32_t rng_state = 12345;

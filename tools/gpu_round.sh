@@ -15,7 +15,7 @@ timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
     --log-file gpurun_out/${tag}_launches.csv python tools/profile_step.py > gpurun_out/${tag}_ncu_launches.log 2>&1
 python tools/summarize_launches.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launches_summary.txt 2>&1
 gzip -f gpurun_out/${tag}_launches.csv
-for spec in "conv_gemm_kernel<128>:40" "conv_wgrad3_kernel:10"; do
+for spec in "conv_gemm2_kernel:40" "conv3_kernel:20" "conv_wgrad3_kernel:10"; do
   name=${spec%%:*}; skip=${spec##*:}
   safe=$(echo $name | tr -c 'a-zA-Z0-9_' '_')
   timeout 240 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$name" -s $skip -c 2 \
