@@ -622,6 +622,7 @@ struct C3Geom {
   int a_bytes;           // (th + 2) * tw * 128
   int sa, sb;            // ring depths (activation boxes, weight tiles)
   int flip;              // 0: fprop taps (x[h + r - 1][w + s - 1]); 1: dgrad taps (dy[h + 1 - r][w + 1 - s])
+  int two_producers;     // weight tiles issued by a second producer thread (warp 3)
 };
 constexpr int kC3MaxSA = 4, kC3MaxSB = 8;
 constexpr int kC3OutBytes = 2 * 128 * 128;
@@ -654,9 +655,9 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&maps.a);
-    prefetch_tensormap(&maps.b);
     prefetch_tensormap(&maps.d);
   }
+  if (warp == 3 && lane == 0) prefetch_tensormap(&maps.b);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.sa; ++i) {
       mbar_init(afull_bar + 8 * i, 1);
@@ -699,6 +700,27 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
             mbar_arrive_expect_tx(afull_bar + 8 * as, g.a_bytes);
             tma_load_4d(smem_a + as * g.a_bytes, &maps.a, afull_bar + 8 * as, kc * BK, cw, h0 - 1, n0);
             if (++as == g.sa) { as = 0; ap ^= 1; }
+            if (g.two_producers) continue;  // the weight ring is fed by warp 3
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(bempty_bar + 8 * bs, bp ^ 1);
+              mbar_arrive_expect_tx(bfull_bar + 8 * bs, B_BYTES);
+              tma_load_3d(smem_b + bs * B_BYTES, &maps.b, bfull_bar + 8 * bs, kc * BK, r * 3 + s, 0);
+              if (++bs == g.sb) { bs = 0; bp ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ second TMA producer: weight tiles only, so
+    // that the activation ring runs its full depth ahead instead of being throttled by the (shorter) weight ring
+    if (lane == 0 && g.two_producers) {
+      int bs = 0;
+      uint32_t bp = 0;
+      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+        for (int s = 0; s < 3; ++s) {
+          for (int kc = 0; kc < g.kc_blocks; ++kc) {
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {
               mbar_wait(bempty_bar + 8 * bs, bp ^ 1);
@@ -1288,6 +1310,8 @@ static int encode_w_map(CUtensorMap* m, const void* ptr, int64_t K, int64_t taps
 //   NPP_CONV3=0      no 256-pixel halo-sharing kernel for 3x3 / stride-1 fprop + dgrad
 //   NPP_CONV3_MIN_TILES=n  smallest number of 256-pixel tiles for which conv3_kernel is used (default 74)
 //   NPP_CONV3_PAD_PCT=p    largest padded / real pixel ratio (percent) conv3_kernel accepts (default 107)
+//   NPP_CONV3_2PROD=0      one TMA producer thread for both rings of conv3_kernel (default: two)
+//   NPP_CONV3_TILE=i       only the i-th tile candidate {16x16, 32x8, 8x32} (experiments)
 static int env_flag(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -1444,9 +1468,12 @@ static int conv3_try(const npp_view4* a, const npp_view4* d, const void* wmat, i
   if (a->n != d->n || a->h != d->h || a->w != d->w || wRows > 128) return NPP_E_UNSUPPORTED;
   // 256-pixel tile of one image; a one-row shift must be a whole number of 1024-byte swizzle atoms (tw % 8 == 0)
   static const int cand[3][2] = {{16, 16}, {32, 8}, {8, 32}};
+  static const int force_tile = env_flag("NPP_CONV3_TILE", -1);  // experiments: 0 / 1 / 2 = only that candidate
+  static const int two_prod = env_flag("NPP_CONV3_2PROD", 1);
   int tw = 0, th = 0;
   int64_t best = -1;
   for (int i = 0; i < 3; ++i) {
+    if (force_tile >= 0 && i != force_tile) continue;
     const int64_t cost = cdiv64(d->w, cand[i][0]) * cand[i][0] * cdiv64(d->h, cand[i][1]) * cand[i][1];
     if (best < 0 || cost < best) { best = cost; tw = cand[i][0]; th = cand[i][1]; }
   }
@@ -1463,6 +1490,7 @@ static int conv3_try(const npp_view4* a, const npp_view4* d, const void* wmat, i
   g.kc_blocks = (int)cdiv64(wK, BK);
   g.cout = wRows;
   g.flip = flip;
+  g.two_producers = two_prod;
   g.a_bytes = (th + 2) * tw * 128;
   const int bn = pick_bn(wRows);
   const int b_bytes = bn * 128;

@@ -49,17 +49,27 @@ __device__ __forceinline__ void dw_stage(uint4* tile, const DView<const T>& X, c
                                          int iw0, int c0, int cvn, bool relu) {
   constexpr int V = Pack<T>::N;
   const int total = g.IH * g.IW * 8;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int cv = i & 7;
-    const int p = i >> 3;
-    const int pw = p % g.IW, ph = p / g.IW;
-    const int h = ih0 + ph, w = iw0 + pw;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (cv < cvn && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi) {
-      v = ldraw(X.at(n, h, w, c0 + cv * V));
-      if (relu) v = relu_packed<T>(v);
+  // four independent 16-byte loads in flight per thread before the first shared-memory store (the one-load-per-
+  // iteration loop of the first version left the staging phase latency-bound)
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < total) {
+        const int cv = i & 7;
+        const int p = i >> 3;
+        const int pw = p % g.IW, ph = p / g.IW;
+        const int h = ih0 + ph, w = iw0 + pw;
+        if (cv < cvn && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi) v[u] = ldraw(X.at(n, h, w, c0 + cv * V));
+      }
     }
-    tile[i] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < total) tile[i] = relu ? relu_packed<T>(v[u]) : v[u];
+    }
   }
 }
 
@@ -274,7 +284,7 @@ int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride
     return NPP_E_UNSUPPORTED;
   int rc = dw_set_smem<sizeof(T) * 10 + 2>(dw_tile_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_tile_wgrad)");
   if (rc) return rc;
-  int slots = (2 * sm_count()) / g.cblocks;
+  int slots = (2 * sm_count()) / g.cblocks;  // (4 per SM measured slower: twice the same-address atomics at the end)
   if (slots < 1) slots = 1;
   if (slots > g.ntiles) slots = g.ntiles;
   g.slots = slots;

@@ -349,7 +349,9 @@ __global__ void __launch_bounds__(256) reduce_partials_acc_kernel(const float* _
 
 static int node_bwd_blocks(int64_t npix, int C, int V) {
   const VecGeom g = vec_geom(C, V);
-  return stream_grid(npix, g, 8, 4);
+  // ~105 registers x 256 threads: two blocks are resident per SM, so 2 x SMs blocks are one full wave — and half as
+  // many partial rows for reduce_partials to fold as the former 4 x SMs
+  return stream_grid(npix, g, 8, 2);
 }
 
 template <typename T>

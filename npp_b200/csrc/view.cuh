@@ -166,8 +166,12 @@ static inline int reduce_ch(int N, int H, int W, int C, bool per_image, float* o
   if (npix > 0x7fffffff) return NPP_E_UNSUPPORTED;
   const int z = per_image ? N : 1;
   int64_t gx = (npix + g.rows - 1) / g.rows;
-  // fill the machine (~8 blocks per SM) but keep >= 16 pixels per thread so the per-block atomics stay negligible
-  const int64_t cap = ((int64_t)sm_count() * 8 + (int64_t)g.gy * z - 1) / ((int64_t)g.gy * z);
+  // Every block ends with one atomic per (channel, quantity) on the SAME out[] addresses (per image when per_image):
+  // same-address atomics serialise in L2 (~30 clk each), so with 8 blocks per SM the tail of a whole-batch reduction
+  // (1184 blocks -> 1184 serialised adds per address = 18 us) cost more than streaming the tensor.  Two blocks per SM
+  // keep the tail under 5 us; the pixel loop is unrolled x4 so 512 threads still hold 32 KB of loads in flight per SM.
+  const int bps = per_image ? 8 : 2;
+  const int64_t cap = ((int64_t)sm_count() * bps + (int64_t)g.gy * z - 1) / ((int64_t)g.gy * z);
   if (gx > cap) gx = cap;
   const int64_t max_by_work = (npix + (int64_t)g.rows * 16 - 1) / ((int64_t)g.rows * 16);
   if (gx > max_by_work) gx = max_by_work;
