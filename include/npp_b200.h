@@ -185,6 +185,10 @@ int npp_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n
 int npp_nchw_to_nhwc(const float* src, int src_c, const npp_view4* dst, int dtype,
                      npp_stream_t stream); /* channels >= src_c of dst are zero filled */
 int npp_nhwc_to_nchw(const npp_view4* src, float* dst, int dst_c, int dtype, npp_stream_t stream);
+/* 3x3 im2col of a 3-channel bf16 image (x: c == 8 padded) into y: c == 32 with y[.., ci*9 + r*3 + s] =
+ * x[.., ho*stride - pad + r, wo*stride - pad + s, ci]: the stem convolutions Conv2d(3, C, 3, 2, 1)
+ * (models/model_augment.py:244-272) then run as 1x1 convolutions whose [Cout, 27] weight matrix is the OIHW weight. */
+int npp_im2col3x3_c3(const npp_view4* x, const npp_view4* y, int stride, int pad, npp_stream_t stream);
 int npp_fill_zero(const npp_view4* y, int dtype, npp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -351,6 +355,26 @@ int npp_adam_step(const void* tensor_table, int ntensors, const int32_t* chunk_t
 int npp_node_fwd(const npp_view4* a, const float* scale_a, const float* shift_a, const npp_view4* b,
                  const float* scale_b, const float* shift_b, const npp_view4* y_raw,
                  const npp_view4* y_relu, int dtype, npp_stream_t stream);
+/* node_fwd with the BatchNorm finalize of either side folded into the kernel (replaces one npp_bn_finalize launch
+ * per side): fin_x != NULL => side x is normalised with the batch statistics in fin_x->stats ([2][C] sums over
+ * `count` elements per channel), the kernel writes fin_x->coef = [scale | shift | mean | invstd] (4C floats, the
+ * backward kernels read it) and updates running_mean / running_var[0:c_run] with `momentum` (unbiased variance), as
+ * nn.BatchNorm2d does in training mode (models/operations.py:27,61,79).  fin_x == NULL => scale_x / shift_x as in
+ * npp_node_fwd. */
+typedef struct {
+  const float* stats;
+  const float* gamma;        /* NULL = 1 */
+  const float* beta;         /* NULL = 0 */
+  float* running_mean;       /* NULL = not tracked */
+  float* running_var;
+  float* coef;
+  float momentum, eps;
+  int32_t c_run;
+} npp_bn_fin;
+int npp_node_fwd_bn(const npp_view4* a, const npp_bn_fin* fin_a, const float* scale_a, const float* shift_a,
+                    const npp_view4* b, const npp_bn_fin* fin_b, const float* scale_b, const float* shift_b,
+                    const npp_view4* y_raw, const npp_view4* y_relu, double count, int dtype,
+                    npp_stream_t stream);
 int npp_node_bwd_blocks(int n, int h, int w, int c, int dtype);
 int npp_node_bwd_reduce(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
                         const npp_view4* a, const float* mean_a, const float* invstd_a,
@@ -366,6 +390,30 @@ int npp_node_bwd_reduce_atomic(const npp_view4* g_raw, const npp_view4* g_relu, 
                                const npp_view4* b, const float* mean_b, const float* invstd_b,
                                const npp_view4* g_out, float* sums, float* const* acc,
                                const int* acc_valid, int dtype, npp_stream_t stream);
+/* Two-kernel BatchNorm backward of a node without the partials buffer and the fold kernel: reduce blocks add their
+ * per-channel sums with fp32 atomics into copy (block % stripes) of sums = [stripes][nq][C] (zeroed by the caller; the
+ * striping keeps same-address atomic chains short), apply folds the copies while it builds its coefficients and its
+ * first pixel block adds d beta / d gamma into acc[i][0:acc_valid[i]] (HOST arrays of nq entries in sums-row order,
+ * entries may be NULL; acc may be NULL).  Not usable when the sums must be all-reduced in between (SyncBN). */
+int npp_node_bwd_reduce_striped(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
+                                const npp_view4* a, const float* mean_a, const float* invstd_a,
+                                const npp_view4* b, const float* mean_b, const float* invstd_b,
+                                const npp_view4* g_out, float* sums, int stripes, int dtype, npp_stream_t stream);
+/* General form of the first backward kernel: g = g_raw + g_raw2 + [relu_out > 0] * (g_relu + g_relu2).  g_raw2 /
+ * g_relu2 are second gradients of the same outputs (the channel slice of the cell-output gradient that the consumers
+ * of the concat buffer hand down, model_augment.py:62) — summed here instead of by a separate strided add kernel;
+ * g_x2 requires g_x.  Exactly one of partials (per-block rows, fold with npp_reduce_partials) / sums (striped atomic
+ * totals, see above) when a BatchNorm side exists. */
+int npp_node_bwd_reduce2(const npp_view4* g_raw, const npp_view4* g_raw2, const npp_view4* g_relu,
+                         const npp_view4* g_relu2, const npp_view4* relu_out, const npp_view4* a,
+                         const float* mean_a, const float* invstd_a, const npp_view4* b, const float* mean_b,
+                         const float* invstd_b, const npp_view4* g_out, float* partials, float* sums,
+                         int stripes, int dtype, npp_stream_t stream);
+int npp_node_bwd_apply_striped(const npp_view4* g, const npp_view4* a, const float* gamma_a, const float* mean_a,
+                               const float* invstd_a, const npp_view4* da, const npp_view4* b,
+                               const float* gamma_b, const float* mean_b, const float* invstd_b,
+                               const npp_view4* db, const float* sums, int stripes, float* const* acc,
+                               const int* acc_valid, double count, int dtype, npp_stream_t stream);
 /* reduce_partials that also accumulates segment s = columns [s*seg_len,(s+1)*seg_len) of the folded row into
  * acc[s][0:acc_valid[s]] (+=; NULL = skip): BatchNorm d beta / d gamma go straight into the optimizer's flat
  * gradient buffer.  acc / acc_valid: HOST arrays of len/seg_len (<= NPP_ACC_MAX) entries. */

@@ -36,6 +36,13 @@ class MixDesc(ctypes.Structure):
                 ("gamma", ctypes.c_void_p * NPP_MIX_MAX), ("dy", View4 * NPP_MIX_MAX)]
 
 
+class BnFin(ctypes.Structure):
+    """Mirror of `npp_bn_fin` (include/npp_b200.h)."""
+    _fields_ = [("stats", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p), ("coef", ctypes.c_void_p),
+                ("momentum", ctypes.c_float), ("eps", ctypes.c_float), ("c_run", ctypes.c_int32)]
+
+
 _lib = None
 
 

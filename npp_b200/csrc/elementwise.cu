@@ -121,6 +121,67 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, DView<T> dst,
   }
 }
 
+// Images (C <= 8 -> one 16-byte bf16 vector per pixel): a thread per pixel reads its C channel planes (coalesced
+// across the warp) and writes one uint4.  The generic 32 x 32 transpose above wastes 29 of 32 tile rows on a
+// 3-channel image and writes 2-byte elements (ncu: 154 GB/s on the 32 x 3 x 384 x 384 input batch).
+template <int DUMMY>
+__global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restrict__ src, DView<__nv_bfloat16> dst,
+                                                            int C) {
+  const int hw = dst.h * dst.w;
+  const int n = blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? src[((int64_t)n * C + c) * hw + p] : 0.f;
+    Pack<__nv_bfloat16>::store(dst.at(n, p / dst.w, p % dst.w, 0), v);
+  }
+}
+
+// 3x3 im2col of a 3-channel image (internal NHWC bf16, channels padded to 8) for the network stems
+// (models/model_augment.py:244-272: Conv2d(3, C, 3, stride 2, padding 1)): y[n, ho, wo, ci*9 + r*3 + s] =
+// x[n, ho*stride - pad + r, wo*stride - pad + s, ci] (zero outside), channels 27..31 zero.  With the taps folded into
+// the channel axis the stem is a 1x1 convolution with K = 32 whose weight matrix [Cout, 27] IS the OIHW master
+// weight — the implicit-GEMM kernel otherwise spends nine 64-wide K blocks on 3 real channels each (7.6 TFLOP/s).
+__global__ void __launch_bounds__(256) im2col3x3_c3_kernel(DView<const __nv_bfloat16> X, DView<__nv_bfloat16> Y,
+                                                           int stride, int pad) {
+  const int npix = Y.n * Y.h * Y.w;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const int wo = p % Y.w;
+    const int t = p / Y.w;
+    const int ho = t % Y.h;
+    const int n = t / Y.h;
+    uint2 in[9];  // channels 0..3 of the nine taps (channel 3 is padding)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int h = ho * stride - pad + r, w = wo * stride - pad + q;
+        in[r * 3 + q] = (h >= 0 && h < X.h && w >= 0 && w < X.w) ? *reinterpret_cast<const uint2*>(X.at(n, h, w, 0))
+                                                                   : make_uint2(0u, 0u);
+      }
+    // 16-bit element k = ci*9 + tap of the output row
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      uint32_t pair = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 2 * j + e;
+        if (k < 27) {
+          const int ci = k / 9, tap = k % 9;
+          const uint32_t word = ci < 2 ? in[tap].x : in[tap].y;
+          const uint32_t el = (ci & 1) ? (word >> 16) : (word & 0xffffu);
+          pair |= el << (16 * e);
+        }
+      }
+      o[j] = pair;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(Y.at(n, ho, wo, 0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(DView<const T> src, float* __restrict__ dst, int C) {
   __shared__ float tile[32][33];
@@ -229,9 +290,30 @@ int npp_cast(const void* src, int sd, void* dst, int dd, int64_t n, npp_stream_t
 }
 int npp_nchw_to_nhwc(const float* src, int src_c, const npp_view4* dst, int dtype, npp_stream_t s) {
   if (!src || !view_ok(dst, dtype) || src_c <= 0 || src_c > dst->c) return NPP_E_INVALID;
+  if (dtype == NPP_BF16 && dst->c == 8 && dst->n <= 65535) {
+    const int hw = dst->h * dst->w;
+    int gx = (hw + 255) / 256;
+    if (gx > 2048) gx = 2048;
+    nchw_to_nhwc8_kernel<0><<<dim3(gx, dst->n), 256, 0, as_stream(s)>>>(src, dview<__nv_bfloat16>(dst), src_c);
+    NPP_CHECK_LAUNCH("nchw_to_nhwc8_kernel");
+    return NPP_OK;
+  }
   dim3 grid((dst->h * dst->w + 31) / 32, (dst->c + 31) / 32, dst->n), block(32, 8);
   NPP_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, as_stream(s)>>>(src, dview<T>(dst), src_c););
   NPP_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return NPP_OK;
+}
+int npp_im2col3x3_c3(const npp_view4* x, const npp_view4* y, int stride, int pad, npp_stream_t s) {
+  if (!view_ok(x, NPP_BF16) || !view_ok(y, NPP_BF16) || x->c != 8 || y->c != 32 || x->n != y->n || stride < 1 || pad < 0)
+    return NPP_E_INVALID;
+  if (y->h != (x->h + 2 * pad - 3) / stride + 1 || y->w != (x->w + 2 * pad - 3) / stride + 1) return NPP_E_INVALID;
+  const int64_t npix = (int64_t)y->n * y->h * y->w;
+  if (npix > 0x7fffffff) return NPP_E_UNSUPPORTED;
+  int64_t grid = (npix + 255) / 256;
+  if (grid > (int64_t)sm_count() * 32) grid = (int64_t)sm_count() * 32;
+  im2col3x3_c3_kernel<<<(unsigned)grid, 256, 0, as_stream(s)>>>(dview<const __nv_bfloat16>(x), dview<__nv_bfloat16>(y),
+                                                               stride, pad);
+  NPP_CHECK_LAUNCH("im2col3x3_c3_kernel");
   return NPP_OK;
 }
 int npp_nhwc_to_nchw(const npp_view4* src, float* dst, int dst_c, int dtype, npp_stream_t s) {

@@ -169,6 +169,7 @@ class TrainStep:
                 self._step_body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        F_._arena.reserve(self.images.device)   # sized by the warm-up step; cannot grow during capture
         self.graph = torch.cuda.CUDAGraph()
         c0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):

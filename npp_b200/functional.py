@@ -6,6 +6,7 @@ C padded to a multiple of 8 with zero channels.  Every Function below launches h
 kernels on torch's current CUDA stream through the C ABI; torch only owns the memory.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -13,7 +14,15 @@ from torch.autograd import Function
 from . import _lib as L
 from ._lib import call, view, stream, fptr, i32, i64, f32, f64, ref, NULL
 
-_state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None}
+_state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
+          # kernel-selection switches (A/B timing, bisecting): NPP_NODE_STRIPED=0 -> partials + fold kernel for the
+          # BatchNorm backward sums of a node; NPP_NODE_FUSED_FINALIZE=0 -> separate npp_bn_finalize launches
+          "node_striped": os.environ.get("NPP_NODE_STRIPED", "1") != "0",
+          "node_fused_finalize": os.environ.get("NPP_NODE_FUSED_FINALIZE", "1") != "0",
+          # NPP_STEM_IM2COL=0 -> the 3-channel stems run through the generic 3x3 implicit-GEMM kernel
+          "stem_im2col": os.environ.get("NPP_STEM_IM2COL", "1") != "0",
+          # NPP_NODE_CAT_GRADS=0 -> the concat-slice gradient of a cell state is added by autograd (strided at::add)
+          "node_cat_grads": os.environ.get("NPP_NODE_CAT_GRADS", "1") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -76,13 +85,19 @@ class ZeroArena:
         if self.buf is None or self.buf.numel() < self.need:
             if torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("ZeroArena must be sized by an eager step before CUDA-graph capture")
-            self.buf = torch.zeros(max(self.need, 1 << 16), dtype=torch.float32, device=device)
+            self.buf = torch.zeros(max(self.need, 1 << 20), dtype=torch.float32, device=device)
         else:
             self.buf.zero_()
         self.cursor, self.need, self.active = 0, 0, True
 
     def end(self):
         self.active = False
+
+    def reserve(self, device):
+        """Grows the buffer to what the last step asked for.  engine.TrainStep.prepare() calls this between its eager
+        warm-up step and the CUDA-graph capture (the buffer cannot be re-allocated while capturing)."""
+        if self.buf is None or self.buf.numel() < self.need:
+            self.buf = torch.zeros(max(self.need, 1 << 20), dtype=torch.float32, device=device)
 
     def take(self, n):
         n4 = (n + 3) // 4 * 4          # keep every slice 16-byte aligned (float4 loads)
@@ -335,10 +350,30 @@ class _ConvFn(Function):
         return dx, dw, db, None, None, None, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_stats=False):
+def im2col3x3_c3(x, stride, pad):
+    """[N, 3(+5 pad), H, W] internal bf16 image -> [N, 32, Ho, Wo] with channel ci*9 + r*3 + s = tap (r, s) of input
+    channel ci (npp_im2col3x3_c3).  The result is cached on the image tensor: both task streams' stems
+    (model_augment.py:244-272) read the same input."""
+    key = (int(stride), int(pad))
+    hit = getattr(x, "_npp_im2col", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    n, _, h, w = x.shape
+    ho, wo = conv_out_size(h, 3, stride, pad, 1), conv_out_size(w, 3, stride, pad, 1)
+    y = empty_internal(n, 32, ho, wo, x.dtype, x.device)
+    call("npp_im2col3x3_c3", ref(view(x)), ref(view(y)), i32(stride), i32(pad), stream())
+    x._npp_im2col = (key, y)
+    return y
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_stats=False, slot_of=None):
     """Dense conv on an internal tensor.  Returns (y, stats) where stats is the fused per-channel
-    (sum, sum of squares) of y from the tcgen05 epilogue (empty when not requested / fp32 mode)."""
-    slots = (grad_slot(weight), grad_slot(bias))
+    (sum, sum of squares) of y from the tcgen05 epilogue (empty when not requested / fp32 mode).
+    slot_of: the parameter `weight` is a reshaped view of (its gradient slot, viewed the same way, receives dW)."""
+    wslot = grad_slot(weight) if slot_of is None else grad_slot(slot_of)
+    if wslot is not None and slot_of is not None:
+        wslot = wslot.view(weight.shape)
+    slots = (wslot, grad_slot(bias))
     packed = getattr(weight, "_npp_packed", None) if _state.get("packed_weights") else None
     return _ConvFn.apply(x, weight, bias, int(stride), int(pad), int(dil), int(hoff), int(woff), bool(want_stats),
                          slots if (slots[0] is not None or slots[1] is not None) else None, packed)
@@ -585,9 +620,12 @@ class _BNSide:
     __slots__ = ("bn", "stats", "coef", "c")
 
 
-def _bn_forward_coef(y, stats, bn, sync):
+def _bn_forward_coef(y, stats, bn, sync, defer=False):
     """Batch statistics -> (scale, shift, mean, invstd) as one [4C] tensor; updates the running statistics
-    (nn.BatchNorm2d training semantics, momentum 0.1 / eps 1e-5 in operations.py:27)."""
+    (nn.BatchNorm2d training semantics, momentum 0.1 / eps 1e-5 in operations.py:27).
+    defer=True (training, no SyncBN): the finalize arithmetic is left to the consuming node kernel
+    (npp_node_fwd_bn); returns (coef, count, gamma, fin) with fin = the npp_bn_fin descriptor, or fin = None when
+    the coefficients were computed here."""
     n, c, h, w = y.shape
     dev = y.device
     training = bn.training or not bn.track_running_stats
@@ -603,7 +641,7 @@ def _bn_forward_coef(y, stats, bn, sync):
         if torch.is_grad_enabled():  # backward through running statistics: xhat = (x - rm) * rsqrt(rv + eps)
             coef[2 * c:3 * c] = rm
             coef[3 * c:] = torch.rsqrt(rv + bn.eps)
-        return coef, float(n * h * w), gamma
+        return (coef, float(n * h * w), gamma, None) if defer else (coef, float(n * h * w), gamma)
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         if _state["defer_bn_counters"] is not None:
             _state["defer_bn_counters"].append(bn.num_batches_tracked)  # one foreach add per step (engine.TrainStep)
@@ -616,10 +654,18 @@ def _bn_forward_coef(y, stats, bn, sync):
     if sync:
         count *= _allreduce_sum(stats)
     c_run = bn.running_mean.numel() if bn.running_mean is not None else 0
+    if defer and not sync:
+        fin = L.BnFin(fptr(stats).value, fptr(gamma).value, fptr(beta).value, fptr(bn.running_mean).value,
+                      fptr(bn.running_var).value, fptr(coef).value, float(bn.momentum), float(bn.eps), int(c_run))
+        fin._keep = (stats, gamma, beta, coef)
+        return coef, count, gamma, fin
     call("npp_bn_finalize", fptr(stats), f64(count), fptr(gamma), fptr(beta), fptr(bn.running_mean),
          fptr(bn.running_var), f32(bn.momentum), f32(bn.eps), fptr(coef[:c]), fptr(coef[c:2 * c]), fptr(coef[2 * c:3 * c]),
          fptr(coef[3 * c:]), i32(c), i32(c_run), stream())
-    return coef, count, gamma
+    return (coef, count, gamma, None) if defer else (coef, count, gamma)
+
+
+_NODE_STRIPES = 8
 
 
 class _NodeFn(Function):
@@ -628,7 +674,7 @@ class _NodeFn(Function):
 
     @staticmethod
     def forward(ctx, a, ga, ba, b, gb, bb, cfg):
-        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu, pslots = cfg
+        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu, pslots, want_cat = cfg
         ctx.set_materialize_grads(False)
         ctx.pslots = pslots
         n, c, h, w = a.shape
@@ -637,27 +683,49 @@ class _NodeFn(Function):
         ca = cb = None
         count = float(n * h * w)
         gam_a = gam_b = None
+        fin_a = fin_b = None
+        defer = _state.get("node_fused_finalize", True)
         if bn_a is not None:
-            ca, count, gam_a = _bn_forward_coef(a, st_a, bn_a, sync)
+            ca, count, gam_a, fin_a = _bn_forward_coef(a, st_a, bn_a, sync, defer=defer)
         if bn_b is not None:
-            cb, count, gam_b = _bn_forward_coef(b, st_b, bn_b, sync)
+            cb, count, gam_b, fin_b = _bn_forward_coef(b, st_b, bn_b, sync, defer=defer)
         raw = (out_raw if out_raw is not None else empty_internal(n, c, h, w, a.dtype, a.device)) if want_raw else None
         rel = (out_relu if out_relu is not None else empty_internal(n, c, h, w, a.dtype, a.device)) if want_relu else None
-        call("npp_node_fwd", ref(view(a)), fptr(ca[:c]) if ca is not None else NULL,
-             fptr(ca[c:2 * c]) if ca is not None else NULL, ref(view(b)) if b is not None else NULL,
-             fptr(cb[:c]) if cb is not None else NULL, fptr(cb[c:2 * c]) if cb is not None else NULL,
-             ref(view(raw)) if raw is not None else NULL, ref(view(rel)) if rel is not None else NULL, i32(code), stream())
+        if fin_a is not None or fin_b is not None:
+            # BatchNorm finalize (batch sums -> scale / shift / mean / invstd, running statistics) inside the node kernel
+            call("npp_node_fwd_bn", ref(view(a)), ref(fin_a) if fin_a is not None else NULL,
+                 fptr(ca[:c]) if (ca is not None and fin_a is None) else NULL,
+                 fptr(ca[c:2 * c]) if (ca is not None and fin_a is None) else NULL,
+                 ref(view(b)) if b is not None else NULL, ref(fin_b) if fin_b is not None else NULL,
+                 fptr(cb[:c]) if (cb is not None and fin_b is None) else NULL,
+                 fptr(cb[c:2 * c]) if (cb is not None and fin_b is None) else NULL,
+                 ref(view(raw)) if raw is not None else NULL, ref(view(rel)) if rel is not None else NULL, f64(count),
+                 i32(code), stream(), keep=(fin_a, fin_b))
+        else:
+            call("npp_node_fwd", ref(view(a)), fptr(ca[:c]) if ca is not None else NULL,
+                 fptr(ca[c:2 * c]) if ca is not None else NULL, ref(view(b)) if b is not None else NULL,
+                 fptr(cb[:c]) if cb is not None else NULL, fptr(cb[c:2 * c]) if cb is not None else NULL,
+                 ref(view(raw)) if raw is not None else NULL, ref(view(rel)) if rel is not None else NULL, i32(code),
+                 stream())
         eval_a = bn_a is not None and not (bn_a.training or not bn_a.track_running_stats)
         eval_b = bn_b is not None and not (bn_b.training or not bn_b.track_running_stats)
         ctx.flags = (bn_a is not None, bn_b is not None, b is not None, count, sync, eval_a, eval_b)
         ctx.save_for_backward(a if bn_a is not None else None, ca, gam_a, b if bn_b is not None else None, cb, gam_b,
                               rel)
-        return raw, rel
+        # second handles on the same outputs for the concat route (functional.assemble): their gradients reach
+        # backward() separately and are summed inside npp_node_bwd_reduce2 instead of by autograd's add kernels
+        raw_c = alias(raw, 0, c) if (want_cat and raw is not None) else None
+        rel_c = alias(rel, 0, c) if (want_cat and rel is not None) else None
+        return raw, rel, raw_c, rel_c
 
     @staticmethod
-    def backward(ctx, g_raw, g_relu):
+    def backward(ctx, g_raw, g_relu, g_raw2=None, g_relu2=None):
         a, ca, gam_a, b, cb, gam_b, rel = ctx.saved_tensors
         has_a, has_b, two, count, sync, eval_a, eval_b = ctx.flags
+        if g_raw is None and g_raw2 is not None:
+            g_raw, g_raw2 = g_raw2, None
+        if g_relu is None and g_relu2 is not None:
+            g_relu, g_relu2 = g_relu2, None
         if g_raw is None and g_relu is None:
             return None, None, None, None, None, None, None
         like = rel if rel is not None else (a if a is not None else (g_raw if g_raw is not None else g_relu))
@@ -665,14 +733,19 @@ class _NodeFn(Function):
             g_raw = as_internal_grad(g_raw, like)
         if g_relu is not None:
             g_relu = as_internal_grad(g_relu, like)
+        if g_raw2 is not None:
+            g_raw2 = as_internal_grad(g_raw2, like)
+        if g_relu2 is not None:
+            g_relu2 = as_internal_grad(g_relu2, like)
         ref_t = g_raw if g_raw is not None else g_relu
         n, c, h, w = ref_t.shape
         code = L.dtype_code(ref_t)
         dev = ref_t.device
         g = g_raw
         need_bn = has_a or has_b
-        if g_relu is not None or need_bn:
-            if g_relu is not None:
+        combine = g_relu is not None or g_raw2 is not None
+        if combine or need_bn:
+            if combine:
                 g = empty_internal(n, c, h, w, ref_t.dtype, dev)
             nq = 2 * (int(has_a) + int(has_b))
             parts = sums = None
@@ -680,8 +753,14 @@ class _NodeFn(Function):
             # npp_node_bwd_reduce_atomic (per-block sums added with atomics, no partials buffer / fold kernel) was
             # measured SLOWER than partials + fold (15.7 vs 13.8 ms per step: ~600 blocks hammer the same 4C
             # addresses), so the deterministic path stays; the switch is kept for experiments
-            atomic = need_bn and _arena.active and _state.get("node_reduce_atomics", False)
-            if need_bn and not atomic:
+            atomic = (need_bn and _arena.active and _state.get("node_reduce_atomics", False)
+                      and g_raw2 is None and g_relu2 is None)
+            # striped path (default on one GPU): reduce blocks add into 8 striped copies of the totals, the apply
+            # kernel folds them and writes d beta / d gamma into the flat gradient buffer — no partials buffer, no
+            # fold kernel (326 launches per step).  SyncBN needs the totals between the two kernels: old path.
+            striped = (need_bn and not sync and not (eval_a or eval_b) and not atomic
+                       and _state.get("node_striped", True))
+            if need_bn and not atomic and not striped:
                 nblk = L.lib().npp_node_bwd_blocks(i32(n), i32(h), i32(w), i32(c), i32(code))
                 parts = torch.empty(nblk * nq * c, dtype=torch.float32, device=dev)
             common = (ref(view(g_raw)) if g_raw is not None else NULL,
@@ -689,8 +768,15 @@ class _NodeFn(Function):
                       ref(view(a)) if has_a else NULL, fptr(ca[2 * c:3 * c]) if has_a else NULL,
                       fptr(ca[3 * c:]) if has_a else NULL, ref(view(b)) if has_b else NULL,
                       fptr(cb[2 * c:3 * c]) if has_b else NULL, fptr(cb[3 * c:]) if has_b else NULL,
-                      ref(view(g)) if g_relu is not None else NULL)
-            if atomic:
+                      ref(view(g)) if combine else NULL)
+            common2 = (common[0], ref(view(g_raw2)) if g_raw2 is not None else NULL, common[1],
+                       ref(view(g_relu2)) if g_relu2 is not None else NULL) + common[2:]
+            if striped:
+                sums = zeros_f32(_NODE_STRIPES * nq * c, dev)
+                call("npp_node_bwd_reduce2", *common2, NULL, fptr(sums), i32(_NODE_STRIPES), i32(code), stream())
+            elif g_raw2 is not None or g_relu2 is not None:
+                call("npp_node_bwd_reduce2", *common2, fptr(parts), NULL, i32(1), i32(code), stream())
+            elif atomic:
                 sums = zeros_f32(nq * c, dev)
                 segs = []
                 if has_a:
@@ -703,7 +789,34 @@ class _NodeFn(Function):
             else:
                 call("npp_node_bwd_reduce", *common, fptr(parts), i32(code), stream())
         da = db = dga = dba = dgb = dbb = None
-        if need_bn:
+        if need_bn and striped:
+            sl_a, sl_b = ctx.pslots
+            segs = []
+            if has_a:
+                segs += list(sl_a) if sl_a is not None else [None, None]
+            if has_b:
+                segs += list(sl_b) if sl_b is not None else [None, None]
+            accp = (ctypes.c_void_p * len(segs))(*[t.data_ptr() if t is not None else None for t in segs])
+            accv = (ctypes.c_int * len(segs))(*[min(t.numel(), c) if t is not None else 0 for t in segs])
+            if has_a:
+                da = torch.empty_like(a)
+            if has_b:
+                db = torch.empty_like(b)
+            call("npp_node_bwd_apply_striped", ref(view(g)), ref(view(a)) if has_a else NULL,
+                 fptr(gam_a) if has_a else NULL, fptr(ca[2 * c:3 * c]) if has_a else NULL,
+                 fptr(ca[3 * c:]) if has_a else NULL, ref(view(da)) if has_a else NULL,
+                 ref(view(b)) if has_b else NULL, fptr(gam_b) if has_b else NULL,
+                 fptr(cb[2 * c:3 * c]) if has_b else NULL, fptr(cb[3 * c:]) if has_b else NULL,
+                 ref(view(db)) if has_b else NULL, fptr(sums), i32(_NODE_STRIPES), accp, accv, f64(count), i32(code),
+                 stream(), keep=segs)
+            if (has_a and sl_a is None) or (has_b and sl_b is None):   # gradients returned through autograd
+                local = sums.view(_NODE_STRIPES, nq * c).sum(0)
+                if has_a:
+                    dba, dga = local[:c], local[c:2 * c]
+                if has_b:
+                    o = 2 * c * int(has_a)
+                    dbb, dgb = local[o:o + c], local[o + c:o + 2 * c]
+        elif need_bn:
             if sums is None:   # deterministic path: fold the per-block partials
                 sums = torch.empty(nq * c, dtype=torch.float32, device=dev)
                 if (has_a and sl_a is not None) or (has_b and sl_b is not None):
@@ -765,10 +878,13 @@ def _side(x):
     return check_raw(x, "node"), None, None
 
 
-def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None):
+def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None, want_cat=False):
     """One fused pass for a cell node (model_augment.py:48-62): a and b are internal tensors or Pending BatchNorm
     outputs; returns (raw, relu) — either None when not wanted — with `raw._npp_relu = relu` when both exist.
-    out_raw / out_relu: preallocated destinations (channel slices of a concat buffer, see alias())."""
+    out_raw / out_relu: preallocated destinations (channel slices of a concat buffer, see alias()).
+    want_cat: also return second handles (raw_c, relu_c) on the same storage for the concat route — the gradient that
+    comes down through the concat buffer then stays separate from the in-cell consumers' gradients until the node's
+    own backward kernel adds them (no strided autograd add)."""
     if b is not None and not isinstance(a, Pending) and isinstance(b, Pending):
         a, b = b, a  # keep a BatchNorm side first (the kernels take either layout; this just normalises)
     ya, bn_a, st_a = _side(a)
@@ -795,12 +911,16 @@ def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None)
             if sl[0] is None or sl[1] is None:
                 sl = None
         pslots.append(sl)
-    raw, rel = _NodeFn.apply(ya, ga, ba, yb, gb, bb, (bn_a, st_a, bn_b, st_b, bool(want_raw), bool(want_relu), out_raw,
-                                                       out_relu, pslots))
+    cat_req = bool(want_cat)
+    want_cat = cat_req and _state.get("node_cat_grads", True)
+    raw, rel, raw_c, rel_c = _NodeFn.apply(ya, ga, ba, yb, gb, bb, (bn_a, st_a, bn_b, st_b, bool(want_raw),
+                                                                    bool(want_relu), out_raw, out_relu, pslots, want_cat))
     if rel is not None:
         rel._npp_is_relu = True   # relu(rel) is rel (no tensor ever references itself: that would leak the graph)
         if raw is not None:
             raw._npp_relu = rel
+    if cat_req:
+        return raw, rel, (raw_c if raw_c is not None else raw), (rel_c if rel_c is not None else rel)
     return raw, rel
 
 

@@ -143,11 +143,17 @@ class _StepCell(nn.Module):
                         o_raw = t
                     else:
                         o_rel = t
-            raw, rel = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel)
-            if o_raw is not None:
-                slices[(mem[0], "raw")][mem[1]] = raw
-            if o_rel is not None:
-                slices[(mem[0], "relu")][mem[1]] = rel
+            if o_raw is not None or o_rel is not None:
+                # concat member: the concat buffer gets its own handles, so the gradient coming down through the cell
+                # output is summed with the in-cell consumers' gradients inside the node's backward kernel
+                raw, rel, raw_c, rel_c = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel,
+                                                 want_cat=True)
+                if o_raw is not None:
+                    slices[(mem[0], "raw")][mem[1]] = raw_c
+                if o_rel is not None:
+                    slices[(mem[0], "relu")][mem[1]] = rel_c
+            else:
+                raw, rel = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel)
             handles.append(F_.state_handle(raw, rel))
 
         for k, p in enumerate(pre):

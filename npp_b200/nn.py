@@ -61,6 +61,15 @@ class Conv2d(nn.Conv2d):
             x = F_.relu(x)
         else:
             F_.check_raw(x, "conv")
+        if (self.in_channels == 3 and self.kernel_size == (3, 3) and self.dilation[0] == 1 and not hoff and not woff
+                and x.dtype == torch.bfloat16 and x.shape[1] == 8 and not x.requires_grad
+                and F_._state.get("stem_im2col", True)):
+            # image stem: taps folded into the channel axis (K = 27 -> 32), then a 1x1 convolution whose weight
+            # matrix [Cout, 27] is the OIHW master weight itself (same memory, so dW lands in the parameter's slot)
+            xc = F_.im2col3x3_c3(x, self.stride[0], self.padding[0])
+            y, stats = F_.conv2d(xc, self.weight.view(self.out_channels, 27, 1, 1), self.bias, 1, 0, 1, 0, 0, want_stats,
+                                 slot_of=self.weight)
+            return y, (stats if stats.numel() else None)
         y, stats = F_.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], self.dilation[0], hoff, woff,
                              want_stats)
         return y, (stats if stats.numel() else None)
