@@ -276,13 +276,29 @@ def main():
     # ---- end to end through the public API: H2D of the batch from pinned host memory, step, D2H of the loss
     losses = []
 
-    def e2e_step():
+    def e2e_step_plain():
         step.load(*host, non_blocking=True)
         step.run()
         losses.append(float(step.loss.item()))
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_step_prefetch():
+        # public API with input prefetch: run() consumes the batch staged on the device and the upload of the NEXT
+        # batch (pinned host -> device, side stream) overlaps the step; one full upload + one loss read per step
+        step.run()
+        step.prefetch(*host)
+        losses.append(float(step.loss.item()))
+
+    e2e_step, e2e_mode = e2e_step_prefetch, "next batch's H2D overlaps the running step (TrainStep.prefetch)"
+    try:
+        step.prefetch(*host)
+        for _ in range(2):
+            e2e_step()
+    except Exception as exc:   # fall back to the serial upload
+        print("prefetch path failed (%r): serial H2D" % (exc,), file=sys.stderr)
+        step._staged = False
+        e2e_step, e2e_mode = e2e_step_plain, "serial: H2D, step, D2H"
+        for _ in range(2):
+            e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop()
 
@@ -299,6 +315,15 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback (B200_PROFILING.md)"
         gemm = prof["conv_gemm(fprop+dgrad)"]
+        # DRAM traffic of the dominant kernel class from the committed ncu capture of the same kernels (one eager step
+        # under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`, tools/gpu_final.sh -> tools/ncu_traffic.py):
+        # bytes per launch, averaged over the class like `achieved`
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = tj["conv_gemm"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
         kernels = {}
         for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
@@ -326,10 +351,11 @@ def main():
                        "l2": "no flush: per-step working set (%.1f GB peak activations) >> 126 MB L2" % (peak_mem / 1e9)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": step.input_bytes(), "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps, "loss_first": losses[0], "loss_last": losses[-1]},
+                    "ms_per_step": ms_e2e / args.steps, "loss_first": losses[0], "loss_last": losses[-1],
+                    "mode": e2e_mode},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak if tf_peak else None, "traffic": None,
+                         "frac": achieved / tf_peak if tf_peak else None, "traffic": traffic,
                          "kernel": "conv_gemm_kernel<BN> (tcgen05 implicit GEMM: fprop + dgrad, %d launches/step)" % gemm["calls"],
                          "how": "algorithmic FLOPs (2*N*Ho*Wo*Cout*Cin*kh*kw) of every dense-conv fprop and dgrad launch of "
                                 "one step / CUDA-event time of those launches replayed back to back on the launch stream",

@@ -13,6 +13,7 @@
 //   wgrad : dw[c,t] += sum_p dy[p] * relu(x)[p*stride - pad + t*dil]         persistent CTAs keep the 9 x 8
 //           accumulators of their channel vector in registers over all their tiles, one atomic per (CTA, c, t).
 #include "view.cuh"
+#include <stdlib.h>
 
 namespace npp {
 
@@ -102,10 +103,17 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, co
   const int pw = lane % g.TW, pr = lane / g.TW;
   const int ow = ow0 + pw;
   if (ow >= g.Wo) return;
+  // dgrad: the ReLU mask (x at the produced pixel) of the NEXT row is fetched while the current row is computed —
+  // ncu showed the row loop stalled on this global load (long scoreboard) once per row
+  uint4 mnext = make_uint4(0u, 0u, 0u, 0u);
+  if (BWD && relu_in && pr < g.TH && oh0 + pr < g.Ho) mnext = ldraw(M.at(n, oh0 + pr, ow, c));
   for (int k = 0; k < g.PPT; ++k) {
     const int ph = pr + k * g.RPP;
     const int oh = oh0 + ph;
     if (ph >= g.TH || oh >= g.Ho) break;
+    const uint4 mcur = mnext;
+    if (BWD && relu_in && k + 1 < g.PPT && ph + g.RPP < g.TH && oh + g.RPP < g.Ho)
+      mnext = ldraw(M.at(n, oh + g.RPP, ow, c));
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.f;
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, co
       }
     if (BWD && relu_in) {
       float xv[V];
-      Pack<T>::load(M.at(n, oh, ow, c), xv);
+      Pack<T>::unpack(mcur, xv);
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = xv[i] > 0.f ? acc[i] : 0.f;
     }
@@ -159,12 +167,17 @@ __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T>
     __syncthreads();
     const int ow = ow0 + pw;
     if (cv < cvn && ow < g.Wo) {
+      // dY of the next row is in flight while the nine taps of the current row are accumulated
+      uint4 dnext = make_uint4(0u, 0u, 0u, 0u);
+      if (pr < g.TH && oh0 + pr < g.Ho) dnext = ldraw(DY.at(n, oh0 + pr, ow, c));
       for (int k = 0; k < g.PPT; ++k) {
         const int ph = pr + k * g.RPP;
         const int oh = oh0 + ph;
         if (ph >= g.TH || oh >= g.Ho) break;
+        const uint4 dcur = dnext;
+        if (k + 1 < g.PPT && ph + g.RPP < g.TH && oh + g.RPP < g.Ho) dnext = ldraw(DY.at(n, oh + g.RPP, ow, c));
         float d[V];
-        Pack<T>::load(DY.at(n, oh, ow, c), d);
+        Pack<T>::unpack(dcur, d);
         const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -196,6 +209,233 @@ __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T>
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined variants: persistent CTAs, TWO staged tiles in shared memory, cp.async staging.
+// ncu on the kernels above (128 channels @ 96x96 x 32): 23 % of the warp slots active, top stalls = the shared-memory
+// store waiting for the staging loads and the CTA barrier behind it — every CTA runs "load tile, wait, compute" back
+// to back and two or three resident CTAs do not hide a DRAM round trip.  Here the copy of tile i+1 (cp.async, zero
+// fill outside the tensor, no registers) is in flight while tile i is computed; the leading ReLU is applied in place
+// by the thread that issued the copy.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void dw_stage_async(uint4* tile, const DView<const T>& X, const DwTileGeom& g, int n, int ih0,
+                                               int iw0, int c0, int cvn) {
+  constexpr int V = Pack<T>::N;
+  const int total = g.IH * g.IW * 8;
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int cv = i & 7;
+    const int p = i >> 3;
+    const int pw = p % g.IW, ph = p / g.IW;
+    const int h = ih0 + ph, w = iw0 + pw;
+    const bool ok = cv < cvn && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi;
+    cp_async16_zfill(base + i * 16, ok ? static_cast<const void*>(X.at(n, h, w, c0 + cv * V)) : static_cast<const void*>(X.p), ok);
+  }
+}
+// in-place ReLU of the elements this thread copied (visible to it after its own cp.async.wait_group)
+template <typename T>
+__device__ __forceinline__ void dw_relu_own(uint4* tile, const DwTileGeom& g) {
+  const int total = g.IH * g.IW * 8;
+  for (int i = threadIdx.x; i < total; i += 256) tile[i] = relu_packed<T>(tile[i]);
+}
+
+__device__ __forceinline__ void dw_tile_coords(const DwTileGeom& g, int tix, int& n, int& oh0, int& ow0) {
+  const int tw = tix % g.tiles_w;
+  tix /= g.tiles_w;
+  const int th = tix % g.tiles_h;
+  n = tix / g.tiles_h;
+  oh0 = th * g.TH;
+  ow0 = tw * g.TW;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, const float* __restrict__ wgt,
+                                                      const DView<T> Y, const DView<const T> M, const DwTileGeom g,
+                                                      int relu_in, int tile_elems) {
+  constexpr int V = Pack<T>::N;
+  extern __shared__ uint4 dw_tile_smem[];
+  const int cb = blockIdx.x % g.cblocks;
+  const int slot = blockIdx.x / g.cblocks;
+  const int c0 = cb * 8 * V;
+  int cvn = (g.C - c0) / V;
+  if (cvn > 8) cvn = 8;
+  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = c0 + cv * V;
+  const int pw = lane % g.TW, pr = lane / g.TW;
+  const bool cv_ok = cv < cvn;
+  float wr[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < V; ++i) wr[t][i] = cv_ok ? __ldg(wgt + (c + i) * 9 + (BWD ? 8 - t : t)) : 0.f;
+  const bool relu_stage = !BWD && relu_in;
+  int it = 0;
+  {
+    int n, oh0, ow0;
+    if (slot < g.ntiles) {
+      dw_tile_coords(g, slot, n, oh0, ow0);
+      dw_stage_async<T>(dw_tile_smem, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn);
+    }
+    cp_async_commit();
+  }
+  for (int tix = slot; tix < g.ntiles; tix += g.slots, ++it) {
+    uint4* cur = dw_tile_smem + (it & 1) * tile_elems;
+    uint4* nxt = dw_tile_smem + ((it + 1) & 1) * tile_elems;
+    if (tix + g.slots < g.ntiles) {
+      int n2, oh2, ow2;
+      dw_tile_coords(g, tix + g.slots, n2, oh2, ow2);
+      dw_stage_async<T>(nxt, X, g, n2, oh2 * g.stride + g.off_h, ow2 * g.stride + g.off_w, c0, cvn);
+    }
+    cp_async_commit();       // (possibly empty) group: keeps the group count uniform
+    cp_async_wait<1>();      // everything but the newest group has landed: tile `tix` is in `cur`
+    if (relu_stage) dw_relu_own<T>(cur, g);
+    __syncthreads();
+    int n, oh0, ow0;
+    dw_tile_coords(g, tix, n, oh0, ow0);
+    const int ow = ow0 + pw;
+    if (cv_ok && ow < g.Wo) {
+      uint4 mnext = make_uint4(0u, 0u, 0u, 0u);
+      if (BWD && relu_in && pr < g.TH && oh0 + pr < g.Ho) mnext = ldraw(M.at(n, oh0 + pr, ow, c));
+      for (int k = 0; k < g.PPT; ++k) {
+        const int ph = pr + k * g.RPP;
+        const int oh = oh0 + ph;
+        if (ph >= g.TH || oh >= g.Ho) break;
+        const uint4 mcur = mnext;
+        if (BWD && relu_in && k + 1 < g.PPT && ph + g.RPP < g.TH && oh + g.RPP < g.Ho)
+          mnext = ldraw(M.at(n, oh + g.RPP, ow, c));
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        const uint4* base = cur + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float v[V];
+            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = fmaf(v[i], wr[r * 3 + q][i], acc[i]);
+          }
+        if (BWD && relu_in) {
+          float xv[V];
+          Pack<T>::unpack(mcur, xv);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] = xv[i] > 0.f ? acc[i] : 0.f;
+        }
+        Pack<T>::store(Y.at(n, oh, ow, c), acc);
+      }
+    }
+    __syncthreads();  // `cur` is the copy target of the next iteration
+  }
+  cp_async_wait<0>();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T> X, const DView<const T> DY,
+                                                            float* __restrict__ dw, const DwTileGeom g, int relu_in,
+                                                            int tile_elems) {
+  constexpr int V = Pack<T>::N;
+  extern __shared__ uint4 dw_tile_smem[];
+  const int cb = blockIdx.x % g.cblocks;
+  const int slot = blockIdx.x / g.cblocks;
+  const int c0 = cb * 8 * V;
+  int cvn = (g.C - c0) / V;
+  if (cvn > 8) cvn = 8;
+  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = c0 + cv * V;
+  const int pw = lane % g.TW, pr = lane / g.TW;
+  float acc[9][V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[t][i] = 0.f;
+  int it = 0;
+  {
+    int n, oh0, ow0;
+    if (slot < g.ntiles) {
+      dw_tile_coords(g, slot, n, oh0, ow0);
+      dw_stage_async<T>(dw_tile_smem, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn);
+    }
+    cp_async_commit();
+  }
+  for (int tix = slot; tix < g.ntiles; tix += g.slots, ++it) {
+    uint4* cur = dw_tile_smem + (it & 1) * tile_elems;
+    uint4* nxt = dw_tile_smem + ((it + 1) & 1) * tile_elems;
+    if (tix + g.slots < g.ntiles) {
+      int n2, oh2, ow2;
+      dw_tile_coords(g, tix + g.slots, n2, oh2, ow2);
+      dw_stage_async<T>(nxt, X, g, n2, oh2 * g.stride + g.off_h, ow2 * g.stride + g.off_w, c0, cvn);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    if (relu_in) dw_relu_own<T>(cur, g);
+    __syncthreads();
+    int n, oh0, ow0;
+    dw_tile_coords(g, tix, n, oh0, ow0);
+    const int ow = ow0 + pw;
+    if (cv < cvn && ow < g.Wo) {
+      uint4 dnext = make_uint4(0u, 0u, 0u, 0u);
+      if (pr < g.TH && oh0 + pr < g.Ho) dnext = ldraw(DY.at(n, oh0 + pr, ow, c));
+      for (int k = 0; k < g.PPT; ++k) {
+        const int ph = pr + k * g.RPP;
+        const int oh = oh0 + ph;
+        if (ph >= g.TH || oh >= g.Ho) break;
+        const uint4 dcur = dnext;
+        if (k + 1 < g.PPT && ph + g.RPP < g.TH && oh + g.RPP < g.Ho) dnext = ldraw(DY.at(n, oh + g.RPP, ow, c));
+        float d[V];
+        Pack<T>::unpack(dcur, d);
+        const uint4* base = cur + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float v[V];
+            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[r * 3 + q][i] = fmaf(d[i], v[i], acc[r * 3 + q][i]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  // fold the 32 pixel lanes of every channel vector, one atomic per (CTA, channel, tap)
+  float* red = reinterpret_cast<float*>(dw_tile_smem);  // 256 * V floats <= one staged tile
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = acc[t][i];
+    __syncthreads();
+    if (threadIdx.x < 8 * V) {
+      const int cvj = threadIdx.x / V, ij = threadIdx.x % V;
+      if (cvj < cvn) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) s += red[((l * 8) + cvj) * V + ij];
+        atomicAdd(dw + (int64_t)(c0 + threadIdx.x) * 9 + t, s);
+      }
+    }
+  }
+}
+
+static int dw_pipe_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NPP_DW_PIPE");
+    v = (e && *e) ? atoi(e) : 1;
+  }
+  return v;
 }
 
 // Tile geometry; returns false when the shape should stay on the gather kernels (stride-2 tiles that would not fit).
@@ -242,6 +482,23 @@ static int dw_set_smem(K kernel, const char* name) {
   return NPP_OK;
 }
 
+template <int TAG, typename K>
+static int dw_set_smem2(K kernel, const char* name) {
+  static bool done = false;
+  if (done) return NPP_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  if (e != cudaSuccess) { set_error(name, e); return NPP_E_CUDA; }
+  done = true;
+  return NPP_OK;
+}
+// persistent grid of the pipelined kernels: two CTAs (2 x <= 112 KB) per SM, every CTA keeps one channel block
+static void dw_pipe_slots(DwTileGeom& g) {
+  int slots = (2 * sm_count()) / g.cblocks;
+  if (slots < 1) slots = 1;
+  if (slots > g.ntiles) slots = g.ntiles;
+  g.slots = slots;
+}
+
 // returns NPP_E_UNSUPPORTED when the caller should use the gather kernels instead
 template <typename T>
 int dw_tile_fwd(const npp_view4* x, const float* w, const npp_view4* y, int stride, int pad, int dil, int relu_in,
@@ -250,9 +507,18 @@ int dw_tile_fwd(const npp_view4* x, const float* w, const npp_view4* y, int stri
   size_t smem;
   if (!dw_tile_geom(g, y->n, x->h, x->w, y->h, y->w, y->c, Pack<T>::N, stride, dil, -pad, -pad, &smem))
     return NPP_E_UNSUPPORTED;
+  const auto X = dview<const T>(x);
+  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
+    int rc = dw_set_smem2<sizeof(T) * 10 + 3>(dw_pipe_kernel<T, false>, "cudaFuncSetAttribute(dw_pipe_fwd)");
+    if (rc) return rc;
+    dw_pipe_slots(g);
+    dw_pipe_kernel<T, false><<<g.slots * g.cblocks, 256, 2 * smem, st>>>(X, w, dview<T>(y), X, g, relu_in,
+                                                                         (int)(smem / 16));
+    NPP_CHECK_LAUNCH("dw_pipe_fwd");
+    return NPP_OK;
+  }
   int rc = dw_set_smem<sizeof(T) * 10 + 0>(dw_tile_kernel<T, false>, "cudaFuncSetAttribute(dw_tile_fwd)");
   if (rc) return rc;
-  const auto X = dview<const T>(x);
   dw_tile_kernel<T, false><<<g.ntiles * g.cblocks, 256, smem, st>>>(X, w, dview<T>(y), X, g, relu_in);
   NPP_CHECK_LAUNCH("dw_tile_fwd");
   return NPP_OK;
@@ -267,6 +533,15 @@ int dw_tile_dgrad(const npp_view4* x, const float* w, const npp_view4* dy, const
   // dx[h] = sum_t dy[h + pad - t*dil] w[t] = sum_t' dy[h + pad - 2*dil + t'*dil] w[2 - t']
   if (!dw_tile_geom(g, dx->n, dy->h, dy->w, dx->h, dx->w, dx->c, Pack<T>::N, 1, dil, pad - 2 * dil, pad - 2 * dil, &smem))
     return NPP_E_UNSUPPORTED;
+  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
+    int rc = dw_set_smem2<sizeof(T) * 10 + 4>(dw_pipe_kernel<T, true>, "cudaFuncSetAttribute(dw_pipe_dgrad)");
+    if (rc) return rc;
+    dw_pipe_slots(g);
+    dw_pipe_kernel<T, true><<<g.slots * g.cblocks, 256, 2 * smem, st>>>(dview<const T>(dy), w, dview<T>(dx),
+                                                                        dview<const T>(x), g, relu_in, (int)(smem / 16));
+    NPP_CHECK_LAUNCH("dw_pipe_dgrad");
+    return NPP_OK;
+  }
   int rc = dw_set_smem<sizeof(T) * 10 + 1>(dw_tile_kernel<T, true>, "cudaFuncSetAttribute(dw_tile_dgrad)");
   if (rc) return rc;
   dw_tile_kernel<T, true><<<g.ntiles * g.cblocks, 256, smem, st>>>(dview<const T>(dy), w, dview<T>(dx),
@@ -282,6 +557,15 @@ int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride
   size_t smem;
   if (!dw_tile_geom(g, dy->n, x->h, x->w, dy->h, dy->w, dy->c, Pack<T>::N, stride, dil, -pad, -pad, &smem))
     return NPP_E_UNSUPPORTED;
+  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
+    int rc = dw_set_smem2<sizeof(T) * 10 + 5>(dw_pipe_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_pipe_wgrad)");
+    if (rc) return rc;
+    dw_pipe_slots(g);
+    dw_pipe_wgrad_kernel<T><<<g.slots * g.cblocks, 256, 2 * smem, st>>>(dview<const T>(x), dview<const T>(dy), dw, g,
+                                                                        relu_in, (int)(smem / 16));
+    NPP_CHECK_LAUNCH("dw_pipe_wgrad");
+    return NPP_OK;
+  }
   int rc = dw_set_smem<sizeof(T) * 10 + 2>(dw_tile_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_tile_wgrad)");
   if (rc) return rc;
   int slots = (2 * sm_count()) / g.cblocks;  // (4 per SM measured slower: twice the same-address atomics at the end)

@@ -100,6 +100,8 @@ class TrainStep:
         self.flat_grads = optimizer.use_flat_grads() if hasattr(optimizer, "use_flat_grads") else None
         self.launches_per_step = None
         self.packer = F_.WeightPacker(model) if dev.type == "cuda" else None   # all conv weights: one launch per step
+        self._stage = None       # prefetch(): staging copies of the inputs, filled on a side stream
+        self._staged = False
 
     # ---- pieces ------------------------------------------------------------------------------------
     def load(self, images, par_lab, edge_lab, pose_gt, pose_aux_gt, non_blocking=True):
@@ -109,6 +111,33 @@ class TrainStep:
         self.edge_lab.copy_(edge_lab, non_blocking=non_blocking)
         self.pose_gt.copy_(pose_gt, non_blocking=non_blocking)
         self.pose_aux_gt.copy_(pose_aux_gt, non_blocking=non_blocking)
+
+    def _inputs(self):
+        return (self.images, self.par_lab, self.edge_lab, self.pose_gt, self.pose_aux_gt)
+
+    def prefetch(self, images, par_lab, edge_lab, pose_gt, pose_aux_gt):
+        """Uploads the NEXT batch (pinned host memory) into staging buffers on a side stream, so the host->device
+        copy overlaps the step that is running; the next run() moves it into the static inputs with device-to-device
+        copies (the DataLoader prefetch of augment_lip_sync.py:173-184, moved onto the device side)."""
+        if self._stage is None:
+            self._stage = [torch.empty_like(t) for t in self._inputs()]
+            self._copy_stream = torch.cuda.Stream()
+            self._ev_up, self._ev_used = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_used.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_used)   # the previous staged batch has been consumed
+            for s, h in zip(self._stage, (images, par_lab, edge_lab, pose_gt, pose_aux_gt)):
+                s.copy_(h, non_blocking=True)
+            self._ev_up.record(self._copy_stream)
+        self._staged = True
+
+    def _consume_staged(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ev_up)
+        for d, s in zip(self._inputs(), self._stage):
+            d.copy_(s, non_blocking=True)
+        self._ev_used.record(cur)
+        self._staged = False
 
     def input_bytes(self):
         return sum(t.numel() * t.element_size() for t in (self.images, self.par_lab, self.edge_lab, self.pose_gt,
@@ -177,7 +206,10 @@ class TrainStep:
         self.launches_per_step = _lib.launch_count() - c0
 
     def run(self):
-        """Runs one step on whatever is in the static input buffers; returns the (device) loss scalar."""
+        """Runs one step on whatever is in the static input buffers (or on the batch staged by prefetch()); returns
+        the (device) loss scalar."""
+        if self._staged:
+            self._consume_staged()
         if self.use_graph:
             if self.graph is None:
                 self.prepare()

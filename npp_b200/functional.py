@@ -665,7 +665,7 @@ def _bn_forward_coef(y, stats, bn, sync, defer=False):
     return (coef, count, gamma, None) if defer else (coef, count, gamma)
 
 
-_NODE_STRIPES = 8
+_NODE_STRIPES = max(1, min(64, int(os.environ.get("NPP_NODE_STRIPES", "8"))))
 
 
 class _NodeFn(Function):
