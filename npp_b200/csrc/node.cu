@@ -251,7 +251,10 @@ struct NodeBwdReduceArgs {
   VecGeom g;
 };
 
-template <typename T, int U>
+// HAS2 = the second-gradient inputs exist.  A separate instantiation (with one pixel in flight per thread instead of
+// two): compiled into the common kernel the two extra 16-byte loads per pixel pushed it past the 128-register cap of
+// two resident blocks per SM and it spilled (ptxas: 168 bytes), slowing every node backward of the step.
+template <typename T, int U, bool HAS2>
 __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdReduceArgs<T> A) {
   constexpr int V = Pack<T>::N;
   __shared__ float red[256 * V];
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
   const bool active = trow < A.g.rows && mycv < A.g.cv;
   const int c0 = mycv * V;
   const bool has_raw = A.graw.p != nullptr, has_relu = A.grelu.p != nullptr;
-  const bool has_raw2 = A.graw2.p != nullptr, has_relu2 = A.grelu2.p != nullptr;
+  const bool has_raw2 = HAS2 && A.graw2.p != nullptr, has_relu2 = HAS2 && A.grelu2.p != nullptr;
   const bool has_a = A.a.p != nullptr, has_b = A.b.p != nullptr;
   float ma[V], mb[V];
   float s0[V], s1[V], s2[V];  // sum g, sum g*(x_a - mean_a), sum g*(x_b - mean_b); invstd is applied at the end
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
     if (has_b) load_coef<V>(A.mean_b, c0, mb);
     const int step = gridDim.x * A.g.rows;
     for (int p0 = blockIdx.x * A.g.rows + trow; p0 < A.npix; p0 += U * step) {
-      uint4 qg[U], qgr[U], qr[U], qa[U], qb[U], qg2[U], qgr2[U];
+      uint4 qg[U], qgr[U], qr[U], qa[U], qb[U], qg2[HAS2 ? U : 1], qgr2[HAS2 ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int p = p0 + u * step;
@@ -282,8 +285,8 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
             qgr[u] = ldraw(A.grelu.at(p, c0));
             qr[u] = ldraw(A.r.at(p, c0));
           }
-          if (has_raw2) qg2[u] = ldraw(A.graw2.at(p, c0));
-          if (has_relu2) qgr2[u] = ldraw(A.grelu2.at(p, c0));
+          if (HAS2 && has_raw2) qg2[HAS2 ? u : 0] = ldraw(A.graw2.at(p, c0));
+          if (HAS2 && has_relu2) qgr2[HAS2 ? u : 0] = ldraw(A.grelu2.at(p, c0));
           if (has_a) qa[u] = ldraw(A.a.at(p, c0));
           if (has_b) qb[u] = ldraw(A.b.at(p, c0));
         }
@@ -297,15 +300,15 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
         if (has_relu) { Pack<T>::unpack(qgr[u], gr[0]); Pack<T>::unpack(qr[u], rr[0]); }
         if (has_a) Pack<T>::unpack(qa[u], xa[0]);
         if (has_b) Pack<T>::unpack(qb[u], xb[0]);
-        if (has_raw2) {   // host guarantees has_raw2 => has_raw, has_relu2 => has_relu
+        if (HAS2 && has_raw2) {   // host guarantees has_raw2 => has_raw, has_relu2 => has_relu
           float t2[V];
-          Pack<T>::unpack(qg2[u], t2);
+          Pack<T>::unpack(qg2[HAS2 ? u : 0], t2);
 #pragma unroll
           for (int i = 0; i < V; ++i) g[0][i] += t2[i];
         }
-        if (has_relu2) {
+        if (HAS2 && has_relu2) {
           float t2[V];
-          Pack<T>::unpack(qgr2[u], t2);
+          Pack<T>::unpack(qgr2[HAS2 ? u : 0], t2);
 #pragma unroll
           for (int i = 0; i < V; ++i) gr[0][i] += t2[i];
         }
@@ -484,7 +487,10 @@ static int node_bwd_reduce_t(const npp_view4* graw, const npp_view4* grelu, cons
   A.g = vec_geom(ref->c, V);
   if (A.g.gy != 1) return NPP_E_UNSUPPORTED;
   dim3 grid((unsigned)node_bwd_blocks(npix, ref->c, V), 1);
-  node_bwd_reduce_kernel<T, 2><<<grid, 256, 0, st>>>(A);
+  if (graw2 || grelu2)
+    node_bwd_reduce_kernel<T, 1, true><<<grid, 256, 0, st>>>(A);
+  else
+    node_bwd_reduce_kernel<T, 2, false><<<grid, 256, 0, st>>>(A);
   NPP_CHECK_LAUNCH("node_bwd_reduce_kernel");
   return NPP_OK;
 }
@@ -541,7 +547,9 @@ __device__ __forceinline__ void bn_bwd_coef(const float* gamma, const float* mea
   }
 }
 
-template <typename T, int U>
+// STRIPED = striped totals / gradient-slot writes (npp_node_bwd_apply_striped); kept out of the default instantiation
+// for the same register-budget reason as HAS2 above.
+template <typename T, int U, bool STRIPED>
 __global__ void __launch_bounds__(256, 2) node_bwd_apply_kernel(const NodeBwdApplyArgs<T> A) {
   constexpr int V = Pack<T>::N;
   const int tcv = threadIdx.x % A.geom.cvb;
@@ -551,13 +559,14 @@ __global__ void __launch_bounds__(256, 2) node_bwd_apply_kernel(const NodeBwdApp
   const int c0 = mycv * V;
   const bool has_a = A.a.p != nullptr, has_b = A.b.p != nullptr;
   float aa[V], ab[V], ak[V], ba[V], bb[V], bk[V];
-  const bool owner = blockIdx.x == 0 && trow == 0;  // exactly one thread per channel vector writes the slots
+  const bool owner = STRIPED && blockIdx.x == 0 && trow == 0;  // one thread per channel vector writes the slots
+  const int stripes = STRIPED ? A.stripes : 1;
   if (has_a)
-    bn_bwd_coef<V>(A.gamma_a, A.mean_a, A.invstd_a, A.sums_a, A.C, c0, A.inv_count, aa, ab, ak, A.stripes,
+    bn_bwd_coef<V>(A.gamma_a, A.mean_a, A.invstd_a, A.sums_a, A.C, c0, A.inv_count, aa, ab, ak, stripes,
                    A.stripe_stride, owner ? A.acc.s[0].ptr : nullptr, A.acc.s[0].valid, owner ? A.acc.s[1].ptr : nullptr,
                    A.acc.s[1].valid);
   if (has_b)
-    bn_bwd_coef<V>(A.gamma_b, A.mean_b, A.invstd_b, A.sums_b, A.C, c0, A.inv_count, ba, bb, bk, A.stripes,
+    bn_bwd_coef<V>(A.gamma_b, A.mean_b, A.invstd_b, A.sums_b, A.C, c0, A.inv_count, ba, bb, bk, stripes,
                    A.stripe_stride, owner ? A.acc.s[2].ptr : nullptr, A.acc.s[2].valid, owner ? A.acc.s[3].ptr : nullptr,
                    A.acc.s[3].valid);
   const int step = gridDim.x * A.geom.rows;
@@ -619,7 +628,10 @@ static int node_bwd_apply_t(const npp_view4* g, const npp_view4* a, const float*
   A.C = g->c;
   A.geom = vec_geom(g->c, V);
   dim3 grid((unsigned)stream_grid(npix, A.geom, 4, 8), (unsigned)A.geom.gy);
-  node_bwd_apply_kernel<T, 4><<<grid, 256, 0, st>>>(A);
+  if (A.stripes > 1 || acc)
+    node_bwd_apply_kernel<T, 4, true><<<grid, 256, 0, st>>>(A);
+  else
+    node_bwd_apply_kernel<T, 4, false><<<grid, 256, 0, st>>>(A);
   NPP_CHECK_LAUNCH("node_bwd_apply_kernel");
   return NPP_OK;
 }

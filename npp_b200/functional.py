@@ -15,9 +15,11 @@ from . import _lib as L
 from ._lib import call, view, stream, fptr, i32, i64, f32, f64, ref, NULL
 
 _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
-          # kernel-selection switches (A/B timing, bisecting): NPP_NODE_STRIPED=0 -> partials + fold kernel for the
-          # BatchNorm backward sums of a node; NPP_NODE_FUSED_FINALIZE=0 -> separate npp_bn_finalize launches
-          "node_striped": os.environ.get("NPP_NODE_STRIPED", "1") != "0",
+          # kernel-selection switches (A/B timing, bisecting): NPP_NODE_STRIPED=1 -> striped-atomic totals instead of
+          # partials + fold kernel for the BatchNorm backward sums of a node (measured on B200: 111.8 ms/step with 2
+          # stripes, 110.1 with partials + fold — the apply kernel pays for folding the stripes — so OFF by default);
+          # NPP_NODE_FUSED_FINALIZE=0 -> separate npp_bn_finalize launches
+          "node_striped": os.environ.get("NPP_NODE_STRIPED", "0") != "0",
           "node_fused_finalize": os.environ.get("NPP_NODE_FUSED_FINALIZE", "1") != "0",
           # NPP_STEM_IM2COL=0 -> the 3-channel stems run through the generic 3x3 implicit-GEMM kernel
           "stem_im2col": os.environ.get("NPP_STEM_IM2COL", "1") != "0",
@@ -755,9 +757,10 @@ class _NodeFn(Function):
             # addresses), so the deterministic path stays; the switch is kept for experiments
             atomic = (need_bn and _arena.active and _state.get("node_reduce_atomics", False)
                       and g_raw2 is None and g_relu2 is None)
-            # striped path (default on one GPU): reduce blocks add into 8 striped copies of the totals, the apply
+            # striped path (NPP_NODE_STRIPED=1): reduce blocks add into striped copies of the totals, the apply
             # kernel folds them and writes d beta / d gamma into the flat gradient buffer — no partials buffer, no
-            # fold kernel (326 launches per step).  SyncBN needs the totals between the two kernels: old path.
+            # fold kernel (326 launches per step), but measured slower end to end (see _state); SyncBN needs the
+            # totals between the two kernels and always takes the partials path.
             striped = (need_bn and not sync and not (eval_a or eval_b) and not atomic
                        and _state.get("node_striped", True))
             if need_bn and not atomic and not striped:

@@ -59,11 +59,10 @@ def test_derived_network_call_flow(recorder):
     fwd = recorder.get("npp_node_fwd", 0) + recorder.get("npp_node_fwd_bn", 0)
     bwd = recorder.get("npp_node_bwd_apply", 0) + recorder.get("npp_node_bwd_apply_striped", 0)
     assert fwd > 100 and bwd > 100
-    assert recorder.get("npp_node_fwd_bn", 0) > 100 and recorder.get("npp_node_bwd_apply_striped", 0) > 100
-    # every BatchNorm-carrying node backward = one reduce2 (striped totals) + one apply; reduce2 also serves the
-    # nodes without BatchNorm that only have to add the concat-slice gradient to the in-cell one
-    assert recorder.get("npp_node_bwd_reduce2", 0) >= recorder.get("npp_node_bwd_apply_striped", 0)
-    assert recorder.get("npp_reduce_partials_acc", 0) == 0
+    assert recorder.get("npp_node_fwd_bn", 0) > 100
+    # concat members hand the gradient that comes down through the cell output to the node as a second input
+    assert recorder.get("npp_node_bwd_reduce2", 0) > 20
+    assert recorder.get("npp_node_bwd_reduce", 0) + recorder.get("npp_node_bwd_reduce2", 0) >= bwd
     # parameters never used by the forward get no gradient (SE_Block.bn at stride 1: SURVEY.md §5, find_unused_parameters)
     unused = [k for k, p in net.named_parameters() if p.grad is None]
     assert unused and all(".bn." in k for k in unused)
