@@ -356,7 +356,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak if tf_peak else None, "traffic": traffic,
-                         "kernel": "conv_gemm_kernel<BN> (tcgen05 implicit GEMM: fprop + dgrad, %d launches/step)" % gemm["calls"],
+                         "kernel": "conv_gemm2_kernel<BN> + conv3_kernel<BN> (tcgen05 implicit GEMM: fprop + dgrad, "
+                                   "%d launches/step)" % gemm["calls"],
                          "how": "algorithmic FLOPs (2*N*Ho*Wo*Cout*Cin*kh*kw) of every dense-conv fprop and dgrad launch of "
                                 "one step / CUDA-event time of those launches replayed back to back on the launch stream",
                          "avg_launch_us": 1e3 * gemm["ms"] / max(1, gemm["calls"]), "peak_source": peak_src,
