@@ -316,6 +316,18 @@ int npp_tta_merge(const float* pred, const float* flip_pred, int n, int c, int h
                   int ow, int swap_lr, float* out, npp_stream_t stream);
 int npp_heatmap_argmax(const float* hm_nchw, int nj, int h, int w, int32_t* idx, float* maxval,
                        npp_stream_t stream);
+/* LIP pose post-process of validate_sync (core/function.py:962-986), NCHW fp32:
+ *   pose_merge: out[n,j] = 0.5*(cv2.resize(pred[n,j], (ow,oh), INTER_LINEAR) +
+ *               cv2.flip(cv2.resize(flip_pred[n, flip_idx[j]], (ow,oh), INTER_LINEAR), 1))      (:973-979);
+ *               flip_idx: HOST array of nj (<= 32) joint indices (flipped_poseidx, :908).
+ *   gaussian_filter: scipy.ndimage.gaussian_filter(x, sigma) per [h,w] plane (:980): separable, rows then columns,
+ *               radius int(truncate*sigma+0.5), mode 'reflect', fp64 accumulation, each pass rounded to fp32; tmp is a
+ *               caller-provided scratch of the same size; dst may alias src.
+ *   The peak (:981-986) is npp_heatmap_argmax on the filtered maps. */
+int npp_pose_merge(const float* pred, const float* flip_pred, int n, int nj, int h, int w,
+                   const int* flip_idx, int oh, int ow, float* out, npp_stream_t stream);
+int npp_gaussian_filter(const float* src, float* tmp, float* dst, int planes, int h, int w, double sigma,
+                        double truncate, npp_stream_t stream);
 int npp_pck_counts(const int32_t* pred_idx, const float* pred_max, const int32_t* gt_idx,
                    const float* gt_max, int n, int j, int h, int w, float thr, int64_t* hit,
                    int64_t* valid, npp_stream_t stream);

@@ -7,6 +7,7 @@
 // Counts are int64; every floating-point comparison that decides a count is done in fp64 with the
 // same operation order as numpy (no FMA contraction) so the counters match the reference exactly.
 #include "common.cuh"
+#include <math.h>
 #include "resample.cuh"
 
 namespace npp {
@@ -63,6 +64,79 @@ tta_merge_kernel(const float* __restrict__ pred, const float* __restrict__ flip,
     const float* b = flip + ((int64_t)n * C + cf) * H * W;
     const float vb = lh0 * (lw0 * b[h0 * W + w0] + lw1 * b[h0 * W + w1]) + lh1 * (lw0 * b[h1 * W + w0] + lw1 * b[h1 * W + w1]);
     out[i] = 0.5f * (va + vb);
+  }
+}
+
+// ---- LIP pose post-process of validate_sync (core/function.py:962-986) --------------------------
+//   merged[n, j] = 0.5 * (cv2.resize(pred[n, j]) + cv2.flip(cv2.resize(flip[n, flipped_poseidx[j]]), 1))
+// cv2.resize(INTER_LINEAR) on float32: half-pixel centres, source index clamped into the image with weight 0 at the
+// borders, horizontal pass then vertical pass, every product and sum rounded to float32 (no FMA contraction — the
+// arg-max that follows decides integer pixel coordinates).  Restated and pinned in oracle/pose_post_ref.py.
+__device__ __forceinline__ void cv2_linear_tap(int d, double scale, int src, int& i0, int& i1, float& w1) {
+  double f = ((double)d + 0.5) * scale - 0.5;
+  int s = (int)floor(f);
+  f -= (double)s;
+  if (s < 0) { s = 0; f = 0.0; }
+  if (s >= src - 1) { s = src - 1; f = 0.0; }
+  i0 = s;
+  i1 = s + 1 < src ? s + 1 : src - 1;
+  w1 = (float)f;
+}
+__device__ __forceinline__ float cv2_bilinear(const float* __restrict__ img, int W, int y0, int y1, float ay, int x0,
+                                              int x1, float ax) {
+  const float bx = __fsub_rn(1.0f, ax), by = __fsub_rn(1.0f, ay);
+  const float r0 = __fadd_rn(__fmul_rn(img[y0 * W + x0], bx), __fmul_rn(img[y0 * W + x1], ax));
+  const float r1 = __fadd_rn(__fmul_rn(img[y1 * W + x0], bx), __fmul_rn(img[y1 * W + x1], ax));
+  return __fadd_rn(__fmul_rn(r0, by), __fmul_rn(r1, ay));
+}
+
+struct FlipIdx { int idx[32]; };
+
+__global__ void __launch_bounds__(256)
+pose_merge_kernel(const float* __restrict__ pred, const float* __restrict__ flip, int N, int J, int H, int W, int OH,
+                  int OW, FlipIdx fi, float* __restrict__ out) {
+  const double sy = (double)H / (double)OH, sx = (double)W / (double)OW;
+  const int64_t total = (int64_t)N * J * OH * OW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % OW);
+    const int y = (int)((i / OW) % OH);
+    const int j = (int)((i / ((int64_t)OW * OH)) % J);
+    const int n = (int)(i / ((int64_t)OW * OH * J));
+    int y0, y1, x0, x1;
+    float ay, ax;
+    cv2_linear_tap(y, sy, H, y0, y1, ay);
+    cv2_linear_tap(x, sx, W, x0, x1, ax);
+    const float va = cv2_bilinear(pred + ((int64_t)n * J + j) * H * W, W, y0, y1, ay, x0, x1, ax);
+    cv2_linear_tap(OW - 1 - x, sx, W, x0, x1, ax);   // cv2.flip(.., 1) of the resized flipped map
+    const float vb = cv2_bilinear(flip + ((int64_t)n * J + fi.idx[j]) * H * W, W, y0, y1, ay, x0, x1, ax);
+    out[i] = __fmul_rn(__fadd_rn(va, vb), 0.5f);
+  }
+}
+
+// scipy.ndimage.gaussian_filter: one separable pass along `axis` (0 = rows, 1 = columns) of [planes, H, W] float32
+// maps, mode 'reflect' (d c b a | a b c d | d c b a), float64 accumulation in tap order, result rounded to float32.
+struct GaussTaps { double k[64]; int radius; };
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - i - 1;
+  return i;
+}
+
+__global__ void __launch_bounds__(256)
+gauss1d_reflect_kernel(const float* __restrict__ src, float* __restrict__ dst, int planes, int H, int W, int axis,
+                       GaussTaps g) {
+  const int64_t total = (int64_t)planes * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const float* p = src + (i / ((int64_t)W * H)) * (int64_t)W * H;
+    double acc = 0.0;
+    for (int t = 0; t <= 2 * g.radius; ++t) {
+      const int o = t - g.radius;
+      const float v = axis == 0 ? p[reflect_index(y + o, H) * W + x] : p[y * W + reflect_index(x + o, W)];
+      acc = __dadd_rn(acc, __dmul_rn(g.k[t], (double)v));
+    }
+    dst[i] = (float)acc;
   }
 }
 
@@ -164,6 +238,48 @@ int npp_tta_merge(const float* pred, const float* flip_pred, int n, int c, int h
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
   tta_merge_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, n, c, h, w, oh, ow, ah, aw, swap_lr, out);
   NPP_CHECK_LAUNCH("tta_merge_kernel");
+  return NPP_OK;
+}
+
+int npp_pose_merge(const float* pred, const float* flip_pred, int n, int nj, int h, int w, const int* flip_idx, int oh,
+                   int ow, float* out, npp_stream_t s) {
+  if (!pred || !flip_pred || !out || !flip_idx || n <= 0 || nj <= 0 || nj > 32 || h <= 0 || w <= 0 || oh <= 0 || ow <= 0)
+    return NPP_E_INVALID;
+  FlipIdx fi;
+  for (int j = 0; j < 32; ++j) fi.idx[j] = 0;
+  for (int j = 0; j < nj; ++j) {
+    if (flip_idx[j] < 0 || flip_idx[j] >= nj) return NPP_E_INVALID;
+    fi.idx[j] = flip_idx[j];
+  }
+  const int64_t total = (int64_t)n * nj * oh * ow;
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  pose_merge_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, n, nj, h, w, oh, ow, fi, out);
+  NPP_CHECK_LAUNCH("pose_merge_kernel");
+  return NPP_OK;
+}
+
+int npp_gaussian_filter(const float* src, float* tmp, float* dst, int planes, int h, int w, double sigma,
+                        double truncate, npp_stream_t s) {
+  if (!src || !tmp || !dst || planes <= 0 || h <= 0 || w <= 0 || !(sigma > 0.0) || !(truncate > 0.0)) return NPP_E_INVALID;
+  GaussTaps g;
+  g.radius = (int)(truncate * sigma + 0.5);   // scipy: int(truncate * sd + 0.5)
+  if (g.radius < 0 || 2 * g.radius + 1 > 64) return NPP_E_UNSUPPORTED;
+  double sum = 0.0;
+  for (int t = 0; t <= 2 * g.radius; ++t) {
+    const double x = (double)(t - g.radius);
+    g.k[t] = exp(-0.5 / (sigma * sigma) * x * x);
+    sum += g.k[t];
+  }
+  for (int t = 0; t <= 2 * g.radius; ++t) g.k[t] /= sum;
+  for (int t = 2 * g.radius + 1; t < 64; ++t) g.k[t] = 0.0;
+  const int64_t total = (int64_t)planes * h * w;
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  gauss1d_reflect_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(src, tmp, planes, h, w, 0, g);
+  NPP_CHECK_LAUNCH("gauss1d_reflect_kernel(axis 0)");
+  gauss1d_reflect_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(tmp, dst, planes, h, w, 1, g);
+  NPP_CHECK_LAUNCH("gauss1d_reflect_kernel(axis 1)");
   return NPP_OK;
 }
 
