@@ -146,3 +146,4 @@ def test_direct_gradient_slots_match_autograd_accumulation(lib_built):
         assert flat.abs().sum() > 0
     finally:
         F_.set_compute_dtype(torch.bfloat16)
+
