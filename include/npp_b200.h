@@ -242,6 +242,10 @@ int npp_bilinear_fwd(const npp_view4* x, const npp_view4* y, int align_corners, 
                      double scale_w, int dtype, npp_stream_t stream);
 int npp_bilinear_bwd(const npp_view4* dy, const npp_view4* dx, int align_corners, double scale_h,
                      double scale_w, int dtype, npp_stream_t stream);
+/* Separable bilinear backward (same result as npp_bilinear_bwd up to fp32 summation order): column pass into the
+ * caller's fp32 scratch tmp[n * dy->h * dx->w * c] (16-byte aligned), then row pass.  Reads dY once. */
+int npp_bilinear_bwd_sep(const npp_view4* dy, const npp_view4* dx, float* tmp, int align_corners,
+                         double scale_h, double scale_w, int dtype, npp_stream_t stream);
 int npp_nearest_fwd(const npp_view4* x, const npp_view4* y, double scale_h, double scale_w,
                     int dtype, npp_stream_t stream);
 int npp_nearest_bwd(const npp_view4* dy, const npp_view4* dx, double scale_h, double scale_w,

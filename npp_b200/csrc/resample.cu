@@ -72,6 +72,67 @@ static int bilinear_bwd_t(const npp_view4* dy, const npp_view4* dx, Axis ah, Axi
   });
 }
 
+// Separable form of the bilinear backward (candidate for round 2, selected by functional._state["bilinear_sep"];
+// not the default: written after the round-1 GPU budget was spent, see tests/test_gpu_zz_bilinear_sep.py).
+// The gather kernel above re-reads every dY element through L1/L2 once per input pixel it touches in BOTH axes
+// (~(2s+1)^2 candidates at scale s, 4 real contributions) and evaluates the taps of every candidate pair.  Bilinear
+// weights factor as wh(ho,h) * ww(wo,w), so
+//     T[n, ho, w, c]  = sum_wo ww(wo, w) * dy[n, ho, wo, c]        (pass 1, fp32 scratch of N*Ho*Wi*C floats)
+//     dx[n, h, w, c]  = sum_ho wh(ho, h) * T[n, ho, w, c]          (pass 2)
+// reads dY once, touches 2s+1 candidates per axis instead of (2s+1)^2, and keeps the same tap arithmetic
+// (bilinear_taps / bilinear_range); only the summation order differs from the gather form (fp32 rounding).
+template <typename T>
+static int bilinear_bwd_sep_t(const npp_view4* dy, const npp_view4* dx, float* tmp, Axis ah, Axis aw, cudaStream_t st) {
+  constexpr int V = Pack<T>::N;
+  const auto DY = dview<const T>(dy);
+  const auto DX = dview<T>(dx);
+  const int Ho = dy->h, Wi = dx->w, C = dx->c;
+  int rc = foreach_vec<V>(dy->n, Ho, Wi, C, st, "bilinear_bwd_sep(w)", [=] __device__(int n, int ho, int w, int c) {
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+    int wlo, whi;
+    bilinear_range(aw, w, wlo, whi);
+    for (int wo = wlo; wo <= whi; ++wo) {
+      int w0, w1;
+      float lw0, lw1;
+      bilinear_taps(aw, wo, w0, w1, lw0, lw1);
+      const float ww = (w0 == w ? lw0 : 0.f) + (w1 == w ? lw1 : 0.f);
+      if (ww == 0.f) continue;
+      float d[V];
+      Pack<T>::load(DY.at(n, ho, wo, c), d);
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] = fmaf(ww, d[i], g[i]);
+    }
+    float* tp = tmp + (((int64_t)n * Ho + ho) * Wi + w) * C + c;
+#pragma unroll
+    for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]);
+  });
+  if (rc) return rc;
+  return foreach_vec<V>(dx->n, dx->h, Wi, C, st, "bilinear_bwd_sep(h)", [=] __device__(int n, int h, int w, int c) {
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+    int hlo, hhi;
+    bilinear_range(ah, h, hlo, hhi);
+    for (int ho = hlo; ho <= hhi; ++ho) {
+      int h0, h1;
+      float lh0, lh1;
+      bilinear_taps(ah, ho, h0, h1, lh0, lh1);
+      const float wh = (h0 == h ? lh0 : 0.f) + (h1 == h ? lh1 : 0.f);
+      if (wh == 0.f) continue;
+      const float* tp = tmp + (((int64_t)n * Ho + ho) * Wi + w) * C + c;
+#pragma unroll
+      for (int i = 0; i < V; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(tp + i);
+        g[i] = fmaf(wh, t.x, g[i]); g[i + 1] = fmaf(wh, t.y, g[i + 1]);
+        g[i + 2] = fmaf(wh, t.z, g[i + 2]); g[i + 3] = fmaf(wh, t.w, g[i + 3]);
+      }
+    }
+    Pack<T>::store(DX.at(n, h, w, c), g);
+  });
+}
+
 // nearest: src = min(floor(dst * scale), in-1), scale = 1/scale_factor (ATen nearest_neighbor_compute_source_index)
 __device__ __forceinline__ int nearest_src(const Axis& a, int o) {
   int s = (int)floorf((float)o * a.scale);
@@ -138,6 +199,14 @@ int npp_bilinear_bwd(const npp_view4* dy, const npp_view4* dx, int align_corners
   if (!view_ok(dx, dtype) || !view_ok(dy, dtype) || dx->n != dy->n || dx->c != dy->c) return NPP_E_INVALID;
   const Axis ah = make_axis(dx->h, dy->h, align_corners, scale_h), aw = make_axis(dx->w, dy->w, align_corners, scale_w);
   NPP_DISPATCH_DTYPE(dtype, return bilinear_bwd_t<T>(dy, dx, ah, aw, as_stream(s)););
+}
+int npp_bilinear_bwd_sep(const npp_view4* dy, const npp_view4* dx, float* tmp, int align_corners, double scale_h,
+                         double scale_w, int dtype, npp_stream_t s) {
+  if (!view_ok(dx, dtype) || !view_ok(dy, dtype) || dx->n != dy->n || dx->c != dy->c || !tmp ||
+      (reinterpret_cast<uintptr_t>(tmp) & 15))
+    return NPP_E_INVALID;
+  const Axis ah = make_axis(dx->h, dy->h, align_corners, scale_h), aw = make_axis(dx->w, dy->w, align_corners, scale_w);
+  NPP_DISPATCH_DTYPE(dtype, return bilinear_bwd_sep_t<T>(dy, dx, tmp, ah, aw, as_stream(s)););
 }
 int npp_nearest_fwd(const npp_view4* x, const npp_view4* y, double scale_h, double scale_w, int dtype, npp_stream_t s) {
   if (!view_ok(x, dtype) || !view_ok(y, dtype) || x->n != y->n || x->c != y->c) return NPP_E_INVALID;

@@ -24,7 +24,9 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # NPP_STEM_IM2COL=0 -> the 3-channel stems run through the generic 3x3 implicit-GEMM kernel
           "stem_im2col": os.environ.get("NPP_STEM_IM2COL", "1") != "0",
           # NPP_NODE_CAT_GRADS=0 -> the concat-slice gradient of a cell state is added by autograd (strided at::add)
-          "node_cat_grads": os.environ.get("NPP_NODE_CAT_GRADS", "1") != "0"}
+          "node_cat_grads": os.environ.get("NPP_NODE_CAT_GRADS", "1") != "0",
+          # NPP_BILINEAR_SEP=1 -> separable two-pass bilinear backward (round-2 candidate, not yet run on hardware)
+          "bilinear_sep": os.environ.get("NPP_BILINEAR_SEP", "0") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -1184,7 +1186,12 @@ class _ResampleFn(Function):
         n, c, h, w = shape
         dx = empty_internal(n, c, h, w, dy.dtype, dy.device)
         code = L.dtype_code(dy)
-        if mode == "bilinear":
+        if mode == "bilinear" and _state.get("bilinear_sep", False):
+            # separable two-pass form (round-2 candidate, off by default: see csrc/resample.cu)
+            tmp = torch.empty(n * dy.shape[2] * w * c, dtype=torch.float32, device=dy.device)
+            call("npp_bilinear_bwd_sep", ref(view(dy)), ref(view(dx)), fptr(tmp), i32(align), f64(sh), f64(sw), i32(code),
+                 stream())
+        elif mode == "bilinear":
             call("npp_bilinear_bwd", ref(view(dy)), ref(view(dx)), i32(align), f64(sh), f64(sw), i32(code), stream())
         else:
             call("npp_nearest_bwd", ref(view(dy)), ref(view(dx)), f64(sh), f64(sw), i32(code), stream())
