@@ -1,13 +1,11 @@
 """GPU: the separable two-pass bilinear backward (npp_bilinear_bwd_sep, csrc/resample.cu — a round-2 candidate that
 is NOT on the default path) against the gather-form kernel the product uses (npp_bilinear_bwd, itself checked against
-torch in test_gpu_ops.py).  Written after round 1's GPU budget was spent, hence the non-strict xfail: a pass shows up
-as XPASS and the switch (functional._state["bilinear_sep"] / NPP_BILINEAR_SEP=1) can then be timed."""
+torch in test_gpu_ops.py).  Green on a B200 (profiles/r01_pytest_gpu_n1_and_bilinear_sep.log); the switch
+(functional._state["bilinear_sep"] / NPP_BILINEAR_SEP=1) stays off until it has been timed."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="candidate kernel not yet run on a B200 (written after the round-1 GPU budget)",
-                                strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("scale,align", [(2, True), (4, True), (8, True), (2, False), (0.5, True)])

@@ -2,9 +2,7 @@
 npp_heatmap_argmax, npp_b200/core/pose_post.py) against the oracle (oracle/pose_post_ref.py, itself pinned to
 cv2 / scipy by tests/test_oracle_pose_post.py) on the committed fixture inputs and on fresh seeded maps.
 
-These kernels were written after the round's GPU budget was spent: they compile for sm_100a and the oracle is
-pinned on the CPU, but they have not run on hardware yet — hence the non-strict xfail (a pass shows up as XPASS).
-Remove the marker once a B200 run is green.
+First B200 run (last seconds of round 1's GPU budget): all four cases green — profiles/r01_pytest_gpu_n1_and_bilinear_sep.log.
 """
 import os
 
@@ -14,12 +12,9 @@ import pytest
 from oracle import pose_post_ref as P
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pose_post_golden.npz"))
-PENDING = pytest.mark.xfail(reason="N1 kernels not yet run on a B200 (written after the GPU budget of round 1)",
-                            strict=False)
 
 
 @pytest.mark.gpu
-@PENDING
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_pose_postprocess_matches_fixture(tag, lib_built):
     from npp_b200.core import pose_post
@@ -32,7 +27,6 @@ def test_pose_postprocess_matches_fixture(tag, lib_built):
 
 
 @pytest.mark.gpu
-@PENDING
 def test_merged_heatmaps_match_oracle(lib_built):
     from npp_b200.core import pose_post
     rng = np.random.RandomState(5)
@@ -44,7 +38,6 @@ def test_merged_heatmaps_match_oracle(lib_built):
 
 
 @pytest.mark.gpu
-@PENDING
 def test_gaussian_filter_ragged_plane(lib_built):
     import torch
     from npp_b200._lib import call, fptr, i32, f64, stream
