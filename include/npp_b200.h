@@ -106,6 +106,14 @@ int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int
 int npp_pack_weights_multi(const void* table, int ntensors, const int32_t* chunk_tensor,
                            const int32_t* chunk_index, int nchunks, int chunk_elems, npp_stream_t stream);
 
+/* Pixel-pair layout for 3x3 / stride-1 / pad-1 convolutions with 32 input and 32 output channels (the C = 32 cells
+ * of the first encoder stage, models/model_augment.py:274-295): [N,H,W,32] read as [N,H,W/2,64] turns the layer into a
+ * 64 -> 64 convolution on half as many (full 128-byte) rows.  pack_weight_pair: fp32 OIHW [32,32,3,3] -> bf16
+ * [64,9,64] (+ transposed for dgrad); in npp_pack_weights_multi a table row with pad == 1 selects the same mapping.
+ * fold_pair_wgrad: dw[32,32,3,3] += the [64,64,3,3] gradient of the paired convolution folded back. */
+int npp_pack_weight_pair(const float* w32, void* w, void* wt, npp_stream_t stream);
+int npp_fold_pair_wgrad(const float* dw_pair, float* dw, npp_stream_t stream);
+
 /* Validation-mode / cross-check convolution on CUDA cores (fp32 accumulate, dtype-templated).
  * Same arithmetic as the three functions above, any dtype, groups==1. w/dw are fp32 OHWI
  * when dtype==NPP_F32 and bf16 (w) / fp32 (dw) when dtype==NPP_BF16. */

@@ -1829,10 +1829,34 @@ struct PackTensor {
 };
 static_assert(sizeof(PackTensor) == 48, "table layout is part of the ABI (npp_b200/engine.py mirrors it)");
 
+// Pixel-pair layout (PackTensor.pad_ == 1; round-2 candidate, see functional._ConvPairFn): a 3x3 / stride-1 / pad-1
+// convolution with 32 input and 32 output channels on an NHWC tensor [N, H, W, 32] is the same arithmetic as a
+// 3x3 convolution with 64 -> 64 channels on the SAME memory read as [N, H, W/2, 64] (two neighbouring pixels = one
+// "super-pixel"): output (po, co) of super-pixel j reads input (pi, ci) of super-pixel j + ds through the original
+// horizontal tap s = 2*ds + pi - po + 1 when 0 <= s <= 2 (zero otherwise); vertical taps are unchanged.  Rows
+// of the packed matrix = po*32 + co, columns = pi*32 + ci, horizontal tap index = ds + 1.
+__device__ __forceinline__ float pair_weight(const float* __restrict__ w32, int row, int tap, int col) {
+  const int po = row >> 5, co = row & 31, pi = col >> 5, ci = col & 31;
+  const int r = tap / 3, s = 2 * (tap % 3 - 1) + pi - po + 1;
+  return (s >= 0 && s <= 2) ? w32[(co * 32 + ci) * 9 + r * 3 + s] : 0.f;
+}
+
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const PackTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
                           const int* __restrict__ chunk_index, int chunk_elems) {
   const PackTensor t = tensors[chunk_tensor[blockIdx.x]];
+  if (t.pad_ == 1) {
+    const int total = 64 * 9 * 64;
+    const int begin = chunk_index[blockIdx.x] * chunk_elems;
+    const int end = begin + chunk_elems < total ? begin + chunk_elems : total;
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+      const int col = i & 63, tap = (i >> 6) % 9, row = i / (64 * 9);
+      const __nv_bfloat16 h = __float2bfloat16_rn(pair_weight(t.w32, row, tap, col));
+      if (t.w) t.w[i] = h;
+      if (t.wt) t.wt[(col * 9 + tap) * 64 + row] = h;
+    }
+    return;
+  }
   const int64_t total = (int64_t)t.cout_pad * t.taps * t.cin_pad;
   const int64_t begin = (int64_t)chunk_index[blockIdx.x] * chunk_elems;
   int64_t end = begin + chunk_elems;
@@ -1855,6 +1879,53 @@ int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor,
   pack_weights_multi_kernel<<<nchunks, 256, 0, st>>>(static_cast<const PackTensor*>(table), chunk_tensor, chunk_index,
                                                      chunk_elems);
   NPP_CHECK_LAUNCH("pack_weights_multi_kernel");
+  return NPP_OK;
+}
+
+// dW[co, ci, r, s] += sum over the pair-layout entries that carry that tap (inverse of pair_weight): the weight
+// gradient of the 64 -> 64 super-pixel convolution folded back onto the 32 x 32 x 3 x 3 master gradient.
+__global__ void __launch_bounds__(256) fold_pair_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (co, ci, r, s)
+  if (i >= 32 * 32 * 9) return;
+  const int s = i % 3, r = (i / 3) % 3, ci = (i / 9) & 31, co = i / (9 * 32);
+  float acc = 0.f;
+#pragma unroll
+  for (int po = 0; po < 2; ++po)
+#pragma unroll
+    for (int pi = 0; pi < 2; ++pi) {
+      const int t2 = s - 1 - pi + po;       // 2 * ds
+      if (t2 & 1) continue;
+      const int ds = t2 / 2;                // exact: t2 even (also for negatives)
+      if (ds < -1 || ds > 1) continue;
+      // dwp is torch OIHW of the paired conv: [64 rows][64 cols][3][3]
+      acc += dwp[((po * 32 + co) * 64 + (pi * 32 + ci)) * 9 + r * 3 + (ds + 1)];
+    }
+  dw[i] += acc;
+}
+
+int fold_pair_wgrad(const float* dwp, float* dw, cudaStream_t st) {
+  if (!dwp || !dw) return NPP_E_INVALID;
+  fold_pair_wgrad_kernel<<<(32 * 32 * 9 + 255) / 256, 256, 0, st>>>(dwp, dw);
+  NPP_CHECK_LAUNCH("fold_pair_wgrad_kernel");
+  return NPP_OK;
+}
+
+// one-off packing of a single pair-layout weight (tests; the per-step path is pack_weights_multi with pad_ = 1)
+__global__ void __launch_bounds__(256) pack_pair_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ w,
+                                                        __nv_bfloat16* __restrict__ wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 9 * 64) return;
+  const int col = i & 63, tap = (i >> 6) % 9, row = i / (64 * 9);
+  const __nv_bfloat16 h = __float2bfloat16_rn(pair_weight(w32, row, tap, col));
+  if (w) w[i] = h;
+  if (wt) wt[(col * 9 + tap) * 64 + row] = h;
+}
+
+int pack_weight_pair(const float* w32, void* w, void* wt, cudaStream_t st) {
+  if (!w32 || (!w && !wt)) return NPP_E_INVALID;
+  pack_pair_kernel<<<(64 * 9 * 64 + 255) / 256, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w),
+                                                              static_cast<__nv_bfloat16*>(wt));
+  NPP_CHECK_LAUNCH("pack_pair_kernel");
   return NPP_OK;
 }
 

@@ -26,7 +26,9 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # NPP_NODE_CAT_GRADS=0 -> the concat-slice gradient of a cell state is added by autograd (strided at::add)
           "node_cat_grads": os.environ.get("NPP_NODE_CAT_GRADS", "1") != "0",
           # NPP_BILINEAR_SEP=1 -> separable two-pass bilinear backward (round-2 candidate, not yet run on hardware)
-          "bilinear_sep": os.environ.get("NPP_BILINEAR_SEP", "0") != "0"}
+          "bilinear_sep": os.environ.get("NPP_BILINEAR_SEP", "0") != "0",
+          # NPP_CONV_PAIR=1 -> 3x3 convolutions with 32 -> 32 channels run in pixel-pair form (round-2 candidate)
+          "conv_pair": os.environ.get("NPP_CONV_PAIR", "0") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -354,6 +356,77 @@ class _ConvFn(Function):
         return dx, dw, db, None, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# pixel-pair form of the C = 32 3x3 convolutions (round-2 candidate, NPP_CONV_PAIR=1; csrc/conv_tcgen05.cu pair_weight)
+# ------------------------------------------------------------------------------------------------
+def _pair_ok(t):
+    """dense NHWC [N, 32, H, W] with an even width: can be re-read as [N, 64, H, W/2]."""
+    if t.dim() != 4 or t.shape[1] != 32 or t.shape[3] % 2:
+        return False
+    n, c, h, w = t.shape
+    return tuple(t.stride()) == (h * w * c, 1, w * c, c)
+
+
+def _pair_alias(t):
+    n, c, h, w = t.shape
+    return torch.empty(0, dtype=t.dtype, device=t.device).set_(
+        t.untyped_storage(), t.storage_offset(), (n, 2 * c, h, w // 2), (h * w * c, 1, w * c, 2 * c))
+
+
+class _ConvPairFn(Function):
+    """3x3 / stride 1 / pad 1 convolution with 32 -> 32 channels computed as a 64 -> 64 convolution on the same
+    memory read as super-pixels of two neighbouring pixels: half as many (full 128-byte) TMA rows, K = N = 64 instead
+    of a half-empty 64-wide K block and N = 32.  The weight matrix, the BatchNorm sums and the weight gradient are
+    mapped between the two forms by npp_pack_weight_pair / a fold of the [2][2][32] sums / npp_fold_pair_wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, weight, want_stats, wslot, packed):
+        n, c, h, w = x.shape
+        if packed is not None:
+            wp, wt = packed
+        else:
+            wp = torch.empty(64 * 9 * 64, dtype=x.dtype, device=x.device)
+            wt = torch.empty_like(wp)
+            call("npp_pack_weight_pair", fptr(weight.detach().contiguous()), fptr(wp), fptr(wt), stream())
+        y = empty_internal(n, c, h, w, x.dtype, x.device)
+        xv, yv = _pair_alias(x), _pair_alias(y)
+        stats64 = zeros_f32(2 * 64, x.device) if want_stats else None
+        call("npp_conv2d_fwd", ref(view(xv)), fptr(wp), NULL, ref(view(yv)), i32(3), i32(3), i32(1), i32(1), i32(1), i32(0),
+             i32(0), fptr(stats64), stream(), work=_conv_work(n, h, w, 32, 32, 3, 3, x, y), keep=(x, wp, y, stats64))
+        ctx.wslot = wslot
+        ctx.work = _conv_work(n, h, w, 32, 32, 3, 3, x, y)
+        ctx.save_for_backward(x, wt)
+        if stats64 is not None:
+            stats = stats64.view(2, 2, 32).sum(1).reshape(64)   # (moment, pixel parity, channel) -> (moment, channel)
+        else:
+            stats = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x, wt = ctx.saved_tensors
+        dy = as_internal_grad(dy, x)
+        if not _pair_ok(dy):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        xv, dyv = _pair_alias(x), _pair_alias(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("npp_conv2d_dgrad", ref(view(dyv)), fptr(wt), ref(view(_pair_alias(dx))), i32(3), i32(3), i32(1), i32(1),
+                 i32(1), i32(0), i32(0), stream(), work=ctx.work, keep=(dy, wt, dx))
+        if ctx.needs_input_grad[1]:
+            dwp = zeros_f32(64 * 64 * 9, x.device)
+            ws = _wgrad_workspace(x.device)
+            call("npp_conv2d_wgrad_ws", ref(view(xv)), ref(view(dyv)), fptr(dwp), i32(64), i32(64), i32(3), i32(3), i32(1),
+                 i32(1), i32(1), i32(0), i32(0), fptr(ws), i64(ws.numel() * 4), stream(), work=ctx.work, keep=(x, dy, dwp))
+            dw = ctx.wslot if ctx.wslot is not None else torch.zeros((32, 32, 3, 3), dtype=torch.float32, device=x.device)
+            call("npp_fold_pair_wgrad", fptr(dwp), fptr(dw), stream(), keep=(dwp, dw))
+            if ctx.wslot is not None:
+                dw = None
+        return dx, dw, None, None, None
+
+
 def im2col3x3_c3(x, stride, pad):
     """[N, 3(+5 pad), H, W] internal bf16 image -> [N, 32, Ho, Wo] with channel ci*9 + r*3 + s = tap (r, s) of input
     channel ci (npp_im2col3x3_c3).  The result is cached on the image tensor: both task streams' stems
@@ -377,6 +450,10 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, hoff=0, woff=0, want_st
     wslot = grad_slot(weight) if slot_of is None else grad_slot(slot_of)
     if wslot is not None and slot_of is not None:
         wslot = wslot.view(weight.shape)
+    if (_state.get("conv_pair", False) and bias is None and tuple(weight.shape) == (32, 32, 3, 3) and stride == 1
+            and pad == 1 and dil == 1 and not hoff and not woff and x.dtype == torch.bfloat16 and _pair_ok(x)):
+        packed = getattr(weight, "_npp_packed_pair", None) if _state.get("packed_weights") else None
+        return _ConvPairFn.apply(x, weight, bool(want_stats), wslot, packed)
     slots = (wslot, grad_slot(bias))
     packed = getattr(weight, "_npp_packed", None) if _state.get("packed_weights") else None
     return _ConvFn.apply(x, weight, bias, int(stride), int(pad), int(dil), int(hoff), int(woff), bool(want_stats),
@@ -411,10 +488,24 @@ class WeightPacker:
             self.bufs.append((wp, wt))   # the device table holds raw pointers: keep the buffers alive
             rows.append(struct.pack("<QQQiiiiii", w.data_ptr(), wp.data_ptr(), wt.data_ptr(), cout, kh * kw, cin, cop, cip, 0))
             nch = (n + self.CHUNK - 1) // self.CHUNK
-            ct += [ti] * nch
+            ct += [len(rows) - 1] * nch
             ci += list(range(nch))
+            if _state.get("conv_pair", False) and (cout, cin, kh, kw) == (32, 32, 3, 3):
+                # pixel-pair layout of the same weight (table flag pad == 1), see _ConvPairFn
+                prev = getattr(w, "_npp_packed_pair", None)
+                if prev is not None and prev[0].device == w.device:
+                    pp, pt = prev
+                else:
+                    pp = torch.empty(64 * 9 * 64, dtype=torch.bfloat16, device=w.device)
+                    pt = torch.empty_like(pp)
+                    w._npp_packed_pair = (pp, pt)
+                self.bufs.append((pp, pt))
+                rows.append(struct.pack("<QQQiiiiii", w.data_ptr(), pp.data_ptr(), pt.data_ptr(), 32, 9, 32, 64, 64, 1))
+                nch = (64 * 9 * 64 + self.CHUNK - 1) // self.CHUNK
+                ct += [len(rows) - 1] * nch
+                ci += list(range(nch))
         dev = self.params[0].device if self.params else None
-        self.n = len(self.params)
+        self.n = len(rows)
         if self.n:
             self.table = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8).clone().to(dev)
             self.chunk_tensor = torch.tensor(ct, dtype=torch.int32).to(dev)
