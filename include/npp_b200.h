@@ -229,6 +229,11 @@ int npp_avgpool2x2_bwd(const npp_view4* dy, const npp_view4* dx, int dtype, npp_
 int npp_gap_fwd(const npp_view4* x, float* g, int dtype, npp_stream_t stream);
 int npp_se_fc_fwd(const float* g, const float* w1, const float* b1, const float* w2,
                   const float* b2, float* hbuf, float* s, int n, int c, npp_stream_t stream);
+/* se_fc_bwd in two kernels without weight-gradient atomics (same results up to fp32 summation order): per-image
+ * vectors first, then dW2 += dz2^T h and dW1 += dz1^T g with one thread per element.  scratch: n * (c + c/2) floats. */
+int npp_se_fc_bwd2(const float* g, const float* hbuf, const float* sg, const float* ds, const float* w1,
+                   const float* w2, float* dw1, float* db1, float* dw2, float* db2, float* dg,
+                   float* scratch, int n, int c, npp_stream_t stream);
 int npp_se_scale_fwd(const npp_view4* x, const float* s, const npp_view4* y, int dtype,
                      npp_stream_t stream);
 int npp_se_bwd_reduce(const npp_view4* x, const npp_view4* dy, float* ds, int dtype,

@@ -90,6 +90,67 @@ __global__ void __launch_bounds__(1024) se_fc_bwd_kernel(const float* __restrict
   }
 }
 
+// ---- two-kernel backward of the SE bottleneck (round-2 candidate, functional._state["se_bwd2"]) ------------------
+// se_fc_bwd_kernel above adds every image's outer products dz2 (x) h and dz1 (x) g into dW2 / dW1 with global
+// atomics: 2 * C * C/2 atomics per image on the same addresses from all N blocks (2 M for C = 256, N = 32), which is
+// what its 17 us per launch are spent on.  Here the per-image vectors are written once (kernel A, no weight
+// atomics) and the weight gradients are formed as [C x N] x [N x C/2] products by one thread per element (kernel B):
+// every dW element is written exactly once.
+__global__ void __launch_bounds__(1024) se_fc_bwd_vec_kernel(const float* __restrict__ hbuf, const float* __restrict__ s,
+                                                             const float* __restrict__ ds, const float* __restrict__ w1,
+                                                             const float* __restrict__ w2, float* __restrict__ db1,
+                                                             float* __restrict__ db2, float* __restrict__ dz2g,
+                                                             float* __restrict__ dz1g, float* __restrict__ dg, int C) {
+  extern __shared__ float sm[];
+  float* dz2 = sm;          // C
+  float* sh = sm + C;       // C/2
+  float* dz1 = sh + C / 2;  // C/2
+  const int n = blockIdx.x, Ch = C / 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float sv = s[(int64_t)n * C + c];
+    const float d = ds[(int64_t)n * C + c] * sv * (1.f - sv);
+    dz2[c] = d;
+    dz2g[(int64_t)n * C + c] = d;
+    if (db2) atomicAdd(db2 + c, d);
+  }
+  for (int j = threadIdx.x; j < Ch; j += blockDim.x) sh[j] = hbuf[(int64_t)n * Ch + j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < Ch; j += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w2[(int64_t)c * Ch + j], dz2[c], a);
+    a = sh[j] > 0.f ? a : 0.f;
+    dz1[j] = a;
+    dz1g[(int64_t)n * Ch + j] = a;
+    if (db1) atomicAdd(db1 + j, a);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < Ch; ++j) a = fmaf(w1[(int64_t)j * C + c], dz1[j], a);
+    dg[(int64_t)n * C + c] = a;
+  }
+}
+
+// dW2[c, j] += sum_n dz2[n, c] * h[n, j]   (elements [0, C*Ch));   dW1[j, i] += sum_n dz1[n, j] * g[n, i]   (the rest)
+__global__ void __launch_bounds__(256) se_fc_bwd_outer_kernel(const float* __restrict__ g, const float* __restrict__ hbuf,
+                                                              const float* __restrict__ dz2g,
+                                                              const float* __restrict__ dz1g, float* __restrict__ dw1,
+                                                              float* __restrict__ dw2, int N, int C) {
+  const int Ch = C / 2;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 2 * C * Ch) return;
+  float a = 0.f;
+  if (e < C * Ch) {
+    const int c = e / Ch, j = e % Ch;
+    for (int n = 0; n < N; ++n) a = fmaf(dz2g[(int64_t)n * C + c], hbuf[(int64_t)n * Ch + j], a);
+    dw2[e] += a;
+  } else {
+    const int k = e - C * Ch, j = k / C, i = k % C;
+    for (int n = 0; n < N; ++n) a = fmaf(dz1g[(int64_t)n * Ch + j], g[(int64_t)n * C + i], a);
+    dw1[k] += a;
+  }
+}
+
 template <typename T>
 static int se_scale_fwd_t(const npp_view4* x, const float* s, const npp_view4* y, cudaStream_t st) {
   constexpr int V = Pack<T>::N;
@@ -165,6 +226,22 @@ int npp_se_fc_bwd(const float* g, const float* hbuf, const float* sg, const floa
   if (smem > 48 * 1024) return NPP_E_UNSUPPORTED;
   se_fc_bwd_kernel<<<n, 1024, smem, as_stream(s)>>>(g, hbuf, sg, ds, w1, w2, dw1, db1, dw2, db2, dg, c);
   NPP_CHECK_LAUNCH("se_fc_bwd_kernel");
+  return NPP_OK;
+}
+int npp_se_fc_bwd2(const float* g, const float* hbuf, const float* sg, const float* ds, const float* w1, const float* w2,
+                   float* dw1, float* db1, float* dw2, float* db2, float* dg, float* scratch, int n, int c,
+                   npp_stream_t s) {
+  if (!g || !hbuf || !sg || !ds || !w1 || !w2 || !dw1 || !dw2 || !dg || !scratch || n <= 0 || c <= 1 || (c & 1))
+    return NPP_E_INVALID;
+  const size_t smem = (size_t)(2 * c) * sizeof(float);
+  if (smem > 48 * 1024) return NPP_E_UNSUPPORTED;
+  float* dz2g = scratch;                      // [n][c]
+  float* dz1g = scratch + (size_t)n * c;      // [n][c/2]
+  se_fc_bwd_vec_kernel<<<n, 1024, smem, as_stream(s)>>>(hbuf, sg, ds, w1, w2, db1, db2, dz2g, dz1g, dg, c);
+  NPP_CHECK_LAUNCH("se_fc_bwd_vec_kernel");
+  const int total = c * c;                    // 2 * c * c/2 weight-gradient elements
+  se_fc_bwd_outer_kernel<<<(total + 255) / 256, 256, 0, as_stream(s)>>>(g, hbuf, dz2g, dz1g, dw1, dw2, n, c);
+  NPP_CHECK_LAUNCH("se_fc_bwd_outer_kernel");
   return NPP_OK;
 }
 int npp_se_scale_fwd(const npp_view4* x, const float* sg, const npp_view4* y, int dtype, npp_stream_t s) {

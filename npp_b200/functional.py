@@ -28,7 +28,9 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # NPP_BILINEAR_SEP=1 -> separable two-pass bilinear backward (round-2 candidate, not yet run on hardware)
           "bilinear_sep": os.environ.get("NPP_BILINEAR_SEP", "0") != "0",
           # NPP_CONV_PAIR=1 -> 3x3 convolutions with 32 -> 32 channels run in pixel-pair form (round-2 candidate)
-          "conv_pair": os.environ.get("NPP_CONV_PAIR", "0") != "0"}
+          "conv_pair": os.environ.get("NPP_CONV_PAIR", "0") != "0",
+          # NPP_SE_BWD2=1 -> SE bottleneck backward in two kernels without weight-gradient atomics (round-2 candidate)
+          "se_bwd2": os.environ.get("NPP_SE_BWD2", "0") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -1239,8 +1241,13 @@ class _SEFn(Function):
             db1 = zeros_f32(c // 2, dev)
             db2 = zeros_f32(c, dev)
         dg = torch.empty((n, c), dtype=torch.float32, device=dev)
-        call("npp_se_fc_bwd", fptr(g), fptr(hbuf), fptr(s), fptr(ds), fptr(w1c), fptr(w2c), fptr(dw1), fptr(db1),
-             fptr(dw2), fptr(db2), fptr(dg), i32(n), i32(c), stream())
+        if _state.get("se_bwd2", False):   # round-2 candidate: no weight-gradient atomics (csrc/se.cu)
+            scratch = torch.empty(n * (c + c // 2), dtype=torch.float32, device=dev)
+            call("npp_se_fc_bwd2", fptr(g), fptr(hbuf), fptr(s), fptr(ds), fptr(w1c), fptr(w2c), fptr(dw1), fptr(db1),
+                 fptr(dw2), fptr(db2), fptr(dg), fptr(scratch), i32(n), i32(c), stream())
+        else:
+            call("npp_se_fc_bwd", fptr(g), fptr(hbuf), fptr(s), fptr(ds), fptr(w1c), fptr(w2c), fptr(dw1), fptr(db1),
+                 fptr(dw2), fptr(db2), fptr(dg), i32(n), i32(c), stream())
         dx = torch.empty_like(x)
         call("npp_se_bwd_apply", ref(view(dy)), fptr(s), fptr(dg), ref(view(dx)), i32(code), stream())
         if direct:
