@@ -31,5 +31,6 @@ def test_se_backward_variants_agree(c, lib_built):
             res.append([g.float() for g in torch.autograd.grad((y.float() * gy).sum(), [x] + params)])
     finally:
         F_._state["se_bwd2"] = False
-    for a, b in zip(*res):
-        assert (a - b).abs().max() <= 1e-3 * a.abs().max() + 1e-6
+    for k, (a, b) in enumerate(zip(*res)):
+        tol = 1e-2 if k == 0 else 1e-3     # dx is stored in bf16 (one ulp = 0.8 %), the parameter gradients in fp32
+        assert (a - b).abs().max() <= tol * a.abs().max() + 1e-6
