@@ -106,6 +106,11 @@ int npp_pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int
 int npp_pack_weights_multi(const void* table, int ntensors, const int32_t* chunk_tensor,
                            const int32_t* chunk_index, int nchunks, int chunk_elems, npp_stream_t stream);
 
+/* Same table, tile form: block b packs the 32 (Cout) x 32 (Cin) x taps tile tile_index[b] (row-major over
+ * ceil(cout_pad/32) x ceil(cin_pad/32)) of tensor tile_tensor[b]; taps <= 9; rows with pad != 0 are not supported. */
+int npp_pack_weights_tiles(const void* table, int ntensors, const int32_t* tile_tensor,
+                           const int32_t* tile_index, int ntiles, npp_stream_t stream);
+
 /* Pixel-pair layout for 3x3 / stride-1 / pad-1 convolutions with 32 input and 32 output channels (the C = 32 cells
  * of the first encoder stage, models/model_augment.py:274-295): [N,H,W,32] read as [N,H,W/2,64] turns the layer into a
  * 64 -> 64 convolution on half as many (full 128-byte) rows.  pack_weight_pair: fp32 OIHW [32,32,3,3] -> bf16

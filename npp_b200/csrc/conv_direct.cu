@@ -149,6 +149,8 @@ int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin
                 int out_dtype, cudaStream_t st);
 int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
                        int chunk_elems, cudaStream_t st);
+int pack_weights_tiles(const void* table, int ntensors, const int* tile_tensor, const int* tile_index, int ntiles,
+                       cudaStream_t st);
 int pack_weight_pair(const float* w32, void* w, void* wt, cudaStream_t st);
 int fold_pair_wgrad(const float* dwp, float* dw, cudaStream_t st);
 }  // namespace tc
@@ -189,6 +191,10 @@ int npp_conv2d_wgrad_ws(const npp_view4* x, const npp_view4* dy, float* dw, int 
 int npp_pack_weights_multi(const void* table, int ntensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
                            int nchunks, int chunk_elems, npp_stream_t stream) {
   return tc::pack_weights_multi(table, ntensors, chunk_tensor, chunk_index, nchunks, chunk_elems, as_stream(stream));
+}
+int npp_pack_weights_tiles(const void* table, int ntensors, const int32_t* tile_tensor, const int32_t* tile_index,
+                           int ntiles, npp_stream_t stream) {
+  return tc::pack_weights_tiles(table, ntensors, tile_tensor, tile_index, ntiles, as_stream(stream));
 }
 int npp_pack_weight_pair(const float* w32, void* w, void* wt, npp_stream_t stream) {
   return tc::pack_weight_pair(w32, w, wt, as_stream(stream));

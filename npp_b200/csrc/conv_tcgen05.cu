@@ -1872,6 +1872,56 @@ pack_weights_multi_kernel(const PackTensor* __restrict__ tensors, const int* __r
   }
 }
 
+// Tile form of the multi-tensor pack (round-2 candidate, functional._state["pack_tiles"]): the element-wise kernel
+// above reads the OIHW master with a stride of `taps` floats between threads and writes the transposed copy as
+// scattered 2-byte stores (0.79 ms per step for 77 M weights against ~0.1 ms of HBM time).  Here a block owns a
+// 32 (Cout) x 32 (Cin) x taps tile: the rows are contiguous runs of the master (coalesced fp32 loads into shared
+// memory), both packed layouts are then written as 64-byte runs; the row stride 32*taps + 1 keeps both shared-memory
+// read patterns conflict-free for odd tap counts (1, 9).
+constexpr int kPackTapsMax = 9;
+__global__ void __launch_bounds__(256)
+pack_weights_tiles_kernel(const PackTensor* __restrict__ tensors, const int* __restrict__ tile_tensor,
+                          const int* __restrict__ tile_index) {
+  __shared__ float tile[32 * (32 * kPackTapsMax + 1)];
+  const PackTensor t = tensors[tile_tensor[blockIdx.x]];
+  const int ci_tiles = (t.cin_pad + 31) / 32;
+  const int co0 = (tile_index[blockIdx.x] / ci_tiles) * 32, ci0 = (tile_index[blockIdx.x] % ci_tiles) * 32;
+  const int taps = t.taps, ld = 32 * taps + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int nci = t.cin - ci0;            // real input channels in this tile (<= 0: all padding)
+  if (nci > 32) nci = 32;
+  for (int r = warp; r < 32; r += 8) {
+    const int co = co0 + r;
+    const float* src = t.w32 + ((int64_t)co * t.cin + ci0) * taps;   // nci * taps contiguous floats
+    for (int k = lane; k < 32 * taps; k += 32)
+      tile[r * ld + k] = (co < t.cout && k < nci * taps) ? src[k] : 0.f;
+  }
+  __syncthreads();
+  // w[co][tap][ci]: one 32-channel run per (row, tap)
+  if (t.w)
+    for (int q = warp; q < 32 * taps; q += 8) {
+      const int r = q / taps, tp = q % taps;
+      if (co0 + r < t.cout_pad && ci0 + lane < t.cin_pad)
+        t.w[((int64_t)(co0 + r) * taps + tp) * t.cin_pad + ci0 + lane] = __float2bfloat16_rn(tile[r * ld + lane * taps + tp]);
+    }
+  // wt[ci][tap][co]: one 32-row run per (channel, tap)
+  if (t.wt)
+    for (int q = warp; q < 32 * taps; q += 8) {
+      const int c = q / taps, tp = q % taps;
+      if (ci0 + c < t.cin_pad && co0 + lane < t.cout_pad)
+        t.wt[((int64_t)(ci0 + c) * taps + tp) * t.cout_pad + co0 + lane] = __float2bfloat16_rn(tile[lane * ld + c * taps + tp]);
+    }
+}
+
+int pack_weights_tiles(const void* table, int ntensors, const int* tile_tensor, const int* tile_index, int ntiles,
+                       cudaStream_t st) {
+  if (!table || !tile_tensor || !tile_index || ntensors <= 0 || ntiles < 0) return NPP_E_INVALID;
+  if (ntiles == 0) return NPP_OK;
+  pack_weights_tiles_kernel<<<ntiles, 256, 0, st>>>(static_cast<const PackTensor*>(table), tile_tensor, tile_index);
+  NPP_CHECK_LAUNCH("pack_weights_tiles_kernel");
+  return NPP_OK;
+}
+
 int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
                        int chunk_elems, cudaStream_t st) {
   if (!table || !chunk_tensor || !chunk_index || ntensors <= 0 || nchunks < 0 || chunk_elems <= 0) return NPP_E_INVALID;

@@ -30,7 +30,9 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # NPP_CONV_PAIR=1 -> 3x3 convolutions with 32 -> 32 channels run in pixel-pair form (round-2 candidate)
           "conv_pair": os.environ.get("NPP_CONV_PAIR", "0") != "0",
           # NPP_SE_BWD2=1 -> SE bottleneck backward in two kernels without weight-gradient atomics (round-2 candidate)
-          "se_bwd2": os.environ.get("NPP_SE_BWD2", "0") != "0"}
+          "se_bwd2": os.environ.get("NPP_SE_BWD2", "0") != "0",
+          # NPP_PACK_TILES=1 -> tile-transposing multi-tensor weight pack (round-2 candidate)
+          "pack_tiles": os.environ.get("NPP_PACK_TILES", "0") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -508,19 +510,42 @@ class WeightPacker:
                 ci += list(range(nch))
         dev = self.params[0].device if self.params else None
         self.n = len(rows)
+        self.tiles = None
         if self.n:
             self.table = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8).clone().to(dev)
             self.chunk_tensor = torch.tensor(ct, dtype=torch.int32).to(dev)
             self.chunk_index = torch.tensor(ci, dtype=torch.int32).to(dev)
             self.ptrs = [w.data_ptr() for w in self.params]
+            if _state.get("pack_tiles", False):
+                # tile form (round-2 candidate): one block per 32 x 32 x taps tile of every plain (non-pair) row; rows
+                # the tile kernel cannot take (more than 9 taps, pair layout) stay on the element-wise kernel
+                tt, tix, ect, eci = [], [], [], []
+                for ri, row in enumerate(rows):
+                    _, _, _, cout, taps, cin, cop, cip, flag = struct.unpack("<QQQiiiiii", row)
+                    if flag == 0 and taps <= 9:
+                        nt = ((cop + 31) // 32) * ((cip + 31) // 32)
+                        tt += [ri] * nt
+                        tix += list(range(nt))
+                    else:
+                        tot = 64 * 9 * 64 if flag == 1 else cop * taps * cip
+                        nch = (tot + self.CHUNK - 1) // self.CHUNK
+                        ect += [ri] * nch
+                        eci += list(range(nch))
+                self.tiles = (torch.tensor(tt, dtype=torch.int32).to(dev), torch.tensor(tix, dtype=torch.int32).to(dev))
+                self.chunk_tensor = torch.tensor(ect, dtype=torch.int32).to(dev)
+                self.chunk_index = torch.tensor(eci, dtype=torch.int32).to(dev)
 
     def pack(self):
         if not self.n or _state["dtype"] != torch.bfloat16:
             return
         if [w.data_ptr() for w in self.params] != self.ptrs:
             raise RuntimeError("WeightPacker: a parameter was re-allocated; build a new packer")
-        call("npp_pack_weights_multi", fptr(self.table), i32(self.n), fptr(self.chunk_tensor), fptr(self.chunk_index),
-             i32(self.chunk_tensor.numel()), i32(self.CHUNK), stream())
+        if self.tiles is not None and self.tiles[0].numel():
+            call("npp_pack_weights_tiles", fptr(self.table), i32(self.n), fptr(self.tiles[0]), fptr(self.tiles[1]),
+                 i32(self.tiles[0].numel()), stream())
+        if self.chunk_tensor.numel():
+            call("npp_pack_weights_multi", fptr(self.table), i32(self.n), fptr(self.chunk_tensor), fptr(self.chunk_index),
+                 i32(self.chunk_tensor.numel()), i32(self.CHUNK), stream())
         _state["packed_weights"] = True
 
     @staticmethod
