@@ -72,8 +72,9 @@ static int bilinear_bwd_t(const npp_view4* dy, const npp_view4* dx, Axis ah, Axi
   });
 }
 
-// Separable form of the bilinear backward (candidate for round 2, selected by functional._state["bilinear_sep"];
-// not the default: written after the round-1 GPU budget was spent, see tests/test_gpu_zz_bilinear_sep.py).
+// Separable form of the bilinear backward (the default since the end of round 1; functional._state["bilinear_sep"],
+// NPP_BILINEAR_SEP=0 goes back to the gather kernel above.  Parity-green on a B200, see
+// tests/test_gpu_zz_bilinear_sep.py; its timing is the first thing to check in round 2).
 // The gather kernel above re-reads every dY element through L1/L2 once per input pixel it touches in BOTH axes
 // (~(2s+1)^2 candidates at scale s, 4 real contributions) and evaluates the taps of every candidate pair.  Bilinear
 // weights factor as wh(ho,h) * ww(wo,w), so

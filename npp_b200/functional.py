@@ -25,8 +25,11 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           "stem_im2col": os.environ.get("NPP_STEM_IM2COL", "1") != "0",
           # NPP_NODE_CAT_GRADS=0 -> the concat-slice gradient of a cell state is added by autograd (strided at::add)
           "node_cat_grads": os.environ.get("NPP_NODE_CAT_GRADS", "1") != "0",
-          # NPP_BILINEAR_SEP=1 -> separable two-pass bilinear backward (round-2 candidate, not yet run on hardware)
-          "bilinear_sep": os.environ.get("NPP_BILINEAR_SEP", "0") != "0",
+          # NPP_BILINEAR_SEP=0 -> gather-form bilinear backward.  The separable two-pass form is the default: parity
+          # green on a B200 (tests/test_gpu_zz_bilinear_sep.py), 32 registers per thread in both passes, and by the
+          # traffic / instruction model of DESIGN.md section 4 about 1.7x cheaper than the gather form (237 us measured
+          # at 512 channels 96^2 -> 24^2) — but it could not be TIMED before the round's GPU budget ran out
+          "bilinear_sep": os.environ.get("NPP_BILINEAR_SEP", "1") != "0",
           # NPP_CONV_PAIR=1 -> 3x3 convolutions with 32 -> 32 channels run in pixel-pair form (round-2 candidate)
           "conv_pair": os.environ.get("NPP_CONV_PAIR", "0") != "0",
           # NPP_SE_BWD2=1 -> SE bottleneck backward in two kernels without weight-gradient atomics (round-2 candidate)
@@ -1309,8 +1312,10 @@ class _ResampleFn(Function):
         n, c, h, w = shape
         dx = empty_internal(n, c, h, w, dy.dtype, dy.device)
         code = L.dtype_code(dy)
-        if mode == "bilinear" and _state.get("bilinear_sep", False):
-            # separable two-pass form (round-2 candidate, off by default: see csrc/resample.cu)
+        if (mode == "bilinear" and _state.get("bilinear_sep", True) and dy.shape[2] >= 2 * h and dy.shape[3] >= 2 * w):
+            # separable two-pass form (csrc/resample.cu): reads dY once, fp32 scratch of N*Ho*Wi*C floats.  Only for
+            # up-sampling by >= 2: when dY is not larger than dx the gather form has nothing to re-read and the
+            # scratch round trip would be pure overhead
             tmp = torch.empty(n * dy.shape[2] * w * c, dtype=torch.float32, device=dy.device)
             call("npp_bilinear_bwd_sep", ref(view(dy)), ref(view(dx)), fptr(tmp), i32(align), f64(sh), f64(sw), i32(code),
                  stream())
