@@ -304,6 +304,18 @@ int npp_par_loss_bwd(const float* logits, int n, int c, int h, int w, const int6
                      int lh, int lw, const float* class_w, int ignore_index, int align_corners,
                      const float* prob, const float* out3, const float* gscale, float* dlogits,
                      npp_stream_t stream);
+/* Per-pixel form of the two cross-entropy backward passes: G[n, y, x, 0:cq] (fp32 NHWC at LABEL resolution, cq =
+ * classes rounded up to a multiple of 4, 16-byte aligned) = d loss / d up-sampled logit, zero for ignored /
+ * unselected pixels and padding channels.  d loss / d head-logit = bilinear backward of G (npp_bilinear_bwd_sep with
+ * the same align_corners), converted to NCHW — same result as npp_par_loss_bwd / npp_edge_loss_bwd up to fp32
+ * summation order, without the shared-memory atomics. */
+int npp_par_loss_grad_pixels(const float* logits, int n, int c, int h, int w, const int64_t* target, int lh,
+                             int lw, const float* class_w, int ignore_index, int align_corners,
+                             const float* prob, const float* out3, const float* gscale, float* G, int cq,
+                             npp_stream_t stream);
+int npp_edge_loss_grad_pixels(const float* logits, int n, int h, int w, const int64_t* target, int lh, int lw,
+                              int ignore_index, int align_corners, const int64_t* posneg, const float* out2,
+                              const float* gscale, float* G, int cq, npp_stream_t stream);
 int npp_edge_count(const int64_t* target, int64_t npix, int64_t* posneg, npp_stream_t stream);
 int npp_edge_loss_fwd(const float* logits, int n, int h, int w, const int64_t* target, int lh,
                       int lw, int ignore_index, int align_corners, const int64_t* posneg,

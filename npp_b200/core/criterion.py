@@ -35,6 +35,31 @@ def _prep_target(t):
     return t.contiguous()
 
 
+def _ce_bwd_sep_enabled():
+    from .. import functional as F_
+    return F_._state.get("ce_bwd_sep", False)
+
+
+def _grad_through_upsample(score, lh, lw, align_corners, fill):
+    """d loss / d head-logit from the per-pixel gradient at label resolution: `fill(G, cq)` writes G [N, lh, lw, cq]
+    (fp32 NHWC), the separable bilinear backward pulls it back to the head resolution, the result is converted to
+    the NCHW layout of `score` (round-2 candidate path, see csrc/loss.cu ce_grad_kernel)."""
+    from .._lib import NPP_F32, f64, ref, view
+    n, c, h, w = score.shape
+    cq = (c + 3) // 4 * 4
+    dev = score.device
+    G = torch.empty((n, lh, lw, cq), dtype=torch.float32, device=dev)
+    fill(G, cq)
+    dxn = torch.empty((n, h, w, cq), dtype=torch.float32, device=dev)
+    tmp = torch.empty(n * lh * w * cq, dtype=torch.float32, device=dev)
+    gv, dv = G.permute(0, 3, 1, 2), dxn.permute(0, 3, 1, 2)      # logical NCHW over NHWC memory
+    call("npp_bilinear_bwd_sep", ref(view(gv)), ref(view(dv)), fptr(tmp), i32(align_corners), f64(0.0), f64(0.0),
+         i32(NPP_F32), stream())
+    d = torch.empty_like(score)
+    call("npp_nhwc_to_nchw", ref(view(dv)), fptr(d), i32(c), i32(NPP_F32), stream())
+    return d
+
+
 class _OhemCEFn(Function):
     """OhemCrossEntropy.forward (criterion.py:54-72) of bilinear_upsample(score) — fused."""
 
@@ -65,8 +90,15 @@ class _OhemCEFn(Function):
         score, target, weight, prob, out3 = ctx.saved_tensors
         ignore_index, align_corners = ctx.cfg
         n, c, h, w = score.shape
-        d = torch.zeros_like(score)
         gs = g.reshape(1).float().contiguous()
+        if _ce_bwd_sep_enabled():
+            lh, lw = target.shape[1], target.shape[2]
+            d = _grad_through_upsample(score, lh, lw, align_corners, lambda G, cq: call(
+                "npp_par_loss_grad_pixels", fptr(score), i32(n), i32(c), i32(h), i32(w), fptr(target), i32(lh), i32(lw),
+                fptr(weight), i32(ignore_index), i32(align_corners), fptr(prob), fptr(out3), fptr(gs), fptr(G), i32(cq),
+                stream()))
+            return d, None, None, None, None, None, None
+        d = torch.zeros_like(score)
         call("npp_par_loss_bwd", fptr(score), i32(n), i32(c), i32(h), i32(w), fptr(target), i32(target.shape[1]),
              i32(target.shape[2]), fptr(weight), i32(ignore_index), i32(align_corners), fptr(prob), fptr(out3),
              fptr(gs), fptr(d), stream())
@@ -93,8 +125,14 @@ class _EdgeCEFn(Function):
         score, target, posneg, out2 = ctx.saved_tensors
         ignore_index, align_corners = ctx.cfg
         n, c, h, w = score.shape
-        d = torch.zeros_like(score)
         gs = g.reshape(1).float().contiguous()
+        if _ce_bwd_sep_enabled():
+            lh, lw = target.shape[1], target.shape[2]
+            d = _grad_through_upsample(score, lh, lw, align_corners, lambda G, cq: call(
+                "npp_edge_loss_grad_pixels", fptr(score), i32(n), i32(h), i32(w), fptr(target), i32(lh), i32(lw),
+                i32(ignore_index), i32(align_corners), fptr(posneg), fptr(out2), fptr(gs), fptr(G), i32(cq), stream()))
+            return d, None, None, None, None
+        d = torch.zeros_like(score)
         call("npp_edge_loss_bwd", fptr(score), i32(n), i32(h), i32(w), fptr(target), i32(target.shape[1]),
              i32(target.shape[2]), i32(ignore_index), i32(align_corners), fptr(posneg), fptr(out2), fptr(gs), fptr(d),
              stream())

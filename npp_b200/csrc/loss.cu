@@ -209,6 +209,85 @@ ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targ
   }
 }
 
+// Per-pixel form of the cross-entropy backward (round-2 candidate, criterion._state "ce_bwd_sep"): the kernel above
+// pulls every label pixel's gradient through the four bilinear taps of every class into a shared-memory accumulator
+// with atomics — 80 shared-memory atomics per pixel, 4-8-way conflicted because neighbouring pixels share their
+// source taps (ncu: 1.47 ms per parsing launch, 30 % SM throughput, 24 % warp slots).  Pulling a gradient back
+// through a bilinear up-sampling IS the bilinear backward, for which a separable kernel exists
+// (npp_bilinear_bwd_sep), so this kernel only writes G[n, y, x, c] = d loss / d up-sampled-logit (fp32 NHWC, CQ
+// channels = classes rounded up to a multiple of 4, zero for ignored / unselected pixels); the caller runs the
+// separable bilinear backward on G and converts the NHWC result to the NCHW logit gradient.
+template <int MODE>
+__global__ void __launch_bounds__(kLossThreads)
+ce_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, LossGeom g,
+               const float* __restrict__ class_w, const int64_t* __restrict__ posneg, int ignore,
+               const float* __restrict__ prob, const float* __restrict__ sel, const float* __restrict__ gscale,
+               float* __restrict__ G, int CQ) {
+  extern __shared__ float patch[];  // [c][HR][WR]
+  const int plane = g.HR * g.WR;
+  const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE, n = blockIdx.z;
+  const int hy0 = axis_first(g.ah, ty0), hx0 = axis_first(g.aw, tx0);
+  for (int i = threadIdx.x; i < g.c * plane; i += blockDim.x) {
+    const int c = i / plane, r = (i % plane) / g.WR, q = i % g.WR;
+    const int hy = min(hy0 + r, g.h - 1), hx = min(hx0 + q, g.w - 1);
+    patch[i] = logits[(((int64_t)n * g.c + c) * g.h + hy) * g.w + hx];
+  }
+  __syncthreads();
+  float w_edge[2] = {0.f, 0.f};
+  float base;
+  float thr = 0.f;
+  if (MODE == 1) {
+    const float pos = (float)posneg[0], neg = (float)posneg[1];
+    w_edge[0] = pos / (pos + neg);
+    w_edge[1] = neg / (pos + neg);
+    base = gscale[0] / sel[1];
+  } else {
+    base = sel[1] > 0.f ? gscale[0] / sel[1] : 0.f;
+    thr = sel[2];
+  }
+  const int lx = threadIdx.x % TILE;
+  for (int ly = threadIdx.x / TILE; ly < TILE; ly += kLossThreads / TILE) {
+    const int y = ty0 + ly, x = tx0 + lx;
+    if (y >= g.lh || x >= g.lw) continue;
+    const int64_t pidx = ((int64_t)n * g.lh + y) * g.lw + x;
+    float4* gp = reinterpret_cast<float4*>(G + pidx * CQ);
+    const int64_t t = target[pidx];
+    bool live = !(t == ignore || t < 0 || t >= g.c);
+    if (live && MODE == 0 && !(prob[pidx] < thr)) live = false;
+    if (!live) {
+      for (int k = 0; k < CQ / 4; ++k) gp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    int h0, h1, w0, w1; float lh0, lh1, lw0, lw1;
+    bilinear_taps(g.ah, y, h0, h1, lh0, lh1);
+    bilinear_taps(g.aw, x, w0, w1, lw0, lw1);
+    const int o00 = (h0 - hy0) * g.WR + (w0 - hx0), o01 = (h0 - hy0) * g.WR + (w1 - hx0);
+    const int o10 = (h1 - hy0) * g.WR + (w0 - hx0), o11 = (h1 - hy0) * g.WR + (w1 - hx0);
+    float v[CMAX];
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < g.c) {
+        const float* p = patch + c * plane;
+        v[c] = lh0 * (lw0 * p[o00] + lw1 * p[o01]) + lh1 * (lw0 * p[o10] + lw1 * p[o11]);
+        mx = fmaxf(mx, v[c]);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < g.c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+    }
+    const float coef = base * (MODE == 0 ? class_w[t] : w_edge[t]);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) v[c] = c < g.c ? coef * (v[c] * inv - (c == (int)t ? 1.f : 0.f)) : 0.f;
+#pragma unroll
+    for (int k = 0; k < CMAX / 4; ++k)
+      if (4 * k < CQ) gp[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+}
+
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes) {
   if (bytes > 200 * 1024) return NPP_E_UNSUPPORTED;
@@ -417,6 +496,41 @@ int npp_par_loss_bwd(const float* logits, int n, int c, int h, int w, const int6
   ce_bwd_kernel<0><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index, prob,
                                                                out3, gscale, dlogits);
   NPP_CHECK_LAUNCH("ce_bwd_kernel<par>");
+  return NPP_OK;
+}
+
+int npp_par_loss_grad_pixels(const float* logits, int n, int c, int h, int w, const int64_t* target, int lh, int lw,
+                             const float* class_w, int ignore_index, int align_corners, const float* prob,
+                             const float* out3, const float* gscale, float* G, int cq, npp_stream_t s) {
+  if (!logits || !target || !class_w || !prob || !out3 || !gscale || !G || cq < c || (cq & 3) || cq > CMAX ||
+      (reinterpret_cast<uintptr_t>(G) & 15))
+    return NPP_E_INVALID;
+  LossGeom g;
+  int rc = make_geom(&g, n, c, h, w, lh, lw, align_corners);
+  if (rc) return rc;
+  const size_t smem = (size_t)c * g.HR * g.WR * sizeof(float);
+  if ((rc = ensure_smem(ce_grad_kernel<0>, smem))) return rc;
+  dim3 grid(g.tiles_x, g.tiles_y, n);
+  ce_grad_kernel<0><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index, prob,
+                                                                out3, gscale, G, cq);
+  NPP_CHECK_LAUNCH("ce_grad_kernel<par>");
+  return NPP_OK;
+}
+int npp_edge_loss_grad_pixels(const float* logits, int n, int h, int w, const int64_t* target, int lh, int lw,
+                              int ignore_index, int align_corners, const int64_t* posneg, const float* out2,
+                              const float* gscale, float* G, int cq, npp_stream_t s) {
+  if (!logits || !target || !posneg || !out2 || !gscale || !G || cq < 2 || (cq & 3) || cq > CMAX ||
+      (reinterpret_cast<uintptr_t>(G) & 15))
+    return NPP_E_INVALID;
+  LossGeom g;
+  int rc = make_geom(&g, n, 2, h, w, lh, lw, align_corners);
+  if (rc) return rc;
+  const size_t smem = (size_t)2 * g.HR * g.WR * sizeof(float);
+  if ((rc = ensure_smem(ce_grad_kernel<1>, smem))) return rc;
+  dim3 grid(g.tiles_x, g.tiles_y, n);
+  ce_grad_kernel<1><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
+                                                                nullptr, out2, gscale, G, cq);
+  NPP_CHECK_LAUNCH("ce_grad_kernel<edge>");
   return NPP_OK;
 }
 

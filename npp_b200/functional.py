@@ -35,7 +35,10 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # NPP_SE_BWD2=1 -> SE bottleneck backward in two kernels without weight-gradient atomics (round-2 candidate)
           "se_bwd2": os.environ.get("NPP_SE_BWD2", "0") != "0",
           # NPP_PACK_TILES=1 -> tile-transposing multi-tensor weight pack (round-2 candidate)
-          "pack_tiles": os.environ.get("NPP_PACK_TILES", "0") != "0"}
+          "pack_tiles": os.environ.get("NPP_PACK_TILES", "0") != "0",
+          # NPP_CE_BWD_SEP=1 -> cross-entropy backward as per-pixel gradient + separable bilinear backward instead of
+          # the shared-memory-atomic kernel (round-2 candidate; core/criterion.py, csrc/loss.cu ce_grad_kernel)
+          "ce_bwd_sep": os.environ.get("NPP_CE_BWD_SEP", "0") != "0"}
 
 
 def set_compute_dtype(dtype):
