@@ -427,12 +427,24 @@ class Network(nn.Module):
             z = y if z is None else F_.add(z, y)
         return z, cursor + len(idx)
 
+    # optional per-stage trace: `net._trace = fn` makes forward call fn(name, NCHW fp32 tensor) at the stage boundaries
+    # the oracle records under the same names (oracle/nppnet_ref.py set_trace; tools/parity_trace.py).  Off by default.
+    _trace = None
+
+    def _tr(self, name, t, relu=False):
+        if self._trace is not None:
+            with torch.no_grad():
+                h = F_.relu(t) if relu else F_.to_internal(t)
+                self._trace(name, F_.from_internal(h))
+
     def forward(self, x):
         x = F_.to_internal(x)
         s0 = self.stem1(self.stem0(x))
         s1 = self.stem2(s0)
         s2 = self.stem4(self.stem3(x))
         s3 = self.stem5(s2)
+        self._tr("stem2", s1)
+        self._tr("stem5", s3)
         f1, f2 = [], []           # per-stream feature pyramids (fine -> coarse, then decoder outputs)
         c1 = c2 = stage = 0
         for i, (cell1, cell2) in enumerate(zip(self.cells1, self.cells2)):
@@ -441,14 +453,18 @@ class Network(nn.Module):
             tap = i in self._tap_layers
             s0, s1 = s1, cell1(s0, s1, out_raw=tap, out_relu=True)
             s2, s3 = s3, cell2(s2, s3, out_raw=tap, out_relu=True)
+            self._tr("relu(cells1.%d)" % i, s1, relu=True)
+            self._tr("relu(cells2.%d)" % i, s3, relu=True)
             if i in self._tap_layers:
                 f1.append(s1)
                 f2.append(s3)
                 z1, c1 = self._exchange(self._ops1, c1, self._indices1[stage], f2)
                 z2, c2 = self._exchange(self._ops2, c2, self._indices2[stage], f1)
-                stage += 1
                 s1 = F_.node(s1, z1, want_raw=True, want_relu=True)[0]  # read raw (f1) and through nn.ReLU (cells)
                 s3 = F_.node(s3, z2, want_raw=True, want_relu=True)[0]
+                self._tr("f1.%d" % stage, s1)
+                self._tr("f2.%d" % stage, s3)
+                stage += 1
                 f1[-1], f2[-1] = s1, s3
 
         # decoder: three upsample cells per stream with interaction after each (:453-533)
@@ -463,6 +479,8 @@ class Network(nn.Module):
             z2, c2 = self._exchange(self.up_ops2, c2, self.up_indices2[d], f1)
             o1 = F_.node(o1, z1, want_raw=True, want_relu=True)[0]
             o2 = F_.node(o2, z2, want_raw=True, want_relu=True)[0]
+            self._tr("f1.%d" % (4 + d), o1)
+            self._tr("f2.%d" % (4 + d), o2)
             f1[-1], f2[-1] = o1, o2
             prev1, prev2 = o1, o2
 
@@ -478,6 +496,9 @@ class Network(nn.Module):
         in2 = self.edge_layer.lazy(x2)
         in3 = self.pose_layer.lazy(x1)
         in4 = self.par_layer.lazy(x2)
+        for nm, t in (("relu(pose_auxlayer)", in1), ("relu(edge_layer)", in2), ("relu(pose_layer)", in3),
+                      ("relu(par_layer)", in4)):
+            self._tr(nm, t, relu=True)
 
         pose_list, par_list = [], []
 
@@ -496,6 +517,10 @@ class Network(nn.Module):
                 in1, tmp = self.pose_net[2 * (i - 1) + j](in1, in3, in4, out_raw=False, out_relu=True)
                 in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4, out_raw=False, out_relu=True)
                 in3 = tmp
+                k = 2 * (i - 1) + j
+                for nm, t in (("relu(pose_net.%d.fea1)" % k, in1), ("relu(pose_net.%d.fea2)" % k, in3),
+                              ("relu(par_net.%d.fea1)" % k, in2), ("relu(par_net.%d.fea2)" % k, in4)):
+                    self._tr(nm, t, relu=True)
             emit(i)
         return pose_list, par_list
 

@@ -68,6 +68,22 @@ def rnd(x):
     return x if _STORAGE[0] is None else _Round.apply(x)
 
 
+# ---- optional per-stage trace (tools/parity_trace.py, tests/test_gpu_baseline_config.py) ---------------------------
+# set_trace(dict) makes network_forward record named intermediate tensors (detached) so that a parity failure can be
+# located to a stage instead of being judged at the outputs only.
+_TRACE = [None]
+
+
+def set_trace(store):
+    _TRACE[0] = store
+
+
+def _tr(name, t):
+    if _TRACE[0] is not None:
+        _TRACE[0][name] = t.detach()
+    return t
+
+
 class Params:
     """state_dict accessor with a key prefix; `training` selects batch vs running statistics."""
 
@@ -264,9 +280,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
         return _seq_conv_bn(p.sub(name), x, 0, 1, pad=1, stride=stride, relu_out=relu_out)
 
     s0 = stem("stem1", stem("stem0", x, 2, True), 2, True)
-    s1 = stem("stem2", s0, 1, False)
+    s1 = _tr("stem2", stem("stem2", s0, 1, False))
     s2 = stem("stem4", stem("stem3", x, 2, True), 2, True)
-    s3 = stem("stem5", s2, 1, False)
+    s3 = _tr("stem5", stem("stem5", s2, 1, False))
     f1, f2 = [], []
     c1 = c2 = stage = 0
     red_prev = False
@@ -274,6 +290,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
         red = i in reduces
         s0, s1 = s1, encoder_cell(p.sub("cells1").sub(i), s0, s1, red, red_prev)
         s2, s3 = s3, encoder_cell(p.sub("cells2").sub(i), s2, s3, red, red_prev)
+        if _TRACE[0] is not None:
+            _tr("relu(cells1.%d)" % i, F.relu(s1))
+            _tr("relu(cells2.%d)" % i, F.relu(s3))
         red_prev = red
         if i in taps:
             f1.append(s1)
@@ -282,9 +301,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
             same = lambda ind, cont=stage: ind == cont
             z1, c1 = _interaction(p, "_ops1", c1, INTER_TASK1[stage], f2, sc, same)
             z2, c2 = _interaction(p, "_ops2", c2, INTER_TASK2[stage], f1, sc, same)
+            s1 = _tr("f1.%d" % stage, rnd(s1 + z1))
+            s3 = _tr("f2.%d" % stage, rnd(s3 + z2))
             stage += 1
-            s1 = rnd(s1 + z1)
-            s3 = rnd(s3 + z2)
             f1[-1], f2[-1] = s1, s3
 
     res = [1, 1 / 2, 1 / 4, 1 / 8, 1 / 4, 1 / 2, 1]
@@ -299,7 +318,7 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
         same = lambda ind, d=d: ind == 4 + d
         z1, c1 = _interaction(p, "up_ops1", c1, INTER_TASK3[d], f2, sc, same)
         z2, c2 = _interaction(p, "up_ops2", c2, INTER_TASK4[d], f1, sc, same)
-        o1, o2 = rnd(o1 + z1), rnd(o2 + z2)
+        o1, o2 = _tr("f1.%d" % (4 + d), rnd(o1 + z1)), _tr("f2.%d" % (4 + d), rnd(o2 + z2))
         f1[-1], f2[-1] = o1, o2
         prev1, prev2 = o1, o2
 
@@ -309,6 +328,10 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
     in2 = _seq_conv_bn(p.sub("edge_layer"), x2, 1, 2, relu_in=True)
     in3 = _seq_conv_bn(p.sub("pose_layer"), x1, 1, 2, relu_in=True)
     in4 = _seq_conv_bn(p.sub("par_layer"), x2, 1, 2, relu_in=True)
+    if _TRACE[0] is not None:
+        for nm, t in (("relu(pose_auxlayer)", in1), ("relu(edge_layer)", in2), ("relu(pose_layer)", in3),
+                      ("relu(par_layer)", in4)):
+            _tr(nm, F.relu(t))
     pose_list, par_list = [], []
 
     def emit(i):
@@ -326,6 +349,10 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
             in1, tmp = fusion_cell(p.sub("pose_net").sub(k), in1, in3, in4, FUSION_POSE)
             in2, in4 = fusion_cell(p.sub("par_net").sub(k), in2, in3, in4, FUSION_PAR)
             in3 = tmp
+            if _TRACE[0] is not None:
+                for nm, t in (("relu(pose_net.%d.fea1)" % k, in1), ("relu(pose_net.%d.fea2)" % k, in3),
+                              ("relu(par_net.%d.fea1)" % k, in2), ("relu(par_net.%d.fea2)" % k, in4)):
+                    _tr(nm, F.relu(t))
         emit(i)
     return pose_list, par_list
 
@@ -515,7 +542,7 @@ def parsing_loss(preds, target, weight, ignore_index=255, thresh=0.9, min_kept=1
     h, w = target[0].shape[1:]
     pos = torch.sum(target[1] == 1, dtype=torch.float)
     neg = torch.sum(target[1] == 0, dtype=torch.float)
-    ew = torch.stack([pos / (pos + neg), neg / (pos + neg)]).to(preds[1].device)
+    ew = torch.stack([pos / (pos + neg), neg / (pos + neg)]).to(preds[1].device, preds[1].dtype)
     sp = F.interpolate(preds[0], size=(h, w), mode="bilinear", align_corners=True)
     loss = ohem_ce(sp, target[0], weight, ignore_index, thresh, min_kept)
     se = F.interpolate(preds[1], size=(h, w), mode="bilinear", align_corners=True)
