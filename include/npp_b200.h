@@ -362,6 +362,10 @@ int npp_pose_merge(const float* pred, const float* flip_pred, int n, int nj, int
                    const int* flip_idx, int oh, int ow, float* out, npp_stream_t stream);
 int npp_gaussian_filter(const float* src, float* tmp, float* dst, int planes, int h, int w, double sigma,
                         double truncate, npp_stream_t stream);
+/* pascal validate_sync (core/function_ppp.py:905,957-958): out[n,j] = 0.5*(pred[n,j] + flip_pred[n, flip_idx[j]]) in
+ * heat-map space (the mirrored image's maps are joint-permuted, not mirrored back); out may alias pred. */
+int npp_heatmap_flip_avg(const float* pred, const float* flip_pred, int n, int nj, int h, int w,
+                         const int* flip_idx, float* out, npp_stream_t stream);
 int npp_pck_counts(const int32_t* pred_idx, const float* pred_max, const int32_t* gt_idx,
                    const float* gt_max, int n, int j, int h, int w, float thr, int64_t* hit,
                    int64_t* valid, npp_stream_t stream);
@@ -520,6 +524,43 @@ int npp_mix_dw(const npp_mix_desc* d, const float* sums, const float* const* bet
                npp_stream_t stream);
 int npp_mix_bwd_apply(const npp_mix_desc* d, const npp_view4* g, const float* w, const float* sums,
                       double count, const npp_view4* dpass, int dtype, npp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SyncBN statistics exchange over NVLink peer memory (csrc/peer.cu).
+ * Replaces the per-BatchNorm collectives of torch.nn.SyncBatchNorm that the reference installs with
+ * nn.SyncBatchNorm.convert_sync_batchnorm (augment_lip_sync.py:191, search_lip_sync.py:268): forward all_gather of
+ * (mean, invstd, count), backward all_reduce of (sum_dy, sum_dy_xmu) — here one all-reduce (SUM) of the raw
+ * 2C..4C-float vectors per cell node and direction, done by ONE single-block kernel that reads the peers' staging
+ * buffers directly (one-shot all-reduce; rank-ordered sums, bit-identical on all ranks).
+ *
+ * One process per GPU.  Setup (host, once): every rank allocates a communication buffer (npp_peer_alloc: cudaMalloc of
+ * npp_peer_buffer_bytes(), zeroed), exports it (npp_peer_export: 64-byte cudaIpcMemHandle_t), the handles travel
+ * through the caller's own control plane (torch.distributed all_gather_object), every rank maps its peers' buffers
+ * (npp_peer_open) and fills an npp_peer_comm.  All ranks must issue the same sequence of npp_peer_allreduce calls.
+ *   src0/dst0/n0 (+ optional src1/dst1/n1): fp32 vectors, 16-byte aligned, n multiples of 4, n0 + n1 <=
+ *   NPP_PEER_MAX_FLOATS; dst may alias src.  timeout_ms (0 = 30 s): a peer that does not show up sets the error word
+ *   (npp_peer_status; the kernel then continues with whatever it can read instead of hanging the GPU).
+ * ---------------------------------------------------------------------------------------- */
+#define NPP_PEER_MAX_RANKS 8
+#define NPP_PEER_RING 4
+#define NPP_PEER_MAX_FLOATS 8192
+#define NPP_PEER_HANDLE_BYTES 64
+typedef struct {
+  void* bufs[NPP_PEER_MAX_RANKS]; /* bufs[p]: rank p's communication buffer as mapped in THIS process */
+  int32_t rank, world;
+  int32_t timeout_ms;
+  int32_t reserved;
+} npp_peer_comm;
+
+int64_t npp_peer_buffer_bytes(void);
+int npp_peer_alloc(void** ptr);
+int npp_peer_free(void* ptr);
+int npp_peer_export(void* ptr, void* handle64);
+int npp_peer_open(const void* handle64, void** ptr);
+int npp_peer_close(void* ptr);
+int npp_peer_allreduce(const npp_peer_comm* comm, const float* src0, float* dst0, int n0, const float* src1,
+                       float* dst1, int n1, npp_stream_t stream);
+int npp_peer_status(const npp_peer_comm* comm, unsigned int* seq, unsigned int* error);
 
 #ifdef __cplusplus
 }

@@ -39,14 +39,33 @@ def get_max_preds(batch_heatmaps):
     return preds, mx_np[:, :, None]
 
 
-def pck_counts(output, target, thr=0.5):
-    """Per-joint (hit, valid) int64 counters of evaluate.py:43-65 for hm_type='gaussian'."""
+def flip_average(pred_pose, flip_pred_pose, flipped_poseidx):
+    """core/function_ppp.py:957-958: 0.5 * (pred[:, j] + flip_pred[:, flipped_poseidx[j]]) per joint, in heat-map
+    space (the reference does not mirror the second set of maps back; neither do we)."""
+    import ctypes
+    pred, flip = _as_cuda_f32(pred_pose), _as_cuda_f32(flip_pred_pose)
+    if pred.shape != flip.shape:
+        raise AssertionError("pred_pose / flip_pred_pose must have the same shape")
+    b, j, h, w = pred.shape
+    if len(flipped_poseidx) != j:
+        raise AssertionError("flipped_poseidx must list one source joint per joint")
+    out = torch.empty_like(pred)
+    fidx = (ctypes.c_int * j)(*[int(v) for v in flipped_poseidx])
+    call("npp_heatmap_flip_avg", fptr(pred), fptr(flip), i32(b), i32(j), i32(h), i32(w), fidx, fptr(out), stream())
+    return out
+
+
+def pck_counts(output, target, thr=0.5, hit=None, valid=None):
+    """Per-joint (hit, valid) int64 counters of evaluate.py:43-65 for hm_type='gaussian'; pass `hit` / `valid` to
+    accumulate across batches on the device."""
     out, tgt = _as_cuda_f32(output), _as_cuda_f32(target)
     b, j, h, w = out.shape
     pi, pm = heatmap_argmax(out)
     gi, gm = heatmap_argmax(tgt)
-    hit = torch.zeros(j, dtype=torch.int64, device=out.device)
-    valid = torch.zeros(j, dtype=torch.int64, device=out.device)
+    if hit is None:
+        hit = torch.zeros(j, dtype=torch.int64, device=out.device)
+    if valid is None:
+        valid = torch.zeros(j, dtype=torch.int64, device=out.device)
     call("npp_pck_counts", fptr(pi), fptr(pm), fptr(gi), fptr(gm), i32(b), i32(j), i32(h), i32(w), f32(thr), fptr(hit),
          fptr(valid), stream())
     return hit, valid, (pi, pm)

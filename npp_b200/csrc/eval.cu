@@ -208,6 +208,19 @@ __global__ void pckh_counts_kernel(const double* __restrict__ pred, const double
   if (d <= thr) atomicAdd(hit + p, 1ull);
 }
 
+// pascal validate_sync (core/function_ppp.py:957-958): pred[:, j] = 0.5 * (pred[:, j] + flip_pred[:, flipped_poseidx[j]])
+// in heat-map space — the mirrored image's maps are joint-permuted but NOT mirrored back (reference behaviour).
+__global__ void heatmap_flip_avg_kernel(const float* __restrict__ pred, const float* __restrict__ flip, int nj, int hw,
+                                        FlipIdx fi, int64_t total, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int px = (int)(i % hw);
+    const int64_t t = i / hw;
+    const int j = (int)(t % nj);
+    const int64_t n = t / nj;
+    out[i] = 0.5f * (pred[i] + flip[(n * nj + fi.idx[j]) * hw + px]);
+  }
+}
+
 }  // namespace npp
 
 using namespace npp;
@@ -256,6 +269,23 @@ int npp_pose_merge(const float* pred, const float* flip_pred, int n, int nj, int
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
   pose_merge_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, n, nj, h, w, oh, ow, fi, out);
   NPP_CHECK_LAUNCH("pose_merge_kernel");
+  return NPP_OK;
+}
+
+int npp_heatmap_flip_avg(const float* pred, const float* flip_pred, int n, int nj, int h, int w, const int* flip_idx,
+                         float* out, npp_stream_t s) {
+  if (!pred || !flip_pred || !out || !flip_idx || n <= 0 || nj <= 0 || nj > 32 || h <= 0 || w <= 0) return NPP_E_INVALID;
+  FlipIdx fi;
+  for (int j = 0; j < 32; ++j) fi.idx[j] = 0;
+  for (int j = 0; j < nj; ++j) {
+    if (flip_idx[j] < 0 || flip_idx[j] >= nj) return NPP_E_INVALID;
+    fi.idx[j] = flip_idx[j];
+  }
+  const int64_t total = (int64_t)n * nj * h * w;
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  heatmap_flip_avg_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, nj, h * w, fi, total, out);
+  NPP_CHECK_LAUNCH("heatmap_flip_avg_kernel");
   return NPP_OK;
 }
 

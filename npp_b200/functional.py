@@ -610,10 +610,26 @@ def _sync_group():
     return g
 
 
-def _allreduce_sum(t):
+def _allreduce_sum(t, t2=None):
+    """In-place SUM over the SyncBN group of one or two fp32 statistic vectors; returns the group size.  On CUDA with
+    a peer communicator (distributed.enable_sync_bn) this is ONE single-block kernel reading the peers' staging
+    buffers over NVLink (csrc/peer.cu) instead of an NCCL collective per vector."""
     import torch.distributed as dist
     g = _state["sync_bn"]
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if g is True else g)
+    grp = None if g is True else g
+    comm = _state.get("peer_comm")
+    if comm is not None and t.is_cuda:
+        comm.allreduce(t, t2)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=grp)
+        if t2 is not None:
+            dist.all_reduce(t2, op=dist.ReduceOp.SUM, group=grp)
+    return dist.get_world_size(grp)
+
+
+def _sync_world():
+    import torch.distributed as dist
+    g = _state["sync_bn"]
     return dist.get_world_size(None if g is True else g)
 
 
@@ -748,12 +764,25 @@ class _BNSide:
     __slots__ = ("bn", "stats", "coef", "c")
 
 
-def _bn_forward_coef(y, stats, bn, sync, defer=False):
+def _bn_training(bn):
+    return bn is not None and (bn.training or not bn.track_running_stats)
+
+
+def _bn_local_stats(y, stats):
+    """Per-channel (sum, sum of squares) of y: the conv epilogue's vector when it exists, else one npp_bn_stats pass."""
+    if stats is None or stats.numel() == 0:
+        stats = zeros_f32(2 * y.shape[1], y.device)
+        call("npp_bn_stats", ref(view(y)), fptr(stats), i32(L.dtype_code(y)), stream())
+    return stats
+
+
+def _bn_forward_coef(y, stats, bn, sync, defer=False, reduced=False):
     """Batch statistics -> (scale, shift, mean, invstd) as one [4C] tensor; updates the running statistics
     (nn.BatchNorm2d training semantics, momentum 0.1 / eps 1e-5 in operations.py:27).
-    defer=True (training, no SyncBN): the finalize arithmetic is left to the consuming node kernel
-    (npp_node_fwd_bn); returns (coef, count, gamma, fin) with fin = the npp_bn_fin descriptor, or fin = None when
-    the coefficients were computed here."""
+    defer=True (training): the finalize arithmetic is left to the consuming node kernel (npp_node_fwd_bn);
+    returns (coef, count, gamma, fin) with fin = the npp_bn_fin descriptor, or fin = None when the coefficients were
+    computed here.  reduced=True (SyncBN): `stats` already holds the sums over all ranks (the caller exchanged the
+    vectors of several BatchNorms in one message); only the sample count is scaled here."""
     n, c, h, w = y.shape
     dev = y.device
     training = bn.training or not bn.track_running_stats
@@ -775,14 +804,12 @@ def _bn_forward_coef(y, stats, bn, sync, defer=False):
             _state["defer_bn_counters"].append(bn.num_batches_tracked)  # one foreach add per step (engine.TrainStep)
         else:
             bn.num_batches_tracked.add_(1)
-    if stats is None or stats.numel() == 0:
-        stats = zeros_f32(2 * c, dev)
-        call("npp_bn_stats", ref(view(y)), fptr(stats), i32(L.dtype_code(y)), stream())
+    stats = _bn_local_stats(y, stats)
     count = float(n * h * w)
     if sync:
-        count *= _allreduce_sum(stats)
+        count *= _sync_world() if reduced else _allreduce_sum(stats)
     c_run = bn.running_mean.numel() if bn.running_mean is not None else 0
-    if defer and not sync:
+    if defer:
         fin = L.BnFin(fptr(stats).value, fptr(gamma).value, fptr(beta).value, fptr(bn.running_mean).value,
                       fptr(bn.running_var).value, fptr(coef).value, float(bn.momentum), float(bn.eps), int(c_run))
         fin._keep = (stats, gamma, beta, coef)
@@ -813,10 +840,23 @@ class _NodeFn(Function):
         gam_a = gam_b = None
         fin_a = fin_b = None
         defer = _state.get("node_fused_finalize", True)
+        reduced = False
+        if sync:
+            # SyncBN: the statistic vectors of BOTH BatchNorms of the node travel in one exchange
+            vecs = []
+            if _bn_training(bn_a):
+                st_a = _bn_local_stats(a, st_a)
+                vecs.append(st_a)
+            if _bn_training(bn_b):
+                st_b = _bn_local_stats(b, st_b)
+                vecs.append(st_b)
+            if vecs:
+                _allreduce_sum(*vecs)
+                reduced = True
         if bn_a is not None:
-            ca, count, gam_a, fin_a = _bn_forward_coef(a, st_a, bn_a, sync, defer=defer)
+            ca, count, gam_a, fin_a = _bn_forward_coef(a, st_a, bn_a, sync, defer=defer, reduced=reduced)
         if bn_b is not None:
-            cb, count, gam_b, fin_b = _bn_forward_coef(b, st_b, bn_b, sync, defer=defer)
+            cb, count, gam_b, fin_b = _bn_forward_coef(b, st_b, bn_b, sync, defer=defer, reduced=reduced)
         raw = (out_raw if out_raw is not None else empty_internal(n, c, h, w, a.dtype, a.device)) if want_raw else None
         rel = (out_relu if out_relu is not None else empty_internal(n, c, h, w, a.dtype, a.device)) if want_relu else None
         if fin_a is not None or fin_b is not None:
@@ -1399,11 +1439,22 @@ class _MixFn(Function):
         interleave = pass_ is not None
         count = float(n * h * w)
         coefs = []
+        stats = list(stats)
+        reduced = False
+        if sync:   # SyncBN: the branches' statistic vectors travel two per exchange
+            vecs = []
+            for j, (y, bn) in enumerate(zip(ys, bns)):
+                if _bn_training(bn):
+                    stats[j] = _bn_local_stats(y, stats[j])
+                    vecs.append(stats[j])
+            for j in range(0, len(vecs), 2):
+                _allreduce_sum(*vecs[j:j + 2])
+            reduced = bool(vecs)
         for y, bn, st in zip(ys, bns, stats):
             if bn is None:
                 coefs.append(None)
             else:
-                cf, count, _ = _bn_forward_coef(y, st, bn, sync)
+                cf, count, _ = _bn_forward_coef(y, st, bn, sync, reduced=reduced)
                 coefs.append(cf)
         d = _mix_desc(ys, interleave)
         for j, cf in enumerate(coefs):

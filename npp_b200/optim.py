@@ -20,11 +20,47 @@ CHUNK = 16384
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._key = None
+        self._key = None          # addresses the device table was built for (params, grads, moments, step counters)
+        self._hyper = None        # (lr, weight_decay) per table row as written into the device table
         self._tables = None       # (table, chunk_tensor, chunk_index) device tensors
         self._steps = None        # one int64 device counter per parameter (torch.optim.Adam's state['step'])
         self.flat_grads = None    # the flat gradient buffer once use_flat_grads() was called
         self._flat_views = None
+
+    # ---- resume (augment_lip_sync.py:235 optimizer.load_state_dict) -----------------------------------------------
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict, then: the loaded exp_avg / exp_avg_sq / step tensors are NEW
+        tensors, so the device table (raw pointers) is rebuilt on the next step and the per-parameter step counters
+        are re-seated in one int64 device vector holding the LOADED values (bias correction continues where the
+        checkpoint left off).  Accepts state dicts written by torch.optim.Adam (float / CPU `step`)."""
+        super().load_state_dict(state_dict)
+        self._key = self._hyper = self._tables = None
+        self._steps = None
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._key = self._hyper = self._tables = None
+        self._steps = None
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if getattr(self, "_steps", None) is not None:
+            self._key = self._hyper = None
+            self._steps = None        # re-seated (values kept) on the next step
+
+    def _seat_steps(self, dev):
+        """One int64 device vector with a counter per parameter; state[p]['step'] are 0-dim views into it.  Counters
+        that already exist (a loaded checkpoint, a previous seating) keep their values."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("FusedAdam: run one eager step (or load the checkpoint) before capturing a CUDA graph")
+        allp = [p for group in self.param_groups for p in group["params"]]
+        vals = []
+        for p in allp:
+            old = self.state[p].get("step") if p in self.state else None
+            vals.append(int(float(old)) if old is not None else 0)
+        self._steps = torch.tensor(vals, dtype=torch.int64).to(dev)
+        for i, p in enumerate(allp):
+            self.state[p]["step"] = self._steps[i]
 
     def _init_state(self, p):
         st = self.state[p]
@@ -85,10 +121,37 @@ class FusedAdam(torch.optim.Optimizer):
         ct = torch.tensor(chunk_tensor, dtype=torch.int32)
         ci = torch.tensor(chunk_index, dtype=torch.int32)
         self._tables = tuple(t.to(dev) for t in (tbl, ct, ci))
+        self._rows = rows
+
+    def _current_hyper(self):
+        """(lr, weight_decay) per table row, in table order (parameters with a gradient)."""
+        return tuple((float(g["lr"]), float(g["weight_decay"])) for g in self.param_groups for p in g["params"]
+                     if p.grad is not None)
+
+    def sync_hyperparameters(self):
+        """Writes the param groups' CURRENT lr / weight_decay into the device table IN PLACE (same device memory, so a
+        captured CUDA graph picks the new values up on its next replay).  engine.TrainStep.run() calls this before
+        every replay; it is a tuple comparison unless an lr scheduler (MultiStepLR, augment_lip_sync.py:213,249) or the
+        user changed a group.  Returns True when the table was rewritten."""
+        if self._tables is None or self._key is None:
+            return False
+        hyper = self._current_hyper()
+        if hyper == self._hyper or len(hyper) != len(self._rows):
+            return False
+        rows = []
+        for row, (lr, wd) in zip(self._rows, hyper):
+            f = list(struct.unpack("<QQQQqffQ", row))
+            f[5], f[6] = lr, wd
+            rows.append(struct.pack("<QQQQqffQ", *f))
+        host = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8)
+        self._tables[0].copy_(host)      # stream-ordered before the next launch / graph replay on this stream
+        self._rows, self._hyper = rows, hyper
+        return True
 
     def refresh_hyperparameters(self):
-        """Rebuilds the table on the next step (e.g. after an lr scheduler changed group['lr'])."""
-        self._key = None
+        """Kept for callers of the first version: the table follows param_groups by itself now (step() and
+        sync_hyperparameters() compare lr / weight_decay on every call)."""
+        self.sync_hyperparameters()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -113,19 +176,18 @@ class FusedAdam(torch.optim.Optimizer):
         if not items:
             return None
         if self._steps is None:
-            allp = [p for group in self.param_groups for p in group["params"]]
-            self._steps = torch.zeros(len(allp), dtype=torch.int64, device=dev)
-            for i, p in enumerate(allp):
-                self.state[p]["step"] = self._steps[i]
-        for p, _, _, _ in items:
-            if "step" not in self.state[p]:  # parameter group added after the first step
-                if torch.cuda.is_current_stream_capturing():
-                    raise RuntimeError("FusedAdam: add parameter groups before capturing a CUDA graph")
-                self.state[p]["step"] = torch.zeros((), dtype=torch.int64, device=dev)
-        key = tuple((p.data_ptr(), g.data_ptr(), lr, wd) for p, g, lr, wd in items)
+            self._seat_steps(dev)
+        key = tuple((p.data_ptr(), g.data_ptr(), self._init_state(p)["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr(), self.state[p]["step"].data_ptr()) for p, g, _, _ in items)
         if key != self._key:
             self._build(items, dev)
             self._key = key
+            self._hyper = tuple((lr, wd) for _, _, lr, wd in items)
+        elif self._hyper != tuple((lr, wd) for _, _, lr, wd in items):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedAdam: lr / weight_decay changed while capturing; change them before the capture "
+                                   "or between replays (TrainStep.run() syncs them)")
+            self.sync_hyperparameters()
         tbl, ct, ci = self._tables
         call("npp_adam_step", fptr(tbl), i32(len(items)), fptr(ct), fptr(ci), i32(ct.numel()), i32(CHUNK), f32(b1),
              f32(b2), f32(eps), stream())

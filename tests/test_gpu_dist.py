@@ -1,0 +1,271 @@
+"""GPU, 2 ranks over NCCL + NVLink peer memory (skipped on a box with one GPU): the data-parallel path computes on
+2 ranks x B what one rank computes on the concatenated batch of 2B (augment_lip_sync.py:191,207-208).
+
+  * csrc/peer.cu one-shot all-reduce: exact rank-ordered sums, many exchanges back to back, two vectors per message;
+  * one cell node (conv + BatchNorm on both operands, add, ReLU) forward and backward under SyncBN, fp32 mode, 1e-5;
+  * the derived network under SyncBN + summed gradients against the single-rank run on the whole batch (fp32 mode);
+  * engine.TrainStep(world_size=2) with the CUDA graph: identical parameters on both ranks after several steps,
+    finite falling loss, no exchange time-out, clean teardown (graph released, peer buffers unmapped, process
+    group destroyed).
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn_name, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        globals()[fn_name](rank, world)
+        out[rank] = "ok"
+    except Exception as e:  # surfaced by the parent
+        import traceback
+        out[rank] = "".join(traceback.format_exception(type(e), e, e.__traceback__))
+    finally:
+        try:
+            from npp_b200 import distributed as npp_dist
+            npp_dist.enable_sync_bn(None)
+        except Exception:
+            pass
+        dist.destroy_process_group()
+
+
+def _run(fn_name, world=2):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn_name, out), nprocs=world, join=True)
+    for r in range(world):
+        assert out.get(r) == "ok", "rank %d: %s" % (r, out.get(r))
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ workers
+def _w_peer_allreduce(rank, world):
+    from npp_b200 import distributed as npp_dist
+    from npp_b200 import functional as F_
+    npp_dist.enable_sync_bn(True)
+    comm = npp_dist.peer_comm()
+    assert comm is not None, "peer-memory transport was not set up"
+    gen = torch.Generator().manual_seed(3)
+    full = [torch.randn(world, n, generator=gen) for n in (8, 128, 2048, 4096, 12, 8192)]
+    # many exchanges back to back (ring reuse), one and two vectors per message, in place
+    for it in range(200):
+        for i, f in enumerate(full):
+            t = (f[rank] * (it + 1)).cuda()
+            want = (f.double().sum(0) * (it + 1))
+            if i % 2 == 0 and f.shape[1] <= 4096:
+                t2 = (f[rank] * 0.5).cuda()
+                F_._allreduce_sum(t, t2)
+                assert rel(t2.cpu(), f.double().sum(0) * 0.5) < 1e-6
+            else:
+                F_._allreduce_sum(t)
+            assert rel(t.cpu(), want) < 1e-6, (it, i)
+    # rank-ordered sums: bit-identical on every rank
+    t = torch.randn(1024, generator=torch.Generator().manual_seed(10 + rank)).cuda()
+    F_._allreduce_sum(t)
+    both = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(both, t)
+    assert all(torch.equal(both[0], b) for b in both[1:])
+    # inside a CUDA graph
+    x = torch.full((256,), float(rank + 1), device="cuda")
+    y = torch.empty_like(x)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        y.copy_(x)
+        F_._allreduce_sum(y)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y.copy_(x)
+        F_._allreduce_sum(y)
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y.cpu(), torch.full((256,), float(sum(range(1, world + 1)))))
+    g.reset()
+    assert comm.check() > 0
+
+
+def _node_case(dtype, seed=5):
+    """conv3x3+BN on a, conv1x1+BN on b, add, ReLU -> (raw, relu); returns a callable(model pieces, x) -> outputs."""
+    from npp_b200 import nn as N
+    torch.manual_seed(seed)
+    ca = N.Conv2d(16, 32, 3, padding=1, bias=False)
+    cb = N.Conv2d(16, 32, 1, bias=False)
+    ba, bb = N.BatchNorm2d(32), N.BatchNorm2d(32)
+    with torch.no_grad():
+        for bn in (ba, bb):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.2)
+    return ca, cb, ba, bb
+
+
+def _node_forward(mods, x):
+    from npp_b200 import functional as F_
+    from npp_b200.nn import call_lazy, Sequential
+    ca, cb, ba, bb = mods
+    xi = F_.to_internal(x)
+    a = call_lazy(Sequential(ca, ba), xi)
+    b = call_lazy(Sequential(cb, bb), xi)
+    raw, rel_ = F_.node(a, b, want_raw=True, want_relu=True)
+    return F_.from_internal(raw, 32), F_.from_internal(rel_, 32)
+
+
+def _w_node_syncbn(rank, world):
+    from npp_b200 import distributed as npp_dist
+    from npp_b200 import functional as F_
+    F_.set_compute_dtype(torch.float32)
+    try:
+        gen = torch.Generator().manual_seed(21)
+        xf = torch.randn(4 * world, 16, 24, 24, generator=gen)
+        g1 = torch.randn(4 * world, 32, 24, 24, generator=gen)
+        g2 = torch.randn(4 * world, 32, 24, 24, generator=gen)
+        sl = slice(4 * rank, 4 * rank + 4)
+
+        def run(x, ga, gb):
+            mods = [m.cuda().train() for m in _node_case(torch.float32)]
+            x = x.cuda().requires_grad_(True)
+            raw, r = _node_forward(mods, x)
+            ((raw * ga.cuda()).sum() + (r * gb.cuda()).sum()).backward()
+            grads = [p.grad.clone() for m in mods for p in m.parameters()]
+            stats = [b.clone() for m in mods for b in m.buffers() if b.dtype.is_floating_point]
+            return raw.detach(), r.detach(), x.grad.detach(), grads, stats
+
+        npp_dist.enable_sync_bn(True)
+        raw, r, dx, grads, stats = run(xf[sl], g1[sl], g2[sl])
+        for g in grads:
+            dist.all_reduce(g)                       # DDP sums (then averages) parameter gradients
+        npp_dist.enable_sync_bn(None)
+        raw1, r1, dx1, grads1, stats1 = run(xf, g1, g2)   # single-rank run on the whole batch
+        assert rel(raw, raw1[sl]) < 1e-5 and rel(r, r1[sl]) < 1e-5, (rel(raw, raw1[sl]), rel(r, r1[sl]))
+        assert rel(dx, dx1[sl]) < 1e-4, rel(dx, dx1[sl])
+        for a, b in zip(grads, grads1):
+            assert rel(a, b) < 1e-4, rel(a, b)
+        for a, b in zip(stats, stats1):              # running statistics use the global count / unbiased variance
+            assert rel(a, b) < 1e-5, rel(a, b)
+    finally:
+        F_.set_compute_dtype(torch.bfloat16)
+
+
+def _w_network_syncbn(rank, world):
+    """Derived network, fp32 validation mode, a configuration whose coarsest BatchNorm still sees 288 samples (so the
+    comparison is not dominated by the chaotic amplification of tiny-sample BatchNorm at random init)."""
+    from npp_b200 import distributed as npp_dist
+    from npp_b200 import engine
+    from npp_b200 import functional as F_
+    from npp_b200.models.model_augment import Network
+    F_.set_compute_dtype(torch.float32)
+    try:
+        B, S = 2, 192
+        gen = torch.Generator().manual_seed(31)
+        xf = torch.randn(B * world, 3, S, S, generator=gen)
+        cot = [torch.randn(B * world, c, S // 4, S // 4, generator=gen) for c in (16, 16, 16, 16, 20, 2, 20, 2)]
+        sl = slice(B * rank, B * rank + B)
+
+        def run(x, cots):
+            torch.manual_seed(0)
+            net = Network(engine.make_cfg(layers=4, init_channels=16)).cuda().train()
+            pl, par = net(x.cuda())
+            outs = [t for p in pl + par for t in p]
+            sum((t * c.cuda()).sum() for t, c in zip(outs, cots)).backward()
+            return [o.detach() for o in outs], {k: p.grad.detach().clone() for k, p in net.named_parameters()
+                                                if p.grad is not None}
+
+        npp_dist.enable_sync_bn(True)
+        outs, grads = run(xf[sl], [c[sl] for c in cot])
+        flat = torch.cat([g.reshape(-1) for g in grads.values()])
+        dist.all_reduce(flat)
+        off = 0
+        for k, g in grads.items():
+            grads[k] = flat[off:off + g.numel()].view_as(g)
+            off += g.numel()
+        assert npp_dist.peer_comm().check() > 100
+        npp_dist.enable_sync_bn(None)
+        outs1, grads1 = run(xf, cot)
+        ferr = [rel(a, b[sl]) for a, b in zip(outs, outs1)]
+        gmax = max(g.abs().max().item() for g in grads1.values())
+        gerr = sorted(rel(grads[k], g) for k, g in grads1.items() if g.abs().max().item() > 1e-5 * gmax)
+        if rank == 0:
+            print("2 ranks x %d vs 1 rank x %d (fp32): forward %s | grads median %.2e p90 %.2e max %.2e" % (
+                B, B * world, ["%.1e" % e for e in ferr], gerr[len(gerr) // 2], gerr[int(.9 * len(gerr))], gerr[-1]))
+        assert max(ferr) < 1e-4, ferr
+        assert gerr[len(gerr) // 2] < 1e-4 and gerr[int(.9 * len(gerr))] < 1e-3, (gerr[len(gerr) // 2], gerr[-1])
+    finally:
+        F_.set_compute_dtype(torch.bfloat16)
+
+
+def _w_trainstep(rank, world):
+    from npp_b200 import distributed as npp_dist
+    from npp_b200 import engine
+    from npp_b200 import functional as F_
+    from npp_b200.core.criterion import Criterion_par, Criterion_pose
+    from npp_b200.models.model_augment import Network
+    F_.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    model = Network(engine.make_cfg(layers=8, init_channels=16)).cuda().train()
+    cpose, cpar = Criterion_pose(out_len=2).cuda(), Criterion_par(out_len=2, min_kept=2000).cuda()
+    opt = engine.build_optimizer(model, cpose, cpar)
+    npp_dist.enable_sync_bn(True)
+    step = engine.TrainStep(model, cpose, cpar, opt, 2, 128, use_graph=True, world_size=world, warmup=1)
+    step.load(*engine.synthetic_batch(2, 128, seed=1 + rank))
+    step.prepare()
+    losses = [float(step.run()) for _ in range(6)]
+    torch.cuda.synchronize()
+    assert all(l == l for l in losses) and min(losses[-2:]) < losses[0], losses
+    comm = npp_dist.peer_comm()
+    assert comm is not None and comm.check() > 500
+    # replicas stay bit-identical: rank-ordered SyncBN sums + the same all-reduced gradients on every rank
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    assert all(torch.equal(both[0], b) for b in both[1:])
+    stats = torch.cat([b.detach().float().reshape(-1) for b in model.buffers()])
+    both = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(both, stats)
+    assert all(torch.equal(both[0], b) for b in both[1:])
+    step.close()
+
+
+# ------------------------------------------------------------------------------------------------ tests
+def test_peer_allreduce_world2(lib_built):
+    _run("_w_peer_allreduce")
+
+
+def test_node_syncbn_2ranks_equals_1rank(lib_built):
+    _run("_w_node_syncbn")
+
+
+def test_network_syncbn_2ranks_equals_1rank(lib_built):
+    _run("_w_network_syncbn")
+
+
+def test_trainstep_world2_graph(lib_built):
+    _run("_w_trainstep")

@@ -147,3 +147,42 @@ def test_direct_gradient_slots_match_autograd_accumulation(lib_built):
     finally:
         F_.set_compute_dtype(torch.bfloat16)
 
+
+
+def test_lr_schedule_takes_effect_under_graph(lib_built):
+    """A MultiStepLR-style decay between replays changes the update size of the graph-captured step."""
+    from npp_b200 import engine
+    model, step = _make(3, use_graph=True)
+    step.load(*engine.synthetic_batch(2, 128, seed=5))
+    step.prepare()
+    w = model.stem0[0].weight
+    a = w.detach().clone()
+    step.run()
+    torch.cuda.synchronize()
+    d1 = (w.detach() - a).abs().mean().item()
+    for g in step.opt.param_groups:
+        g["lr"] *= 0.01
+    a = w.detach().clone()
+    step.run()
+    torch.cuda.synchronize()
+    d2 = (w.detach() - a).abs().mean().item()
+    assert d1 > 0 and d2 < 0.05 * d1, (d1, d2)
+
+
+def test_prepare_leaves_training_state_untouched(lib_built):
+    """Warm-up steps and the capture must not consume optimizer updates: parameters, BatchNorm running
+    statistics, num_batches_tracked and Adam step counters after prepare() equal those before."""
+    from npp_b200 import engine
+    model, step = _make(4, use_graph=True)
+    step.load(*engine.synthetic_batch(2, 128, seed=6))
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    step.prepare()
+    torch.cuda.synchronize()
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    steps = [int(st["step"]) for st in step.opt.state.values() if "step" in st]
+    assert steps and max(steps) == 0
+    step.run()
+    torch.cuda.synchronize()
+    assert max(int(st["step"]) for st in step.opt.state.values() if "step" in st) == 1
+    assert int(model.stem0[1].num_batches_tracked) == 1
