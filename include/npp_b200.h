@@ -526,6 +526,21 @@ int npp_mix_bwd_apply(const npp_mix_desc* d, const npp_view4* g, const float* w,
                       double count, const npp_view4* dpass, int dtype, npp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * On-GPU label synthesis (csrc/labels.cu) — what the reference's data loader builds per image on the
+ * host (dataset/data_loader.py:239-285), for a whole batch per launch.
+ *   pose_target:  dataset/target_generation.py:94-121,146-168 gen_pose_target + gen_single_gaussian_map.
+ *                 joints fp64 [b, j, 2] (x, y in crop pixels), visible int32 [b, j]; out fp32 [b, j+1, grid_y, grid_x]
+ *                 (channel j = background = 1 - max); call twice (sigma, 2*sigma) for the aux maps (:109-121).
+ *   edge_label:   target_generation.py:210-239 generate_edge (+ data_loader.py:284 edge[label==255] = 255):
+ *                 label / out int64 [b, h, w]; edge_width odd (3).
+ *   flip_parsing: target_generation.py:44-56 (mirror + left/right relabel); out must not alias label.
+ * ---------------------------------------------------------------------------------------- */
+int npp_pose_target(const double* joints, const int* visible, int b, int j, double stride, int grid_x, int grid_y,
+                    double sigma, float* out, npp_stream_t stream);
+int npp_edge_label(const int64_t* label, int b, int h, int w, int edge_width, int64_t* out, npp_stream_t stream);
+int npp_flip_parsing(const int64_t* label, int b, int h, int w, int64_t* out, npp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * SyncBN statistics exchange over NVLink peer memory (csrc/peer.cu).
  * Replaces the per-BatchNorm collectives of torch.nn.SyncBatchNorm that the reference installs with
  * nn.SyncBatchNorm.convert_sync_batchnorm (augment_lip_sync.py:191, search_lip_sync.py:268): forward all_gather of

@@ -152,6 +152,23 @@ def trace_end():
     return t
 
 
+def signature(trace):
+    """Pointer-independent description of a recorded call sequence: [(abi name, (scalar arguments and view shapes))].
+    Two runs of the same step — eager launches and the pass that a CUDA graph captures — must produce equal signatures
+    (same kernels, same shapes, same order): tests/test_gpu_engine.py."""
+    out = []
+    for name, args, _, _ in trace:
+        sig = []
+        for a in args:
+            obj = getattr(a, "_obj", None)
+            if isinstance(obj, View4):
+                sig.append(("view", obj.n, obj.h, obj.w, obj.c, obj.sw - obj.c >= 0 and obj.sw != obj.c))
+            elif isinstance(a, (ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double)):
+                sig.append(a.value)
+        out.append((name, tuple(sig)))
+    return out
+
+
 def replay(trace, names):
     """Re-issues the recorded calls whose ABI name is in `names` on the current stream (same pointers, same
     shapes).  Stream arguments are re-read so the replay can be captured into a CUDA graph."""

@@ -90,21 +90,25 @@ __global__ void __launch_bounds__(512, 1) peer_allreduce_kernel(const PeerArgs A
     const unsigned long long t0 = globaltimer_ns();
     unsigned int spins = 0;
     while ((int)(ld_acquire_sys(f) - seq) < 0) {
-      __nanosleep(32);
-      if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > A.timeout_ns) {
+      if (++spins > 64u) __nanosleep(20);      // the common case (peers a few microseconds apart) never sleeps
+      if ((spins & 1023u) == 0 && globaltimer_ns() - t0 > A.timeout_ns) {
         atomicCAS(&me->error, 0u, seq);
         break;
       }
     }
   }
   __syncthreads();
-  // 4. sum over ranks in rank order (same order everywhere: identical bits on every rank)
+  // 4. sum over ranks in rank order (same order everywhere: identical bits on every rank).  All peer loads of a
+  //    thread are issued before the first one is consumed: one NVLink round trip per vector, not one per peer.
   for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+    float4 v[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      if (p < A.world) v[p] = p == A.rank ? *reinterpret_cast<const float4*>(stage + i) : ld_peer4(A.bufs[p]->staging[slot] + i);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < A.world; ++p) {
-      const float4 v = p == A.rank ? *reinterpret_cast<const float4*>(stage + i) : ld_peer4(A.bufs[p]->staging[slot] + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      if (p < A.world) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
     if (i < A.n0) *reinterpret_cast<float4*>(A.dst0 + i) = acc;
     else *reinterpret_cast<float4*>(A.dst1 + (i - A.n0)) = acc;
   }

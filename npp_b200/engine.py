@@ -152,8 +152,11 @@ class TrainStep:
         else:
             flat = self.flat_grads if opt is getattr(self, "opt", None) else getattr(opt, "flat_grads", None)
         if flat is not None:
-            dist.all_reduce(flat)
-            flat.div_(self.world_size)
+            if flat.is_cuda and dist.get_backend() == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)      # the 1 / world scaling rides on the collective
+            else:
+                dist.all_reduce(flat)
+                flat.div_(self.world_size)
             return
         params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
         grads = [p.grad for p in params]

@@ -176,7 +176,7 @@ def _w_node_syncbn(rank, world):
 
 
 def _w_network_syncbn(rank, world):
-    """Derived network, fp32 validation mode, a configuration whose coarsest BatchNorm still sees 288 samples (so the
+    """Derived network, fp32 validation mode, a configuration whose coarsest BatchNorm still sees 144 samples (so the
     comparison is not dominated by the chaotic amplification of tiny-sample BatchNorm at random init)."""
     from npp_b200 import distributed as npp_dist
     from npp_b200 import engine
@@ -192,7 +192,7 @@ def _w_network_syncbn(rank, world):
 
         def run(x, cots):
             torch.manual_seed(0)
-            net = Network(engine.make_cfg(layers=4, init_channels=16)).cuda().train()
+            net = Network(engine.make_cfg(layers=8, init_channels=16)).cuda().train()
             pl, par = net(x.cuda())
             outs = [t for p in pl + par for t in p]
             sum((t * c.cuda()).sum() for t, c in zip(outs, cots)).backward()

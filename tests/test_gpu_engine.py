@@ -49,6 +49,76 @@ def test_graph_replay_matches_eager(lib_built):
         assert torch.equal(p, q)
 
 
+def test_captured_step_issues_the_same_kernel_sequence_as_eager(lib_built):
+    """A dropped or doubled term in the graph path would show as a different ABI call sequence: the pass that the CUDA
+    graph captures must launch exactly the kernels (names, shapes, scalar arguments, order) of an eager step."""
+    from npp_b200 import _lib, engine
+    model, step = _make(5, use_graph=True)
+    step.load(*engine.synthetic_batch(2, 128, seed=11))
+    _lib.trace_begin()
+    step._step_body()                      # eager
+    eager_sig = _lib.signature(_lib.trace_end())
+    torch.cuda.synchronize()
+    real_graph = torch.cuda.graph
+
+    captured = {}
+
+    class _TracingGraph(real_graph):       # records the ABI calls issued while the graph is being captured
+        def __enter__(self):
+            r = super().__enter__()
+            _lib.trace_begin()
+            return r
+
+        def __exit__(self, *a):
+            captured["sig"] = _lib.signature(_lib.trace_end())
+            return super().__exit__(*a)
+
+    torch.cuda.graph = _TracingGraph
+    try:
+        step.prepare()
+    finally:
+        torch.cuda.graph = real_graph
+    assert len(eager_sig) > 1500
+    assert captured["sig"] == eager_sig
+
+
+def test_graph_replay_gradients_match_eager_fp32(lib_built):
+    """Element-wise gradient comparison of a graph replay against eager launches, in fp32 validation mode on a
+    configuration whose coarsest BatchNorm still sees 144 samples (L=8, 192^2): atomics reordering stays at rounding
+    level there (no chaotic amplification), so the flat gradient buffers must agree to 1e-3 norm-wise."""
+    from npp_b200 import engine
+    from npp_b200 import functional as F_
+    from npp_b200.core.criterion import Criterion_par, Criterion_pose
+    from npp_b200.models.model_augment import Network
+    F_.set_compute_dtype(torch.float32)
+    try:
+        steps = []
+        for use_graph in (False, True):
+            torch.manual_seed(0)
+            model = Network(engine.make_cfg(layers=8, init_channels=16)).cuda().train()
+            cpose, cpar = Criterion_pose(out_len=2).cuda(), Criterion_par(out_len=2, min_kept=2000).cuda()
+            opt = engine.build_optimizer(model, cpose, cpar)
+            for g in opt.param_groups:
+                g["lr"] = 0.0
+            st = engine.TrainStep(model, cpose, cpar, opt, 2, 192, use_graph=use_graph, warmup=1)
+            st.load(*engine.synthetic_batch(2, 192, seed=12))
+            st.prepare()
+            steps.append(st)
+        for b in range(2):
+            batch = engine.synthetic_batch(2, 192, seed=20 + b)
+            for st in steps:
+                st.load(*batch)
+                st.run()
+            torch.cuda.synchronize()
+            ge, gg = steps[0].flat_grads.double(), steps[1].flat_grads.double()
+            assert abs(float(steps[0].loss) - float(steps[1].loss)) < 1e-5 * abs(float(steps[0].loss))
+            err = ((ge - gg).norm() / ge.norm()).item()
+            print("graph vs eager flat gradient rel err (fp32, L=8, 192^2):", err)
+            assert err < 1e-3, err
+    finally:
+        F_.set_compute_dtype(torch.bfloat16)
+
+
 def test_train_step_loss_decreases(lib_built):
     from npp_b200 import engine
     model, step = _make(2, use_graph=True)

@@ -37,9 +37,21 @@ def test_ops_golden(dtype, tol, lib_built):
             y = F_.from_internal(op(F_.to_internal(x, dtype)), 16)
             (y * torch.from_numpy(g[tag + "/gy"]).cuda()).sum().backward()
             assert rel(y, g[tag + "/y"]) < tol, (tag, rel(y, g[tag + "/y"]))
-            # small-sample BatchNorm backward is ill-conditioned in bf16; the tight gradient bounds live in test_gpu_ops
-            gtol = tol if dtype == torch.float32 else 0.1
-            assert rel(x.grad, g[tag + "/dx"]) < gtol, (tag, "dx", rel(x.grad, g[tag + "/dx"]))
+            gtol = tol
+            if dtype == torch.bfloat16:
+                # small-sample BatchNorm backward is ill-conditioned in bf16: the bound is what the oracle restatement of
+                # the same primitive costs with bf16-rounded storage and bf16 conv operands (1.5x), never below 2e-2
+                from oracle import nppnet_ref as O
+                xo = torch.from_numpy(g[tag + "/x"]).bfloat16().float().requires_grad_(True)
+                sdo = {k: v.clone() for k, v in sd.items()}
+                O.set_storage_dtype(torch.bfloat16, weights=True)
+                try:
+                    yo = O.primitive(name, O.Params(sdo, True), xo, int(stride))
+                    (yo * torch.from_numpy(g[tag + "/gy"])).sum().backward()
+                finally:
+                    O.set_storage_dtype(None)
+                gtol = max(tol, 1.5 * rel(xo.grad, g[tag + "/dx"]))
+            assert rel(x.grad, g[tag + "/dx"]) < gtol, (tag, "dx", rel(x.grad, g[tag + "/dx"]), gtol)
             for k, b in op.named_buffers():
                 if "running" in k:
                     assert rel(b, g["%s/after/%s" % (tag, k)]) < max(tol, 1e-5), (tag, k)

@@ -221,6 +221,7 @@ def test_supernet_bf16_step(lib_built):
     with torch.no_grad():
         for k in arch:
             getattr(net, k).copy_(torch.from_numpy(g["arch/" + k]))
+    sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.cuda().train()
     c0 = _lib.launch_count()
     pl, par = net(torch.from_numpy(g["x"]).cuda())
@@ -230,8 +231,21 @@ def test_supernet_bf16_step(lib_built):
     assert _lib.launch_count() - c0 > 2000
     names = ["pose0", "poseaux0", "pose1", "poseaux1", "par0", "edge0", "par1", "edge1"]
     errs = [rel(t, g["out/" + n]) for n, t in zip(names, outs)]
-    print("bf16 supernet output errors vs fp32 reference fixture:", errs)
-    assert all(torch.isfinite(t).all() for t in outs) and max(errs) < 0.25
+    # yardstick: the oracle restatement of the supernet with every operator output rounded to bf16 and bf16 conv
+    # operands (what bf16 storage costs for this depth / this tiny 32-sample-BatchNorm configuration), same fixture
+    from oracle import nppnet_ref as O
+    O.set_storage_dtype(torch.bfloat16, weights=True)
+    try:
+        with torch.no_grad():
+            ypl, ypar = O.search_forward(sd_cpu, torch.from_numpy(g["x"]).bfloat16().float(), layers=int(g["layers"]),
+                                         training=True)
+    finally:
+        O.set_storage_dtype(None)
+    yerrs = [rel(t, g["out/" + n]) for n, t in zip(names, [t for pair in ypl + ypar for t in pair])]
+    print("bf16 supernet output errors vs fp32 reference fixture: ours", errs, "yardstick", yerrs)
+    assert all(torch.isfinite(t).all() for t in outs)
+    for e, ey in zip(errs, yerrs):
+        assert e < max(2e-2, 1.5 * ey), (errs, yerrs)
     for p in net.arch_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
     with torch.no_grad():
