@@ -34,6 +34,12 @@ class FusedAdam(torch.optim.Optimizer):
         are re-seated in one int64 device vector holding the LOADED values (bias correction continues where the
         checkpoint left off).  Accepts state dicts written by torch.optim.Adam (float / CPU `step`)."""
         super().load_state_dict(state_dict)
+        # torch moves / casts the loaded tensors only when needed, so they can still alias the caller's state dict (or
+        # another optimizer's live state): the kernel updates them in place, hence private copies
+        for st in self.state.values():
+            for k, v in list(st.items()):
+                if torch.is_tensor(v):
+                    st[k] = v.clone()
         self._key = self._hyper = self._tables = None
         self._steps = None
 

@@ -1,8 +1,29 @@
 """GPU versions of the evaluation helpers in the reference's utils/utils.py."""
+import os
+
 import numpy as np
 import torch
 
 from .._lib import call, fptr, i32, stream
+
+
+def save_checkpoint(states, is_best, output_dir, filename="checkpoint.pth"):
+    """utils/utils.py:60-65: the whole `states` dict to checkpoint.pth; when `is_best`, the bare `best_state_dict` to
+    model_best.pth.  Keys as the reference's drivers build them (augment_lip_sync.py:268-278): epoch, state_dict
+    (DistributedDataParallel-prefixed `module.` names), best_state_dict, perf_iou, perf_pck, lr, optimizer, cri1, cri2."""
+    torch.save(states, os.path.join(output_dir, filename))
+    if is_best and "state_dict" in states:
+        torch.save(states["best_state_dict"], os.path.join(output_dir, "model_best.pth"))
+
+
+def ddp_state_dict(model):
+    """The state_dict a DistributedDataParallel-wrapped model would save: every key prefixed with `module.`
+    (augment_lip_sync.py:270 `model.state_dict()` on the DDP wrapper)."""
+    return {"module." + k: v for k, v in model.state_dict().items()}
+
+
+def strip_ddp_prefix(state_dict):
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
 
 
 def confusion_hist(label, pred, num_class, ignore=-1, hist=None):

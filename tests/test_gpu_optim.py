@@ -44,22 +44,28 @@ def test_fused_adam_resume_matches_torch(lib_built):
 
     for _ in range(7):
         step_both(oa, ob, pa, pb)
-    sd_a, sd_b = oa.state_dict(), ob.state_dict()
+    import copy
+    sd_a, sd_b = copy.deepcopy(oa.state_dict()), copy.deepcopy(ob.state_dict())    # as torch.load would hand them over
     for src in (sd_a, sd_b):                        # resume from our own and from torch's checkpoint format
         pa2 = [p.detach().clone().requires_grad_(True) for p in pa]
         pb2 = [p.detach().clone().requires_grad_(True) for p in pb]
         oa2, ob2 = FusedAdam(pa2, 0.01), torch.optim.Adam(pb2, 0.01)
-        oa2.load_state_dict(src)
-        ob2.load_state_dict(sd_b)
+        oa2.load_state_dict(copy.deepcopy(src))
+        ob2.load_state_dict(copy.deepcopy(sd_b))
         for _ in range(3):
             step_both(oa2, ob2, pa2, pb2)
         assert int(oa2.state[pa2[0]]["step"]) == 10
         for a, b in zip(pa2, pb2):
             assert torch.allclose(a, b, rtol=2e-5, atol=1e-7), (a - b).abs().max()
     # loading AFTER a step must drop the stale device table (new moment tensors)
-    oa.load_state_dict(sd_a)
+    oa.load_state_dict(copy.deepcopy(sd_a))
+    ob.load_state_dict(copy.deepcopy(sd_b))
+    for a, b in zip(pa, pb):       # same parameters again (the comparison below starts from one point)
+        b.data.copy_(a.data)
     step_both(oa, ob, pa, pb)
-    ob.load_state_dict(sd_b)
+    assert int(oa.state[pa[0]]["step"]) == 8
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=2e-5, atol=1e-7), (a - b).abs().max()
 
 
 def test_fused_adam_lr_change_reaches_the_kernel_in_place(lib_built):
