@@ -192,18 +192,20 @@ class TrainStep:
 
     # ---- warm-up without side effects ----------------------------------------------------------------------
     def _trainable_state(self):
-        """Every tensor a training step mutates: parameters (model + criteria), buffers (BatchNorm running statistics,
-        num_batches_tracked) and the optimizer's moments / step counters."""
-        ts = [p for m in (self.model, self.cpose, self.cpar) for p in m.parameters()]
-        ts += [b for m in (self.model, self.cpose, self.cpar) for b in m.buffers()]
-        for opt in self.opts:
-            for st in opt.state.values():
-                ts += [v for v in st.values() if torch.is_tensor(v)]
-        seen, out = set(), []
-        for t in ts:
-            if t.data_ptr() not in seen or t.numel() == 0:
-                seen.add(t.data_ptr())
-                out.append(t)
+        """Every tensor a training step mutates, keyed by what it IS rather than where it lives (the optimizer may
+        re-seat its step counters on the first step after a load_state_dict): parameters (model + criteria), buffers
+        (BatchNorm running statistics, num_batches_tracked) and the optimizers' moments / step counters."""
+        out = {}
+        for m in (self.model, self.cpose, self.cpar):
+            for p in m.parameters():
+                out[("param", id(p))] = p
+            for b in m.buffers():
+                out[("buffer", id(b))] = b
+        for oi, opt in enumerate(self.opts):
+            for p, st in opt.state.items():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        out[("opt", oi, id(p), k)] = v
         return out
 
     # ---- public ------------------------------------------------------------------------------------------
@@ -215,21 +217,15 @@ class TrainStep:
         per batch like the reference (core/function.py:105-107)."""
         if self.graph is not None or not self.use_graph:
             if not self.use_graph and self.launches_per_step is None:
-                snap = None
-                if keep_state:
-                    before = self._trainable_state()
-                    snap = [t.detach().clone() for t in before]
+                snap = {k: t.detach().clone() for k, t in self._trainable_state().items()} if keep_state else None
                 c0 = _lib.launch_count()
                 self._step_body()
                 self.launches_per_step = _lib.launch_count() - c0
                 if snap is not None:
-                    self._restore(before, snap)
+                    self._restore(snap)
             return
         gc.collect()  # autograd graphs of earlier steps (AccumulateGrad nodes bound to another stream) must be gone
-        snap = None
-        if keep_state:
-            before = self._trainable_state()
-            snap = [t.detach().clone() for t in before]
+        snap = {k: t.detach().clone() for k, t in self._trainable_state().items()} if keep_state else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -244,18 +240,16 @@ class TrainStep:
             self._step_body()
         self.launches_per_step = _lib.launch_count() - c0
         if snap is not None:
-            self._restore(before, snap)
+            self._restore(snap)
 
-    def _restore(self, before, snap):
+    def _restore(self, snap):
         with torch.no_grad():
-            known = {t.data_ptr(): s for t, s in zip(before, snap)}
-            for t in self._trainable_state():
-                s = known.get(t.data_ptr())
+            for k, t in self._trainable_state().items():
+                s = snap.get(k)
                 if s is not None:
-                    t.copy_(s)
+                    t.copy_(s.to(dtype=t.dtype, device=t.device))   # e.g. a loaded float / CPU `step` re-seated as int64
                 else:
                     t.zero_()     # optimizer state created by the warm-up (exp_avg, exp_avg_sq, step): back to initial
-        del snap
 
     def run(self):
         """Runs one step on whatever is in the static input buffers (or on the batch staged by prefetch()); returns

@@ -56,8 +56,15 @@ def test_labels_at_training_shapes_vs_oracle(lib_built):
     assert int(((edge == 1) & (par.cuda() == 255)).sum()) == 0 and int((edge == 255).sum()) == int((par == 255).sum())
     # the synthesized labels feed the training step's criteria directly
     from npp_b200.core.criterion import Criterion_par, Criterion_pose
+    # (blocky labels: with per-pixel random classes every pixel is an edge, the edge class weights become (1, 0) and
+    #  the weighted cross-entropy is 0 / 0 in the reference too)
+    blocks = torch.randint(0, 20, (4, 48, 48), generator=torch.Generator().manual_seed(1))
+    blocks = blocks.repeat_interleave(8, 1).repeat_interleave(8, 2)
+    blocks[:, :8, :] = 255
+    bedge = T.generate_edge(blocks)
+    assert 0 < int((bedge == 1).sum()) < int((bedge == 0).sum())
     logits = [[torch.randn(4, 20, 96, 96).cuda(), torch.randn(4, 2, 96, 96).cuda()]]
-    lp = Criterion_par(out_len=1).cuda()(logits, [par[:4].cuda(), edge[:4]])
+    lp = Criterion_par(out_len=1).cuda()(logits, [blocks.cuda(), bedge])
     lq = Criterion_pose(out_len=1).cuda()([[maps[:4, :16].contiguous(), aux[:4, :16].contiguous()]],
                                           [maps[:4, :16].contiguous(), aux[:4, :16].contiguous()])
     assert torch.isfinite(lp) and abs(float(lq) + 2.5) < 1e-6        # identical prediction and target: loss = lamda
