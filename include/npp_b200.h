@@ -459,6 +459,16 @@ int npp_node_bwd_reduce2(const npp_view4* g_raw, const npp_view4* g_raw2, const 
                          const float* mean_a, const float* invstd_a, const npp_view4* b, const float* mean_b,
                          const float* invstd_b, const npp_view4* g_out, float* partials, float* sums,
                          int stripes, int dtype, npp_stream_t stream);
+/* Same reduction with two type-flexible extra gradient inputs: an output of the node that is read by several consumers
+ * (more primitives of the cell, the concat route) hands every consumer its own handle, so up to three gradients per
+ * node arrive separately and are summed HERE instead of by autograd's accumulation kernels (one add launch and three
+ * tensor passes per extra consumer in the reference).  extraK_is_relu: the slot is a gradient of the relu output
+ * (masked like g_relu) or of the raw output; the primary gradient of that kind must be present; slots fill in order. */
+int npp_node_bwd_reduce3(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
+                         const npp_view4* extra0, int extra0_is_relu, const npp_view4* extra1, int extra1_is_relu,
+                         const npp_view4* a, const float* mean_a, const float* invstd_a, const npp_view4* b,
+                         const float* mean_b, const float* invstd_b, const npp_view4* g_out, float* partials, int dtype,
+                         npp_stream_t stream);
 int npp_node_bwd_apply_striped(const npp_view4* g, const npp_view4* a, const float* gamma_a, const float* mean_a,
                                const float* invstd_a, const npp_view4* da, const npp_view4* b,
                                const float* gamma_b, const float* mean_b, const float* invstd_b,
@@ -552,7 +562,7 @@ int npp_flip_parsing(const int64_t* label, int b, int h, int w, int64_t* out, np
  * npp_peer_buffer_bytes(), zeroed), exports it (npp_peer_export: 64-byte cudaIpcMemHandle_t), the handles travel
  * through the caller's own control plane (torch.distributed all_gather_object), every rank maps its peers' buffers
  * (npp_peer_open) and fills an npp_peer_comm.  All ranks must issue the same sequence of npp_peer_allreduce calls.
- *   src0/dst0/n0 (+ optional src1/dst1/n1): fp32 vectors, 16-byte aligned, n multiples of 4, n0 + n1 <=
+ *   src0/dst0/n0 (+ optional src1/dst1/n1): fp32 vectors, n0 + n1 <=
  *   NPP_PEER_MAX_FLOATS; dst may alias src.  timeout_ms (0 = 30 s): a peer that does not show up sets the error word
  *   (npp_peer_status; the kernel then continues with whatever it can read instead of hanging the GPU).
  * ---------------------------------------------------------------------------------------- */

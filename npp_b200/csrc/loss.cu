@@ -209,6 +209,167 @@ ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targ
   }
 }
 
+// Gather form of the same backward (default; NPP_CE_BWD_ATOMIC=1 selects the kernel above).  ncu on ce_bwd_kernel:
+// 1.47 ms per parsing launch, 80 shared-memory atomics per label pixel, 4-8-way conflicted because neighbouring
+// pixels share their source taps.  Pulling a gradient back through a bilinear up-sampling is separable, so the tile
+// is processed in chunks of 8 label rows (one per warp, as above) without a single atomic:
+//   1. every thread computes its pixel's gradient w.r.t. the up-sampled logits, G[row][class][x]  (plain stores,
+//      consecutive lanes -> consecutive words);
+//   2. R[row][class][w] = sum_x weight_x(x -> w) * G[row][class][x]   over the <= 9 label columns that touch head
+//      column w (their range per w is tabulated once per tile);
+//   3. acc[class][h][w] += sum_row weight_y(row -> h) * R[row][class][w]   for the <= 4 head rows the chunk touches —
+//      every (class, h, w) has one owner thread per chunk, so plain read-modify-write.
+// The tile's accumulator is flushed with one global atomic per head element as before.  Summation order inside a tile
+// is fixed (deterministic up to the cross-tile flush).
+template <int MODE>
+__global__ void __launch_bounds__(kLossThreads)
+ce_bwd_gather_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, LossGeom g,
+                     const float* __restrict__ class_w, const int64_t* __restrict__ posneg, int ignore,
+                     const float* __restrict__ prob, const float* __restrict__ sel, const float* __restrict__ gscale,
+                     float* __restrict__ dlogits) {
+  constexpr int ROWS = kLossThreads / TILE;   // 8 label rows per chunk
+  constexpr int GP = TILE + 1;                // padded row of G
+  extern __shared__ float sm[];
+  const int plane = g.HR * g.WR;
+  float* patch = sm;                          // [c][HR][WR]
+  float* acc = patch + g.c * plane;           // [c][HR][WR]
+  float* G = acc + g.c * plane;               // [ROWS][c][GP]
+  float* R = G + ROWS * g.c * GP;             // [ROWS][c][WR]
+  __shared__ int xw0[TILE], xw1[TILE], yh0[TILE], yh1[TILE], xs[TILE], xe[TILE];
+  __shared__ float xl0[TILE], xl1[TILE], yl0[TILE], yl1[TILE];
+  const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE, n = blockIdx.z;
+  const int hy0 = axis_first(g.ah, ty0), hx0 = axis_first(g.aw, tx0);
+  for (int i = threadIdx.x; i < g.c * plane; i += blockDim.x) {
+    const int c = i / plane, r = (i % plane) / g.WR, q = i % g.WR;
+    const int hy = min(hy0 + r, g.h - 1), hx = min(hx0 + q, g.w - 1);
+    patch[i] = logits[(((int64_t)n * g.c + c) * g.h + hy) * g.w + hx];
+    acc[i] = 0.f;
+  }
+  if (threadIdx.x < TILE) {
+    int i0, i1; float l0, l1;
+    bilinear_taps(g.aw, min(tx0 + (int)threadIdx.x, g.lw - 1), i0, i1, l0, l1);
+    xw0[threadIdx.x] = i0 - hx0; xw1[threadIdx.x] = i1 - hx0; xl0[threadIdx.x] = l0; xl1[threadIdx.x] = l1;
+  } else if (threadIdx.x < 2 * TILE) {
+    const int t = threadIdx.x - TILE;
+    int i0, i1; float l0, l1;
+    bilinear_taps(g.ah, min(ty0 + t, g.lh - 1), i0, i1, l0, l1);
+    yh0[t] = i0 - hy0; yh1[t] = i1 - hy0; yl0[t] = l0; yl1[t] = l1;
+  }
+  __syncthreads();
+  if (threadIdx.x < g.WR) {   // label columns whose taps touch head column w: contiguous, taps are monotone in x
+    const int w = threadIdx.x;
+    int a = TILE, b = 0;
+    for (int x = 0; x < TILE; ++x)
+      if (xw0[x] == w || xw1[x] == w) { a = min(a, x); b = max(b, x + 1); }
+    xs[w] = a; xe[w] = b;
+  }
+  float w_edge[2] = {0.f, 0.f};
+  float base;
+  float thr = 0.f;
+  if (MODE == 1) {
+    const float pos = (float)posneg[0], neg = (float)posneg[1];
+    w_edge[0] = pos / (pos + neg);
+    w_edge[1] = neg / (pos + neg);
+    base = gscale[0] / sel[1];           // sel = out2 {num, den}
+  } else {
+    base = sel[1] > 0.f ? gscale[0] / sel[1] : 0.f;  // sel = out3 {sum, n_kept, thr}
+    thr = sel[2];
+  }
+  const int lx = threadIdx.x % TILE, wr = threadIdx.x / TILE;
+  for (int chunk = 0; chunk < TILE / ROWS; ++chunk) {
+    const int ly = chunk * ROWS + wr;
+    // ---- 1. per-pixel gradient w.r.t. the up-sampled logits
+    {
+      const int y = ty0 + ly, x = tx0 + lx;
+      float* grow = G + (wr * g.c) * GP + lx;
+      bool live = y < g.lh && x < g.lw;
+      int64_t t = 0;
+      if (live) {
+        const int64_t pidx = ((int64_t)n * g.lh + y) * g.lw + x;
+        t = target[pidx];
+        live = !(t == ignore || t < 0 || t >= g.c);
+        if (live && MODE == 0 && !(prob[pidx] < thr)) live = false;
+      }
+      if (!live) {
+        for (int c = 0; c < g.c; ++c) grow[c * GP] = 0.f;
+      } else {
+        const float lh0 = yl0[ly], lh1 = yl1[ly], lw0 = xl0[lx], lw1 = xl1[lx];
+        const int o00 = yh0[ly] * g.WR + xw0[lx], o01 = yh0[ly] * g.WR + xw1[lx];
+        const int o10 = yh1[ly] * g.WR + xw0[lx], o11 = yh1[ly] * g.WR + xw1[lx];
+        float v[CMAX];
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < g.c) {
+            const float* p = patch + c * plane;
+            v[c] = lh0 * (lw0 * p[o00] + lw1 * p[o01]) + lh1 * (lw0 * p[o10] + lw1 * p[o11]);
+            mx = fmaxf(mx, v[c]);
+          }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < g.c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+        }
+        const float coef = base * (MODE == 0 ? class_w[t] : w_edge[t]);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < g.c) grow[c * GP] = coef * (v[c] * inv - (c == (int)t ? 1.f : 0.f));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 2. along x
+    for (int o = threadIdx.x; o < ROWS * g.c * g.WR; o += kLossThreads) {
+      const int w = o % g.WR, rc = o / g.WR;    // rc = row * c + class
+      const float* gr = G + rc * GP;
+      float a = 0.f;
+      for (int x = xs[w]; x < xe[w]; ++x) {
+        const float wt = (xw0[x] == w ? xl0[x] : 0.f) + (xw1[x] == w ? xl1[x] : 0.f);
+        a = fmaf(wt, gr[x], a);
+      }
+      R[o] = a;
+    }
+    __syncthreads();
+    // ---- 3. along y, into the tile accumulator
+    const int hlo = yh0[chunk * ROWS], hhi = yh1[chunk * ROWS + ROWS - 1];
+    const int nh = hhi - hlo + 1;
+    for (int o = threadIdx.x; o < g.c * nh * g.WR; o += kLossThreads) {
+      const int w = o % g.WR, hh = hlo + (o / g.WR) % nh, c = o / (g.WR * nh);
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const int ry = chunk * ROWS + r;
+        const float wt = (yh0[ry] == hh ? yl0[ry] : 0.f) + (yh1[ry] == hh ? yl1[ry] : 0.f);
+        a = fmaf(wt, R[(r * g.c + c) * g.WR + w], a);
+      }
+      acc[c * plane + hh * g.WR + w] += a;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < g.c * plane; i += blockDim.x) {
+    const float a = acc[i];
+    if (a == 0.f) continue;
+    const int c = i / plane, r = (i % plane) / g.WR, q = i % g.WR;
+    const int hy = hy0 + r, hx = hx0 + q;
+    if (hy < g.h && hx < g.w) atomicAdd(dlogits + (((int64_t)n * g.c + c) * g.h + hy) * g.w + hx, a);
+  }
+}
+
+static size_t ce_bwd_gather_smem(const LossGeom& g) {
+  return ((size_t)2 * g.c * g.HR * g.WR + (size_t)(kLossThreads / TILE) * g.c * (TILE + 1 + g.WR)) * sizeof(float);
+}
+
+static bool ce_bwd_atomic() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NPP_CE_BWD_ATOMIC");
+    v = (e && *e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // Per-pixel form of the cross-entropy backward (round-2 candidate, criterion._state "ce_bwd_sep"): the kernel above
 // pulls every label pixel's gradient through the four bilinear taps of every class into a shared-memory accumulator
 // with atomics — 80 shared-memory atomics per pixel, 4-8-way conflicted because neighbouring pixels share their
@@ -490,9 +651,17 @@ int npp_par_loss_bwd(const float* logits, int n, int c, int h, int w, const int6
   LossGeom g;
   int rc = make_geom(&g, n, c, h, w, lh, lw, align_corners);
   if (rc) return rc;
+  dim3 grid(g.tiles_x, g.tiles_y, n);
+  if (!ce_bwd_atomic() && g.WR <= TILE) {
+    const size_t smem2 = ce_bwd_gather_smem(g);
+    if ((rc = ensure_smem(ce_bwd_gather_kernel<0>, smem2))) return rc;
+    ce_bwd_gather_kernel<0><<<grid, kLossThreads, smem2, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index,
+                                                                        prob, out3, gscale, dlogits);
+    NPP_CHECK_LAUNCH("ce_bwd_gather_kernel<par>");
+    return NPP_OK;
+  }
   const size_t smem = 2 * (size_t)c * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_bwd_kernel<0>, smem))) return rc;
-  dim3 grid(g.tiles_x, g.tiles_y, n);
   ce_bwd_kernel<0><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index, prob,
                                                                out3, gscale, dlogits);
   NPP_CHECK_LAUNCH("ce_bwd_kernel<par>");
@@ -564,9 +733,17 @@ int npp_edge_loss_bwd(const float* logits, int n, int h, int w, const int64_t* t
   LossGeom g;
   int rc = make_geom(&g, n, 2, h, w, lh, lw, align_corners);
   if (rc) return rc;
+  dim3 grid(g.tiles_x, g.tiles_y, n);
+  if (!ce_bwd_atomic() && g.WR <= TILE) {
+    const size_t smem2 = ce_bwd_gather_smem(g);
+    if ((rc = ensure_smem(ce_bwd_gather_kernel<1>, smem2))) return rc;
+    ce_bwd_gather_kernel<1><<<grid, kLossThreads, smem2, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
+                                                                        nullptr, out2, gscale, dlogits);
+    NPP_CHECK_LAUNCH("ce_bwd_gather_kernel<edge>");
+    return NPP_OK;
+  }
   const size_t smem = 2 * (size_t)2 * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_bwd_kernel<1>, smem))) return rc;
-  dim3 grid(g.tiles_x, g.tiles_y, n);
   ce_bwd_kernel<1><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
                                                                nullptr, out2, gscale, dlogits);
   NPP_CHECK_LAUNCH("ce_bwd_kernel<edge>");

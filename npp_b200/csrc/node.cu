@@ -240,6 +240,7 @@ struct NodeBwdReduceArgs {
   float* sums;                    // atomic mode: [nq][C] zero-initialised accumulators (partials == nullptr)
   AccSegs acc;                    // atomic mode: per-row parameter-gradient slots (d beta / d gamma), ptr may be null
   PView<const T> graw, grelu, r;  // gradients of the raw / relu outputs, relu output (mask)
+  int x0_relu, x1_relu;           // kind of the two extra gradient slots below: 0 = added to graw, 1 = to grelu
   PView<const T> graw2, grelu2;   // second gradient of either output (the concat-buffer slice handed down by the
                                   // consumers of the cell output), summed here instead of by a separate add kernel
   PView<const T> a, b;            // BatchNorm inputs (p == nullptr = that input has no BatchNorm)
@@ -300,17 +301,29 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
         if (has_relu) { Pack<T>::unpack(qgr[u], gr[0]); Pack<T>::unpack(qr[u], rr[0]); }
         if (has_a) Pack<T>::unpack(qa[u], xa[0]);
         if (has_b) Pack<T>::unpack(qb[u], xb[0]);
-        if (HAS2 && has_raw2) {   // host guarantees has_raw2 => has_raw, has_relu2 => has_relu
+        // two extra gradient slots (more consumers of the same output: the concat route, further primitives of the
+        // cell).  Each slot is of raw or relu kind; the host guarantees that the primary gradient of that kind exists.
+        if (HAS2 && has_raw2) {
           float t2[V];
           Pack<T>::unpack(qg2[HAS2 ? u : 0], t2);
+          if (A.x0_relu) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) g[0][i] += t2[i];
+            for (int i = 0; i < V; ++i) gr[0][i] += t2[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) g[0][i] += t2[i];
+          }
         }
         if (HAS2 && has_relu2) {
           float t2[V];
           Pack<T>::unpack(qgr2[HAS2 ? u : 0], t2);
+          if (A.x1_relu) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) gr[0][i] += t2[i];
+            for (int i = 0; i < V; ++i) gr[0][i] += t2[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) g[0][i] += t2[i];
+          }
         }
         if (has_relu) {
 #pragma unroll
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
             g[0][i] = has_raw ? g[0][i] + m : m;
           }
         }
-        if (has_relu || has_raw2) {
+        if (has_relu || has_raw2 || has_relu2) {
           if (A.gout.p) {
             Pack<T>::store(A.gout.at(p, c0), g[0]);
             if (sizeof(T) == 2) {  // the apply pass reads the rounded value: accumulate what it will see
@@ -463,7 +476,7 @@ static int node_bwd_reduce_t(const npp_view4* graw, const npp_view4* grelu, cons
                              const float* mean_a, const float* invstd_a, const npp_view4* b, const float* mean_b,
                              const float* invstd_b, const npp_view4* gout, float* partials, float* sums,
                              const AccSegs* acc, cudaStream_t st, int stripes = 1, const npp_view4* graw2 = nullptr,
-                             const npp_view4* grelu2 = nullptr) {
+                             const npp_view4* grelu2 = nullptr, int x0_relu = 0, int x1_relu = 1) {
   constexpr int V = Pack<T>::N;
   const npp_view4* ref = graw ? graw : grelu;
   NodeBwdReduceArgs<T> A;
@@ -472,6 +485,7 @@ static int node_bwd_reduce_t(const npp_view4* graw, const npp_view4* grelu, cons
   A.graw = graw ? pview<const T>(graw) : pview_null<const T>();
   A.grelu = grelu ? pview<const T>(grelu) : pview_null<const T>();
   A.r = r ? pview<const T>(r) : pview_null<const T>();
+  A.x0_relu = x0_relu; A.x1_relu = x1_relu;
   A.graw2 = graw2 ? pview<const T>(graw2) : pview_null<const T>();
   A.grelu2 = grelu2 ? pview<const T>(grelu2) : pview_null<const T>();
   A.a = a ? pview<const T>(a) : pview_null<const T>();
@@ -768,6 +782,35 @@ int npp_node_bwd_reduce2(const npp_view4* g_raw, const npp_view4* g_raw2, const 
                                                         invstd_b, g_out, (a || b) ? partials : nullptr,
                                                         (a || b) ? sums : nullptr, nullptr, as_stream(s),
                                                         sums ? stripes : 1, g_raw2, g_relu2););
+}
+
+int npp_node_bwd_reduce3(const npp_view4* g_raw, const npp_view4* g_relu, const npp_view4* relu_out,
+                         const npp_view4* extra0, int extra0_is_relu, const npp_view4* extra1, int extra1_is_relu,
+                         const npp_view4* a, const float* mean_a, const float* invstd_a, const npp_view4* b,
+                         const float* mean_b, const float* invstd_b, const npp_view4* g_out, float* partials, int dtype,
+                         npp_stream_t s) {
+  const npp_view4* ref = g_raw ? g_raw : g_relu;
+  if (!ref || !view_ok(ref, dtype)) return NPP_E_INVALID;
+  if (g_raw && g_relu && (!view_ok(g_relu, dtype) || !same_shape(ref, g_relu))) return NPP_E_INVALID;
+  if (g_relu && (!relu_out || !view_ok(relu_out, dtype) || !same_shape(ref, relu_out))) return NPP_E_INVALID;
+  if (!extra0 && extra1) return NPP_E_INVALID;                  // slots are filled in order
+  const npp_view4* ex[2] = {extra0, extra1};
+  const int kind[2] = {extra0_is_relu, extra1_is_relu};
+  for (int i = 0; i < 2; ++i) {
+    if (!ex[i]) continue;
+    if (!view_ok(ex[i], dtype) || !same_shape(ref, ex[i])) return NPP_E_INVALID;
+    if (kind[i] ? !g_relu : !g_raw) return NPP_E_INVALID;       // an extra gradient needs the primary one of its kind
+  }
+  if (a && (!view_ok(a, dtype) || !same_shape(ref, a) || !mean_a || !invstd_a)) return NPP_E_INVALID;
+  if (b && (!view_ok(b, dtype) || !same_shape(ref, b) || !mean_b || !invstd_b)) return NPP_E_INVALID;
+  if (g_out && (!view_ok(g_out, dtype) || !same_shape(ref, g_out))) return NPP_E_INVALID;
+  if ((g_relu || extra0) && !g_out) return NPP_E_INVALID;       // a combined gradient has to be written somewhere
+  if ((a || b) && !partials) return NPP_E_INVALID;
+  if (!a && !b && !g_out) return NPP_E_INVALID;
+  NPP_DISPATCH_DTYPE(dtype, return node_bwd_reduce_t<T>(g_raw, g_relu, relu_out, a, mean_a, invstd_a, b, mean_b,
+                                                        invstd_b, g_out, (a || b) ? partials : nullptr, nullptr, nullptr,
+                                                        as_stream(s), 1, extra0, extra1, extra0_is_relu ? 1 : 0,
+                                                        extra1_is_relu ? 1 : 0););
 }
 
 int npp_node_bwd_apply_striped(const npp_view4* g, const npp_view4* a, const float* gamma_a, const float* mean_a,

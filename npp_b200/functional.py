@@ -229,8 +229,13 @@ def relu(x):
     exists: the kernel that produced the state wrote relu(state) next to it (node())."""
     if isinstance(x, Pending):
         if x.relu is None:
-            _, x.relu = node(x, None, want_raw=False, want_relu=True)
-        return x.relu
+            if x.fan > 1:    # several consumers announced (set_fanout): one handle each, gradients summed in the node
+                _, rels = node(x, None, want_raw=False, want_relu=True, fan=(1, x.fan))
+                x.relu, x.spare = rels[0], list(rels[1:])
+            else:
+                _, x.relu = node(x, None, want_raw=False, want_relu=True)
+            return x.relu
+        return x.spare.pop(0) if x.spare else x.relu
     y = relu_of(x)
     if y is None:
         y = _ReluFn.apply(x)
@@ -730,15 +735,24 @@ class Pending:
     conv output), `stats` (per-channel sum / sum of squares from the conv epilogue, or None) and the BatchNorm
     module `bn`.  Consumers fold the normalisation into their own pass (node()); anything else calls
     to_internal() / finish(), which applies it once and caches the result."""
-    __slots__ = ("y", "stats", "bn", "raw", "relu")
+    __slots__ = ("y", "stats", "bn", "raw", "relu", "fan", "spare")
 
     def __init__(self, y, stats, bn):
         self.y, self.stats, self.bn = y, stats, bn
         self.raw = self.relu = None
+        self.fan, self.spare = 1, []      # consumers of relu(.) announced by set_fanout / handles not handed out yet
 
     @property
     def shape(self):
         return self.y.shape
+
+
+def set_fanout(p, n):
+    """Announces that relu(p) of a Pending BatchNorm output will be read by n consumers: each gets its own handle, so
+    their gradients are summed inside the node's backward kernel instead of by autograd add kernels."""
+    if isinstance(p, Pending) and p.relu is None:
+        p.fan = max(1, int(n))
+    return p
 
 
 def finish(p):
@@ -829,7 +843,7 @@ class _NodeFn(Function):
 
     @staticmethod
     def forward(ctx, a, ga, ba, b, gb, bb, cfg):
-        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu, pslots, want_cat = cfg
+        bn_a, st_a, bn_b, st_b, want_raw, want_relu, out_raw, out_relu, pslots, fan = cfg
         ctx.set_materialize_grads(False)
         ctx.pslots = pslots
         n, c, h, w = a.shape
@@ -880,38 +894,59 @@ class _NodeFn(Function):
         ctx.flags = (bn_a is not None, bn_b is not None, b is not None, count, sync, eval_a, eval_b)
         ctx.save_for_backward(a if bn_a is not None else None, ca, gam_a, b if bn_b is not None else None, cb, gam_b,
                               rel)
-        # second handles on the same outputs for the concat route (functional.assemble): their gradients reach
-        # backward() separately and are summed inside npp_node_bwd_reduce2 instead of by autograd's add kernels
-        raw_c = alias(raw, 0, c) if (want_cat and raw is not None) else None
-        rel_c = alias(rel, 0, c) if (want_cat and rel is not None) else None
-        return raw, rel, raw_c, rel_c
+        # One handle per CONSUMER of either output (further primitives of the cell, the concat route of
+        # functional.assemble): the consumers' gradients then reach backward() separately and are summed inside the
+        # node's own backward kernel (npp_node_bwd_reduce3) instead of by autograd's accumulation kernels.
+        n_raw = (max(1, fan[0]) if raw is not None else 0)
+        n_rel = (max(1, fan[1]) if rel is not None else 0)
+        ctx.fan = (n_raw, n_rel)
+        outs = []
+        if raw is not None:
+            outs += [raw] + [alias(raw, 0, c) for _ in range(n_raw - 1)]
+        if rel is not None:
+            outs += [rel] + [alias(rel, 0, c) for _ in range(n_rel - 1)]
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_raw, g_relu, g_raw2=None, g_relu2=None):
+    def backward(ctx, *grads):
         a, ca, gam_a, b, cb, gam_b, rel = ctx.saved_tensors
         has_a, has_b, two, count, sync, eval_a, eval_b = ctx.flags
-        if g_raw is None and g_raw2 is not None:
-            g_raw, g_raw2 = g_raw2, None
-        if g_relu is None and g_relu2 is not None:
-            g_relu, g_relu2 = g_relu2, None
-        if g_raw is None and g_relu is None:
+        n_raw, n_rel = ctx.fan
+        raws = [g for g in grads[:n_raw] if g is not None]
+        rels = [g for g in grads[n_raw:n_raw + n_rel] if g is not None]
+        if not raws and not rels:
             return None, None, None, None, None, None, None
-        like = rel if rel is not None else (a if a is not None else (g_raw if g_raw is not None else g_relu))
-        if g_raw is not None:
-            g_raw = as_internal_grad(g_raw, like)
-        if g_relu is not None:
-            g_relu = as_internal_grad(g_relu, like)
-        if g_raw2 is not None:
-            g_raw2 = as_internal_grad(g_raw2, like)
-        if g_relu2 is not None:
-            g_relu2 = as_internal_grad(g_relu2, like)
+        like = rel if rel is not None else (a if a is not None else (raws[0] if raws else rels[0]))
+        raws = [as_internal_grad(g, like) for g in raws]
+        rels = [as_internal_grad(g, like) for g in rels]
+        g_raw = raws[0] if raws else None
+        g_relu = rels[0] if rels else None
+        # up to two more gradients ride along as typed extra slots of the reduce kernel; any beyond that are folded
+        # into one of the slots first (rare: an output with more than three consumers)
+        extras = [(g, 0) for g in raws[1:]] + [(g, 1) for g in rels[1:]]
+        while len(extras) > 2:
+            g_last, k_last = extras.pop()
+            j = next((i for i, (_, k) in enumerate(extras) if k == k_last), None)
+            if j is not None:
+                extras[j] = (add(extras[j][0], g_last), k_last)
+            elif k_last:
+                g_relu = add(g_relu, g_last)
+            else:
+                g_raw = add(g_raw, g_last)
+        # the typed entry point (npp_node_bwd_reduce2: slot 0 raw, slot 1 relu) serves the striped / legacy paths
+        typed = all(k == i for i, (_, k) in enumerate(extras)) if len(extras) == 2 else (len(extras) == 1)
+        g_raw2 = g_relu2 = None
+        if extras and typed and len(extras) == 1:
+            g_raw2, g_relu2 = (None, extras[0][0]) if extras[0][1] else (extras[0][0], None)
+        elif extras and typed:
+            g_raw2, g_relu2 = extras[0][0], extras[1][0]
         ref_t = g_raw if g_raw is not None else g_relu
         n, c, h, w = ref_t.shape
         code = L.dtype_code(ref_t)
         dev = ref_t.device
         g = g_raw
         need_bn = has_a or has_b
-        combine = g_relu is not None or g_raw2 is not None
+        combine = g_relu is not None or bool(extras)
         if combine or need_bn:
             if combine:
                 g = empty_internal(n, c, h, w, ref_t.dtype, dev)
@@ -921,14 +956,13 @@ class _NodeFn(Function):
             # npp_node_bwd_reduce_atomic (per-block sums added with atomics, no partials buffer / fold kernel) was
             # measured SLOWER than partials + fold (15.7 vs 13.8 ms per step: ~600 blocks hammer the same 4C
             # addresses), so the deterministic path stays; the switch is kept for experiments
-            atomic = (need_bn and _arena.active and _state.get("node_reduce_atomics", False)
-                      and g_raw2 is None and g_relu2 is None)
+            atomic = (need_bn and _arena.active and _state.get("node_reduce_atomics", False) and not extras)
             # striped path (NPP_NODE_STRIPED=1): reduce blocks add into striped copies of the totals, the apply
             # kernel folds them and writes d beta / d gamma into the flat gradient buffer — no partials buffer, no
             # fold kernel (326 launches per step), but measured slower end to end (see _state); SyncBN needs the
             # totals between the two kernels and always takes the partials path.
             striped = (need_bn and not sync and not (eval_a or eval_b) and not atomic
-                       and _state.get("node_striped", True))
+                       and _state.get("node_striped", True) and (not extras or typed))
             if need_bn and not atomic and not striped:
                 nblk = L.lib().npp_node_bwd_blocks(i32(n), i32(h), i32(w), i32(c), i32(code))
                 parts = torch.empty(nblk * nq * c, dtype=torch.float32, device=dev)
@@ -943,8 +977,11 @@ class _NodeFn(Function):
             if striped:
                 sums = zeros_f32(_NODE_STRIPES * nq * c, dev)
                 call("npp_node_bwd_reduce2", *common2, NULL, fptr(sums), i32(_NODE_STRIPES), i32(code), stream())
-            elif g_raw2 is not None or g_relu2 is not None:
-                call("npp_node_bwd_reduce2", *common2, fptr(parts), NULL, i32(1), i32(code), stream())
+            elif extras:
+                ex = extras + [(None, 0)] * (2 - len(extras))
+                call("npp_node_bwd_reduce3", common[0], common[1], common[2],
+                     ref(view(ex[0][0])), i32(ex[0][1]), ref(view(ex[1][0])) if ex[1][0] is not None else NULL, i32(ex[1][1]),
+                     *common[3:], fptr(parts), i32(code), stream())
             elif atomic:
                 sums = zeros_f32(nq * c, dev)
                 segs = []
@@ -1047,13 +1084,16 @@ def _side(x):
     return check_raw(x, "node"), None, None
 
 
-def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None, want_cat=False):
+def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None, want_cat=False, fan=None):
     """One fused pass for a cell node (model_augment.py:48-62): a and b are internal tensors or Pending BatchNorm
     outputs; returns (raw, relu) — either None when not wanted — with `raw._npp_relu = relu` when both exist.
     out_raw / out_relu: preallocated destinations (channel slices of a concat buffer, see alias()).
     want_cat: also return second handles (raw_c, relu_c) on the same storage for the concat route — the gradient that
     comes down through the concat buffer then stays separate from the in-cell consumers' gradients until the node's
-    own backward kernel adds them (no strided autograd add)."""
+    own backward kernel adds them (no strided autograd add).
+    fan=(n_raw, n_relu): return ([raw handles], [relu handles]) with one handle per consumer of either output (the
+    general form of want_cat): every consumer's gradient reaches the node's backward kernel separately and is summed
+    there, not by autograd's accumulation kernels."""
     if b is not None and not isinstance(a, Pending) and isinstance(b, Pending):
         a, b = b, a  # keep a BatchNorm side first (the kernels take either layout; this just normalises)
     ya, bn_a, st_a = _side(a)
@@ -1081,15 +1121,28 @@ def node(a, b=None, want_raw=True, want_relu=False, out_raw=None, out_relu=None,
                 sl = None
         pslots.append(sl)
     cat_req = bool(want_cat)
-    want_cat = cat_req and _state.get("node_cat_grads", True)
-    raw, rel, raw_c, rel_c = _NodeFn.apply(ya, ga, ba, yb, gb, bb, (bn_a, st_a, bn_b, st_b, bool(want_raw),
-                                                                    bool(want_relu), out_raw, out_relu, pslots, want_cat))
-    if rel is not None:
-        rel._npp_is_relu = True   # relu(rel) is rel (no tensor ever references itself: that would leak the graph)
-        if raw is not None:
-            raw._npp_relu = rel
+    split = _state.get("node_cat_grads", True) and torch.is_grad_enabled()
+    if fan is not None:
+        n_raw, n_rel = (max(1, int(fan[0])), max(1, int(fan[1]))) if split else (1, 1)
+    else:
+        n_raw = n_rel = 2 if (cat_req and split) else 1
+    outs = _NodeFn.apply(ya, ga, ba, yb, gb, bb, (bn_a, st_a, bn_b, st_b, bool(want_raw), bool(want_relu), out_raw,
+                                                  out_relu, pslots, (n_raw, n_rel)))
+    raws = list(outs[:n_raw]) if want_raw else []
+    rels = list(outs[len(raws):]) if want_relu else []
+    for r in rels:
+        r._npp_is_relu = True   # relu(rel) is rel (no tensor ever references itself: that would leak the graph)
+    raw, rel = (raws[0] if raws else None), (rels[0] if rels else None)
+    if raw is not None and rel is not None:
+        raw._npp_relu = rel
+    if fan is not None:
+        want = (max(1, int(fan[0])), max(1, int(fan[1])))
+        # without gradient splitting every consumer simply shares the one handle
+        raws = (raws + raws[-1:] * want[0])[:want[0]] if raws else []
+        rels = (rels + rels[-1:] * want[1])[:want[1]] if rels else []
+        return raws, rels
     if cat_req:
-        return raw, rel, (raw_c if raw_c is not None else raw), (rel_c if rel_c is not None else rel)
+        return raw, rel, (raws[1] if len(raws) > 1 else raw), (rels[1] if len(rels) > 1 else rel)
     return raw, rel
 
 
@@ -1123,7 +1176,9 @@ class _AssembleFn(Function):
 
 
 def assemble(buf, slices):
-    return _AssembleFn.apply([buf], *slices)
+    """A handle on the concat buffer `buf` whose channel slices are `slices` (a fresh tensor on the same storage per
+    call: a cell output with several consumers is assembled once per consumer, each from its own slice handles)."""
+    return _AssembleFn.apply([alias(buf, 0, buf.shape[1])], *slices)
 
 # ------------------------------------------------------------------------------------------------
 # add / concat

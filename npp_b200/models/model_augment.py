@@ -110,20 +110,28 @@ class _StepCell(nn.Module):
             out.append((raw, rel, member.get(k)))
         return out
 
-    def _run_fused(self, pre, concats, out_raw=True, out_relu=False):
+    def _run_fused(self, pre, concats, out_raw=True, out_relu=False, n_out=None):
         """Evaluates the cell with one fused pass per state (functional.node): BatchNorm-apply of both operands,
         the add, the ReLU of the consumers and the write into the output concat buffer(s).
-        pre: outputs of the preprocess layers (Pending BatchNorm outputs); returns one handle per concat."""
+        pre: outputs of the preprocess layers (Pending BatchNorm outputs); returns one handle per concat — or, with
+        n_out = [k per concat], a list of k handles per concat, one per CONSUMER of that cell output (the gradients
+        of the consumers then meet inside the member nodes' backward kernels, not in autograd add kernels)."""
         nstates = len(pre) + self._steps
+        n_out = [max(1, int(k)) for k in n_out] if n_out is not None else None
         if not (out_raw or out_relu):
             raise ValueError("a cell must produce its output raw, through ReLU, or both")
         needs = self._needs(nstates, concats, out_raw, out_relu)
         if needs is None:
             states = self._run_steps([F_.finish(p) for p in pre])
-            return [F_.cat([states[i] for i in cat]) for cat in concats]
+            outs = [F_.cat([states[i] for i in cat]) for cat in concats]
+            return [[o] * n_out[cid] for cid, o in enumerate(outs)] if n_out is not None else outs
         bufs = {}      # (concat id, "raw" | "relu") -> buffer
         slices = {}    # same key -> list of slice tensors in slot order
-        handles = []
+        handles = []   # per state: {op index: the handle that primitive reads}
+        # which of {state, relu(state)} every primitive reads (decides the per-consumer handles below)
+        readers = [[] for _ in range(nstates)]
+        for j, (op, idx) in enumerate(zip(self._ops, self._indices)):
+            readers[idx].append((j, self._kind(op)))
 
         def emit(k, a, b):
             raw_w, rel_w, mem = needs[k]
@@ -137,38 +145,57 @@ class _StepCell(nn.Module):
                         continue
                     if (cid, key) not in bufs:
                         bufs[(cid, key)] = F_.empty_internal(n, c * len(concats[cid]), h, w, ya.dtype, ya.device)
-                        slices[(cid, key)] = [None] * len(concats[cid])
+                        slices[(cid, key)] = [[None] * len(concats[cid]) for _ in range(n_out[cid] if n_out else 1)]
                     t = F_.alias(bufs[(cid, key)], slot * c, c)
                     if key == "raw":
                         o_raw = t
                     else:
                         o_rel = t
-            if o_raw is not None or o_rel is not None:
-                # concat member: the concat buffer gets its own handles, so the gradient coming down through the cell
-                # output is summed with the in-cell consumers' gradients inside the node's backward kernel
-                raw, rel, raw_c, rel_c = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel,
-                                                 want_cat=True)
+            # One handle per consumer (primitives of this cell reading the state raw / through nn.ReLU, plus the concat
+            # route): each consumer's gradient reaches the node's backward kernel on its own and is summed there
+            # instead of by autograd's add kernels.
+            reads = []
+            for j, kind in readers[k]:
+                if kind == "relu" or (kind == "relu_ok" and rel_w):
+                    reads.append((j, "relu"))
+                else:
+                    reads.append((j, "raw"))
+            n_cat = (n_out[mem[0]] if n_out else 1) if mem is not None else 0
+            n_raw = sum(1 for _, t in reads if t == "raw") + (n_cat if o_raw is not None else 0)
+            n_rel = sum(1 for _, t in reads if t == "relu") + (n_cat if o_rel is not None else 0)
+            raws, rels = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel,
+                                 fan=(n_raw, n_rel))
+            raws, rels = list(raws), list(rels)
+            for q in range(n_cat):                                  # the concat route(s) take the last handles
                 if o_raw is not None:
-                    slices[(mem[0], "raw")][mem[1]] = raw_c
+                    slices[(mem[0], "raw")][q][mem[1]] = raws.pop()
                 if o_rel is not None:
-                    slices[(mem[0], "relu")][mem[1]] = rel_c
-            else:
-                raw, rel = F_.node(a, b, want_raw=raw_w, want_relu=rel_w, out_raw=o_raw, out_relu=o_rel)
-            handles.append(F_.state_handle(raw, rel))
+                    slices[(mem[0], "relu")][q][mem[1]] = rels.pop()
+            per_op = {}
+            for j, t in reads:
+                if t == "relu":
+                    per_op[j] = F_.state_handle(None, rels.pop(0))
+                else:
+                    per_op[j] = F_.state_handle(raws.pop(0), None)
+            handles.append(per_op)
 
         for k, p in enumerate(pre):
             emit(k, p, None)
         for i in range(self._steps):
-            a = call_lazy(self._ops[2 * i], handles[self._indices[2 * i]])
-            b = call_lazy(self._ops[2 * i + 1], handles[self._indices[2 * i + 1]])
+            ja, jb = 2 * i, 2 * i + 1
+            a = call_lazy(self._ops[ja], handles[self._indices[ja]][ja])
+            b = call_lazy(self._ops[jb], handles[self._indices[jb]][jb])
             emit(len(pre) + i, a, b)
         outs = []
         for cid in range(len(concats)):
-            raw = F_.assemble(bufs[(cid, "raw")], slices[(cid, "raw")]) if (cid, "raw") in bufs else None
-            rel = F_.assemble(bufs[(cid, "relu")], slices[(cid, "relu")]) if (cid, "relu") in bufs else None
-            if raw is not None and rel is not None:
-                raw._npp_relu = rel
-            outs.append(F_.state_handle(raw, rel))
+            hs = []
+            for q in range(n_out[cid] if n_out else 1):
+                raw = F_.assemble(bufs[(cid, "raw")], slices[(cid, "raw")][q]) if (cid, "raw") in bufs else None
+                rel = F_.assemble(bufs[(cid, "relu")], slices[(cid, "relu")][q]) if (cid, "relu") in bufs else None
+                if raw is not None and rel is not None:
+                    raw._npp_relu = rel
+                hs.append(F_.state_handle(raw, rel))
+            outs.append(hs if n_out else hs[0])
         return outs
 
 
@@ -194,9 +221,10 @@ class Cell(_StepCell):
     def _stride_for(self, index):
         return 2 if self._reduction and index < 2 else 1
 
-    def forward(self, s0, s1, out_raw=True, out_relu=False):
+    def forward(self, s0, s1, out_raw=True, out_relu=False, n_out=None):
+        """n_out = k: returns k handles on the cell output, one per consumer (see _run_fused)."""
         return self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1)],
-                               [list(self._concat)], out_raw, out_relu)[0]
+                               [list(self._concat)], out_raw, out_relu, [n_out] if n_out else None)[0]
 
 
 class Upsample(_StepCell):
@@ -243,7 +271,8 @@ class _FusionCell(_StepCell):
 
         self._build_ops(C_cur, edges, wrap=wrap)
 
-    def forward(self, s0, s1, s2, out_raw=True, out_relu=False):
+    def forward(self, s0, s1, s2, out_raw=True, out_relu=False, n_out=None):
+        """n_out = (k1, k2): k1 handles on fea1 and k2 on fea2, one per consumer (see _run_fused)."""
         if self.order == 0:  # model_augment.py:164-166: default-mode (nearest) F.interpolate; unused by Network
             states = self._run_steps([self.preprocess0(s0), self.preprocess1(s1), self.preprocess2(s2)])
             states[0] = F_.interpolate(states[0], scale_factor=4)
@@ -251,7 +280,7 @@ class _FusionCell(_StepCell):
             return F_.cat(states[0:3]), F_.cat([states[i] for i in self._concat])
         fea1, fea2 = self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1),
                                       call_lazy(self.preprocess2, s2)], [[0, 1, 2], list(self._concat)],
-                                     out_raw, out_relu)
+                                     out_raw, out_relu, list(n_out) if n_out else None)
         return fea1, fea2
 
 
@@ -447,12 +476,18 @@ class Network(nn.Module):
         self._tr("stem5", s3)
         f1, f2 = [], []           # per-stream feature pyramids (fine -> coarse, then decoder outputs)
         c1 = c2 = stage = 0
+        n1 = n3 = None            # second handle on the previous cell output (read as `s0` by the cell after next)
         for i, (cell1, cell2) in enumerate(zip(self.cells1, self.cells2)):
             # every encoder cell feeds the next two cells' preprocess layers (nn.ReLU first); only the tapped ones
-            # are also read raw (interaction ops, decoder, multi-scale concat)
+            # are also read raw (interaction ops, decoder, multi-scale concat).  A cell output that is read by exactly
+            # those two consumers is handed out as two handles (n_out=2): their gradients are then summed inside the
+            # backward kernels of the member nodes instead of by an autograd add over the whole 4C-channel tensor.
             tap = i in self._tap_layers
-            s0, s1 = s1, cell1(s0, s1, out_raw=tap, out_relu=True)
-            s2, s3 = s3, cell2(s2, s3, out_raw=tap, out_relu=True)
+            two = (not tap) and i + 2 < len(self.cells1) and self._trace is None
+            o1 = cell1(s0, s1, out_raw=tap, out_relu=True, n_out=2 if two else None)
+            o3 = cell2(s2, s3, out_raw=tap, out_relu=True, n_out=2 if two else None)
+            s0, s2 = (n1 if n1 is not None else s1), (n3 if n3 is not None else s3)
+            (s1, n1), (s3, n3) = (o1, o3) if two else ((o1, None), (o3, None))
             self._tr("relu(cells1.%d)" % i, s1, relu=True)
             self._tr("relu(cells2.%d)" % i, s3, relu=True)
             if i in self._tap_layers:
@@ -496,6 +531,9 @@ class Network(nn.Module):
         in2 = self.edge_layer.lazy(x2)
         in3 = self.pose_layer.lazy(x1)
         in4 = self.par_layer.lazy(x2)
+        split = self.refine_layers == 1 and self._trace is None
+        if split:   # relu(bn(.)) of the four layer outputs is read by a head and by one / two refinement cells each
+            F_.set_fanout(in1, 2), F_.set_fanout(in2, 2), F_.set_fanout(in3, 3), F_.set_fanout(in4, 3)
         for nm, t in (("relu(pose_auxlayer)", in1), ("relu(edge_layer)", in2), ("relu(pose_layer)", in3),
                       ("relu(par_layer)", in4)):
             self._tr(nm, t, relu=True)
@@ -511,12 +549,20 @@ class Network(nn.Module):
             par_list.append([F_.from_internal(par_map, self._num_classes), F_.from_internal(edge, 2)])
 
         emit(0)
+        in3b, in4b = in3, in4     # the handles the parsing cell reads (own ones when the outputs were split per consumer)
         for i in range(1, self.refine_layers + 1):
             for j in range(3):
-                # refinement-cell outputs are read by preprocess layers and heads only (nn.ReLU first)
-                in1, tmp = self.pose_net[2 * (i - 1) + j](in1, in3, in4, out_raw=False, out_relu=True)
-                in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4, out_raw=False, out_relu=True)
-                in3 = tmp
+                # refinement-cell outputs are read by preprocess layers and heads only (nn.ReLU first).  fea2 of either
+                # cell feeds BOTH cells of the next step: two handles (n_out), so the two gradients of these 4C-channel
+                # tensors are summed inside the member nodes' backward kernels, not by an autograd add
+                n_out = (1, 2) if (split and j < 2) else None
+                o1, t3 = self.pose_net[2 * (i - 1) + j](in1, in3, in4, out_raw=False, out_relu=True, n_out=n_out)
+                o2, t4 = self.par_net[2 * (i - 1) + j](in2, in3b, in4b, out_raw=False, out_relu=True, n_out=n_out)
+                if n_out:
+                    in1, in2, (in3, in3b), (in4, in4b) = o1[0], o2[0], t3, t4
+                else:
+                    in1, in2, in3, in4 = o1, o2, t3, t4
+                    in3b, in4b = in3, in4
                 k = 2 * (i - 1) + j
                 for nm, t in (("relu(pose_net.%d.fea1)" % k, in1), ("relu(pose_net.%d.fea2)" % k, in3),
                               ("relu(par_net.%d.fea1)" % k, in2), ("relu(par_net.%d.fea2)" % k, in4)):

@@ -60,9 +60,10 @@ def test_derived_network_call_flow(recorder):
     bwd = recorder.get("npp_node_bwd_apply", 0) + recorder.get("npp_node_bwd_apply_striped", 0)
     assert fwd > 100 and bwd > 100
     assert recorder.get("npp_node_fwd_bn", 0) > 100
-    # concat members hand the gradient that comes down through the cell output to the node as a second input
-    assert recorder.get("npp_node_bwd_reduce2", 0) > 20
-    assert recorder.get("npp_node_bwd_reduce", 0) + recorder.get("npp_node_bwd_reduce2", 0) >= bwd
+    # every consumer of a cell state (further primitives, the concat route) has its own handle: the extra gradients
+    # reach the node's backward kernel as typed slots (npp_node_bwd_reduce3) instead of autograd add kernels
+    assert recorder.get("npp_node_bwd_reduce3", 0) > 60
+    assert recorder.get("npp_node_bwd_reduce", 0) + recorder.get("npp_node_bwd_reduce3", 0) >= bwd
     # parameters never used by the forward get no gradient (SE_Block.bn at stride 1: SURVEY.md §5, find_unused_parameters)
     unused = [k for k, p in net.named_parameters() if p.grad is None]
     assert unused and all(".bn." in k for k in unused)
