@@ -27,6 +27,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, double count,
                                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd, int C, int C_run) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = (double)sums[c] / count;
@@ -50,6 +51,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, double count,
 __global__ void bn_eval_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                     float* __restrict__ scale, float* __restrict__ shift, int C) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = rsqrtf(rv[c] + eps);
@@ -178,7 +180,7 @@ int npp_bn_finalize(const float* sums, double count, const float* gamma, const f
                     float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                     float* save_invstd, int c, int c_running, npp_stream_t s) {
   if (!sums || !scale || !shift || c <= 0 || count <= 0 || c_running > c) return NPP_E_INVALID;
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(s)>>>(sums, count, gamma, beta, running_mean, running_var,
+  NPP_LAUNCH((bn_finalize_kernel), (c + 127) / 128, 128, 0, as_stream(s), sums, count, gamma, beta, running_mean, running_var,
                                                                 momentum, eps, scale, shift, save_mean, save_invstd, c, c_running);
   NPP_CHECK_LAUNCH("bn_finalize_kernel");
   return NPP_OK;
@@ -186,7 +188,7 @@ int npp_bn_finalize(const float* sums, double count, const float* gamma, const f
 int npp_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      float eps, float* scale, float* shift, int c, npp_stream_t s) {
   if (!running_mean || !running_var || !scale || !shift || c <= 0) return NPP_E_INVALID;
-  bn_eval_coef_kernel<<<(c + 127) / 128, 128, 0, as_stream(s)>>>(gamma, beta, running_mean, running_var, eps, scale,
+  NPP_LAUNCH((bn_eval_coef_kernel), (c + 127) / 128, 128, 0, as_stream(s), gamma, beta, running_mean, running_var, eps, scale,
                                                                  shift, c);
   NPP_CHECK_LAUNCH("bn_eval_coef_kernel");
   return NPP_OK;

@@ -24,6 +24,34 @@ void count_launch(int n);  // kernel-launch counter behind npp_launch_count()
 
 static inline cudaStream_t as_stream(npp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A training step is ~3 600 mostly short kernels in one stream / one CUDA graph; between two dependent kernels the
+// GPU otherwise drains, flushes and only then launches the next grid (~2-2.5 us per launch, measured on the tiny
+// fold / fill kernels).  Every kernel of this library is launched with programmatic stream serialization: the next
+// grid may be scheduled while the previous one is still finishing, and blocks at `pdl_wait()` — the first statement
+// of every kernel (after the barrier / TMEM / tensor-map set-up in the tcgen05 kernels) — until the previous grid has
+// completed and its memory is visible.  Every thread of every block executes the wait before it touches global
+// memory or exits, so completion stays transitive along the stream (C after B after A).  The launch attribute is
+// captured into CUDA graphs as a programmatic edge.  NPP_PDL=0 launches everything fully serialized (A/B, bisecting).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in NPP_CHECK_LAUNCH
+}
+#define NPP_LAUNCH(kernel, grid, block, smem, st, ...) ::npp::launch_k(kernel, grid, block, smem, st, ##__VA_ARGS__)
+
 // ---- dtype traits: storage T, math in fp32 ---------------------------------------------------
 template <typename T> struct VecOf;  // 16-byte vector of T
 template <> struct VecOf<float> { static constexpr int N = 4; };

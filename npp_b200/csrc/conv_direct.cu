@@ -11,6 +11,7 @@ __global__ void direct_fwd_kernel(const T* __restrict__ x, const WT* __restrict_
                                   T* __restrict__ y, int N, int H, int W, int Cin, int64_t xsn, int64_t xsh,
                                   int64_t xsw, int Ho, int Wo, int Cout, int64_t ysn, int64_t ysh, int64_t ysw, int kh,
                                   int kw, int stride, int pad, int dil, int hoff, int woff) {
+  pdl_wait();
   const int64_t total = (int64_t)N * Ho * Wo * Cout;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
@@ -40,6 +41,7 @@ __global__ void direct_dgrad_kernel(const T* __restrict__ dy, const WT* __restri
                                     int H, int W, int Cin, int64_t xsn, int64_t xsh, int64_t xsw, int Ho, int Wo,
                                     int Cout, int64_t ysn, int64_t ysh, int64_t ysw, int kh, int kw, int stride,
                                     int pad, int dil, int hoff, int woff) {
+  pdl_wait();
   const int64_t total = (int64_t)N * H * W * Cin;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin);
@@ -74,6 +76,7 @@ __global__ void direct_wgrad_kernel(const T* __restrict__ x, const T* __restrict
                                     int H, int W, int64_t xsn, int64_t xsh, int64_t xsw, int Ho, int Wo,
                                     int64_t ysn, int64_t ysh, int64_t ysw, int dw_cout, int dw_cin, int kh, int kw,
                                     int stride, int pad, int dil, int hoff, int woff, int pix_per_chunk) {
+  pdl_wait();
   const int64_t total = (int64_t)dw_cout * kh * kw * dw_cin;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // OIHW index
   if (i >= total) return;
@@ -108,7 +111,7 @@ template <typename T, typename WT>
 static int direct_fwd_t(const npp_view4* x, const void* w, const float* bias, const npp_view4* y, int kh, int kw,
                         int stride, int pad, int dil, int hoff, int woff, cudaStream_t st) {
   const int64_t total = (int64_t)y->n * y->h * y->w * y->c;
-  direct_fwd_kernel<T, WT><<<grid_for(total), 256, 0, st>>>(
+  NPP_LAUNCH((direct_fwd_kernel<T, WT>), grid_for(total), 256, 0, st, 
       static_cast<const T*>(x->ptr), static_cast<const WT*>(w), bias, static_cast<T*>(y->ptr), x->n, x->h, x->w, x->c,
       x->sn, x->sh, x->sw, y->h, y->w, y->c, y->sn, y->sh, y->sw, kh, kw, stride, pad, dil, hoff, woff);
   NPP_CHECK_LAUNCH("direct_fwd_kernel");
@@ -118,7 +121,7 @@ template <typename T, typename WT>
 static int direct_dgrad_t(const npp_view4* dy, const void* w, const npp_view4* dx, int kh, int kw, int stride, int pad,
                           int dil, int hoff, int woff, cudaStream_t st) {
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * dx->c;
-  direct_dgrad_kernel<T, WT><<<grid_for(total), 256, 0, st>>>(
+  NPP_LAUNCH((direct_dgrad_kernel<T, WT>), grid_for(total), 256, 0, st, 
       static_cast<const T*>(dy->ptr), static_cast<const WT*>(w), static_cast<T*>(dx->ptr), dx->n, dx->h, dx->w, dx->c,
       dx->sn, dx->sh, dx->sw, dy->h, dy->w, dy->c, dy->sn, dy->sh, dy->sw, kh, kw, stride, pad, dil, hoff, woff);
   NPP_CHECK_LAUNCH("direct_dgrad_kernel");
@@ -131,7 +134,7 @@ static int direct_wgrad_t(const npp_view4* x, const npp_view4* dy, float* dw, in
   const int64_t npix = (int64_t)dy->n * dy->h * dy->w;
   const int chunk = 2048;
   dim3 grid((unsigned)((total + 127) / 128), (unsigned)((npix + chunk - 1) / chunk));
-  direct_wgrad_kernel<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x->ptr), static_cast<const T*>(dy->ptr), dw, x->n,
+  NPP_LAUNCH((direct_wgrad_kernel<T>), grid, 128, 0, st, static_cast<const T*>(x->ptr), static_cast<const T*>(dy->ptr), dw, x->n,
                                               x->h, x->w, x->sn, x->sh, x->sw, dy->h, dy->w, dy->sn, dy->sh, dy->sw,
                                               dw_cout, dw_cin, kh, kw, stride, pad, dil, hoff, woff, chunk);
   NPP_CHECK_LAUNCH("direct_wgrad_kernel");

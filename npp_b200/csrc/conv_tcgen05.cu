@@ -77,6 +77,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
                  const float* __restrict__ bias, float* __restrict__ stats) {
+  pdl_wait();
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -443,6 +444,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
                   const float* __restrict__ bias, float* __restrict__ stats) {
+  pdl_wait();
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -631,6 +633,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* __restrict__ bias,
              float* __restrict__ stats) {
+  pdl_wait();
   constexpr int B_BYTES = BN * 128;
   constexpr int TMEM_COLS = 4 * BN;  // 2 accumulator stages x 2 pixel halves; 128 / 256 / 512
   constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
@@ -862,6 +865,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTable taps,
                   float* __restrict__ dw, float* __restrict__ ws) {
+  pdl_wait();
   using Cfg = WgradCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int SLAB = Cfg::KP * 128;  // bytes of one [64 pixels x 64 channels] slab
@@ -1029,6 +1033,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                    const W3Geom g, float* __restrict__ dw, float* __restrict__ ws) {
+  pdl_wait();
   constexpr int A_BYTES = 2 * 64 * 128;  // two 64-channel slabs of dY, 64 pixels each
   constexpr int ASLAB = 64 * 128;
   constexpr int TMEM_COLS = (3 * BN <= 256) ? 256 : 512;
@@ -1179,6 +1184,7 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit, int tiles, int R, int BN,
                     int co_blocks, int ci_blocks, int cout, int cin, int num_taps, const TapTable taps, int mode3,
                     int kgroups) {
+  pdl_wait();
   // block = E consecutive elements x kgroups k groups (E * kgroups == 256): with many k slices (50-150, each
   // per_slice floats apart) one thread per element would walk them serially, so up to 8 threads share an element
   // and fold through shared memory; with few slices kgroups == 1 and every thread owns an element.
@@ -1236,7 +1242,7 @@ static int launch_wgrad_reduce(const float* ws, float* dw, int ksplit, int tiles
   const int E = 256 / kgroups;
   int64_t blocks = per_slice / E;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, dw, ksplit, tiles, R, BN, co_blocks, ci_blocks, cout, cin,
+  NPP_LAUNCH((wgrad_reduce_kernel), (unsigned)blocks, 256, 0, st, ws, dw, ksplit, tiles, R, BN, co_blocks, ci_blocks, cout, cin,
                                                         num_taps, taps, mode3, kgroups);
   NPP_CHECK_LAUNCH("wgrad_reduce_kernel");
   return NPP_OK;
@@ -1366,11 +1372,11 @@ static int launch_fprop(const Maps& maps, const Geom& g, const TapTable& taps, c
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm2)", e); return NPP_E_CUDA; }
       attr2_set = true;
     }
-    conv_gemm2_kernel<BN><<<grid, kThreads2, Cfg::SMEM, st>>>(maps, g, taps, bias, stats);
+    NPP_LAUNCH((conv_gemm2_kernel<BN>), grid, kThreads2, Cfg::SMEM, st, maps, g, taps, bias, stats);
     NPP_CHECK_LAUNCH("conv_gemm2_kernel");
     return NPP_OK;
   }
-  conv_gemm_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, bias, stats);
+  NPP_LAUNCH((conv_gemm_kernel<BN>), grid, kThreads, Cfg::SMEM, st, maps, g, taps, bias, stats);
   NPP_CHECK_LAUNCH("conv_gemm_kernel");
   return NPP_OK;
 }
@@ -1452,7 +1458,7 @@ static int launch_conv3(const C3Maps& maps, const C3Geom& g, int smem, const flo
   }
   int grid = sm_count();
   if (grid > g.num_ptiles) grid = g.num_ptiles;
-  conv3_kernel<BN><<<grid, kThreads2, smem, st>>>(maps, g, bias, stats);
+  NPP_LAUNCH((conv3_kernel<BN>), grid, kThreads2, smem, st, maps, g, bias, stats);
   NPP_CHECK_LAUNCH("conv3_kernel");
   return NPP_OK;
 }
@@ -1644,7 +1650,7 @@ static int launch_wgrad(const WMaps& maps, const WGeom& g, const TapTable& taps,
   // one k slice: its atomics are the only writers anyway; narrow layers (<= 64 x 64): most of the 128 x BN tile is
   // masked out, the few atomics are cheaper than storing and re-reading whole tiles
   if (g.ksplit == 1 || need > ws_bytes || (g.cout <= 64 && g.cin <= 64)) ws = nullptr;
-  conv_wgrad_kernel<BN><<<grid, kThreads, Cfg::SMEM, st>>>(maps, g, taps, dw, ws);
+  NPP_LAUNCH((conv_wgrad_kernel<BN>), grid, kThreads, Cfg::SMEM, st, maps, g, taps, dw, ws);
   NPP_CHECK_LAUNCH("conv_wgrad_kernel");
   if (ws)
     return launch_wgrad_reduce(ws, dw, g.ksplit, (int)grid.x, 1, BN, g.co_blocks, g.ci_blocks, g.cout, g.cin,
@@ -1668,7 +1674,7 @@ static int launch_wgrad3(const CUtensorMap& mx, const CUtensorMap& mdy, const W3
   dim3 grid(3 * g.co_blocks * g.ci_blocks, g.ksplit);
   const size_t need = (size_t)grid.x * grid.y * 3 * 128 * BN * sizeof(float);
   if (g.ksplit == 1 || need > ws_bytes || (g.cout <= 64 && g.cin <= 64)) ws = nullptr;
-  conv_wgrad3_kernel<BN><<<grid, kThreads, smem, st>>>(mx, mdy, g, dw, ws);
+  NPP_LAUNCH((conv_wgrad3_kernel<BN>), grid, kThreads, smem, st, mx, mdy, g, dw, ws);
   NPP_CHECK_LAUNCH("conv_wgrad3_kernel");
   if (ws) {
     TapTable none;
@@ -1807,6 +1813,7 @@ int conv_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int dw_cout, 
 template <typename D>
 __global__ void pack_weight_kernel(const float* __restrict__ w32, D* __restrict__ w, D* __restrict__ wt, int cout,
                                    int taps, int cin, int cout_pad, int cin_pad) {
+  pdl_wait();
   const int64_t total = (int64_t)cout_pad * taps * cin_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin_pad);
@@ -1844,6 +1851,7 @@ __device__ __forceinline__ float pair_weight(const float* __restrict__ w32, int 
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const PackTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
                           const int* __restrict__ chunk_index, int chunk_elems) {
+  pdl_wait();
   const PackTensor t = tensors[chunk_tensor[blockIdx.x]];
   if (t.pad_ == 1) {
     const int total = 64 * 9 * 64;
@@ -1882,6 +1890,7 @@ constexpr int kPackTapsMax = 9;
 __global__ void __launch_bounds__(256)
 pack_weights_tiles_kernel(const PackTensor* __restrict__ tensors, const int* __restrict__ tile_tensor,
                           const int* __restrict__ tile_index) {
+  pdl_wait();
   __shared__ float tile[32 * (32 * kPackTapsMax + 1)];
   const PackTensor t = tensors[tile_tensor[blockIdx.x]];
   const int ci_tiles = (t.cin_pad + 31) / 32;
@@ -1917,7 +1926,7 @@ int pack_weights_tiles(const void* table, int ntensors, const int* tile_tensor, 
                        cudaStream_t st) {
   if (!table || !tile_tensor || !tile_index || ntensors <= 0 || ntiles < 0) return NPP_E_INVALID;
   if (ntiles == 0) return NPP_OK;
-  pack_weights_tiles_kernel<<<ntiles, 256, 0, st>>>(static_cast<const PackTensor*>(table), tile_tensor, tile_index);
+  NPP_LAUNCH((pack_weights_tiles_kernel), ntiles, 256, 0, st, static_cast<const PackTensor*>(table), tile_tensor, tile_index);
   NPP_CHECK_LAUNCH("pack_weights_tiles_kernel");
   return NPP_OK;
 }
@@ -1926,7 +1935,7 @@ int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor,
                        int chunk_elems, cudaStream_t st) {
   if (!table || !chunk_tensor || !chunk_index || ntensors <= 0 || nchunks < 0 || chunk_elems <= 0) return NPP_E_INVALID;
   if (nchunks == 0) return NPP_OK;
-  pack_weights_multi_kernel<<<nchunks, 256, 0, st>>>(static_cast<const PackTensor*>(table), chunk_tensor, chunk_index,
+  NPP_LAUNCH((pack_weights_multi_kernel), nchunks, 256, 0, st, static_cast<const PackTensor*>(table), chunk_tensor, chunk_index,
                                                      chunk_elems);
   NPP_CHECK_LAUNCH("pack_weights_multi_kernel");
   return NPP_OK;
@@ -1935,6 +1944,7 @@ int pack_weights_multi(const void* table, int ntensors, const int* chunk_tensor,
 // dW[co, ci, r, s] += sum over the pair-layout entries that carry that tap (inverse of pair_weight): the weight
 // gradient of the 64 -> 64 super-pixel convolution folded back onto the 32 x 32 x 3 x 3 master gradient.
 __global__ void __launch_bounds__(256) fold_pair_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (co, ci, r, s)
   if (i >= 32 * 32 * 9) return;
   const int s = i % 3, r = (i / 3) % 3, ci = (i / 9) & 31, co = i / (9 * 32);
@@ -1955,7 +1965,7 @@ __global__ void __launch_bounds__(256) fold_pair_wgrad_kernel(const float* __res
 
 int fold_pair_wgrad(const float* dwp, float* dw, cudaStream_t st) {
   if (!dwp || !dw) return NPP_E_INVALID;
-  fold_pair_wgrad_kernel<<<(32 * 32 * 9 + 255) / 256, 256, 0, st>>>(dwp, dw);
+  NPP_LAUNCH((fold_pair_wgrad_kernel), (32 * 32 * 9 + 255) / 256, 256, 0, st, dwp, dw);
   NPP_CHECK_LAUNCH("fold_pair_wgrad_kernel");
   return NPP_OK;
 }
@@ -1963,6 +1973,7 @@ int fold_pair_wgrad(const float* dwp, float* dw, cudaStream_t st) {
 // one-off packing of a single pair-layout weight (tests; the per-step path is pack_weights_multi with pad_ = 1)
 __global__ void __launch_bounds__(256) pack_pair_kernel(const float* __restrict__ w32, __nv_bfloat16* __restrict__ w,
                                                         __nv_bfloat16* __restrict__ wt) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 9 * 64) return;
   const int col = i & 63, tap = (i >> 6) % 9, row = i / (64 * 9);
@@ -1973,7 +1984,7 @@ __global__ void __launch_bounds__(256) pack_pair_kernel(const float* __restrict_
 
 int pack_weight_pair(const float* w32, void* w, void* wt, cudaStream_t st) {
   if (!w32 || (!w && !wt)) return NPP_E_INVALID;
-  pack_pair_kernel<<<(64 * 9 * 64 + 255) / 256, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w),
+  NPP_LAUNCH((pack_pair_kernel), (64 * 9 * 64 + 255) / 256, 256, 0, st, w32, static_cast<__nv_bfloat16*>(w),
                                                               static_cast<__nv_bfloat16*>(wt));
   NPP_CHECK_LAUNCH("pack_pair_kernel");
   return NPP_OK;
@@ -1987,11 +1998,11 @@ int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin
   int grid = (int)((total + 255) / 256);
   if (grid > 4096) grid = 4096;
   if (out_dtype == NPP_BF16)
-    pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w32, static_cast<__nv_bfloat16*>(w),
+    NPP_LAUNCH((pack_weight_kernel<__nv_bfloat16>), grid, 256, 0, st, w32, static_cast<__nv_bfloat16*>(w),
                                                              static_cast<__nv_bfloat16*>(wt), cout, taps, cin, cout_pad,
                                                              cin_pad);
   else if (out_dtype == NPP_F32)
-    pack_weight_kernel<float><<<grid, 256, 0, st>>>(w32, static_cast<float*>(w), static_cast<float*>(wt), cout, taps,
+    NPP_LAUNCH((pack_weight_kernel<float>), grid, 256, 0, st, w32, static_cast<float*>(w), static_cast<float*>(wt), cout, taps,
                                                     cin, cout_pad, cin_pad);
   else
     return NPP_E_UNSUPPORTED;

@@ -78,6 +78,7 @@ template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, const float* __restrict__ wgt,
                                                       const DView<T> Y, const DView<const T> M, const DwTileGeom g,
                                                       int relu_in) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   extern __shared__ uint4 dw_tile_smem[];
   uint4* tile = dw_tile_smem;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, co
 template <typename T>
 __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T> X, const DView<const T> DY,
                                                             float* __restrict__ dw, const DwTileGeom g, int relu_in) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   extern __shared__ uint4 dw_tile_smem[];
   uint4* tile = dw_tile_smem;
@@ -262,6 +264,7 @@ template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, const float* __restrict__ wgt,
                                                       const DView<T> Y, const DView<const T> M, const DwTileGeom g,
                                                       int relu_in, int tile_elems) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   extern __shared__ uint4 dw_tile_smem[];
   const int cb = blockIdx.x % g.cblocks;
@@ -344,6 +347,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T> X, const DView<const T> DY,
                                                             float* __restrict__ dw, const DwTileGeom g, int relu_in,
                                                             int tile_elems) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   extern __shared__ uint4 dw_tile_smem[];
   const int cb = blockIdx.x % g.cblocks;
@@ -512,14 +516,14 @@ int dw_tile_fwd(const npp_view4* x, const float* w, const npp_view4* y, int stri
     int rc = dw_set_smem2<sizeof(T) * 10 + 3>(dw_pipe_kernel<T, false>, "cudaFuncSetAttribute(dw_pipe_fwd)");
     if (rc) return rc;
     dw_pipe_slots(g);
-    dw_pipe_kernel<T, false><<<g.slots * g.cblocks, 256, 2 * smem, st>>>(X, w, dview<T>(y), X, g, relu_in,
+    NPP_LAUNCH((dw_pipe_kernel<T, false>), g.slots * g.cblocks, 256, 2 * smem, st, X, w, dview<T>(y), X, g, relu_in,
                                                                          (int)(smem / 16));
     NPP_CHECK_LAUNCH("dw_pipe_fwd");
     return NPP_OK;
   }
   int rc = dw_set_smem<sizeof(T) * 10 + 0>(dw_tile_kernel<T, false>, "cudaFuncSetAttribute(dw_tile_fwd)");
   if (rc) return rc;
-  dw_tile_kernel<T, false><<<g.ntiles * g.cblocks, 256, smem, st>>>(X, w, dview<T>(y), X, g, relu_in);
+  NPP_LAUNCH((dw_tile_kernel<T, false>), g.ntiles * g.cblocks, 256, smem, st, X, w, dview<T>(y), X, g, relu_in);
   NPP_CHECK_LAUNCH("dw_tile_fwd");
   return NPP_OK;
 }
@@ -537,14 +541,14 @@ int dw_tile_dgrad(const npp_view4* x, const float* w, const npp_view4* dy, const
     int rc = dw_set_smem2<sizeof(T) * 10 + 4>(dw_pipe_kernel<T, true>, "cudaFuncSetAttribute(dw_pipe_dgrad)");
     if (rc) return rc;
     dw_pipe_slots(g);
-    dw_pipe_kernel<T, true><<<g.slots * g.cblocks, 256, 2 * smem, st>>>(dview<const T>(dy), w, dview<T>(dx),
+    NPP_LAUNCH((dw_pipe_kernel<T, true>), g.slots * g.cblocks, 256, 2 * smem, st, dview<const T>(dy), w, dview<T>(dx),
                                                                         dview<const T>(x), g, relu_in, (int)(smem / 16));
     NPP_CHECK_LAUNCH("dw_pipe_dgrad");
     return NPP_OK;
   }
   int rc = dw_set_smem<sizeof(T) * 10 + 1>(dw_tile_kernel<T, true>, "cudaFuncSetAttribute(dw_tile_dgrad)");
   if (rc) return rc;
-  dw_tile_kernel<T, true><<<g.ntiles * g.cblocks, 256, smem, st>>>(dview<const T>(dy), w, dview<T>(dx),
+  NPP_LAUNCH((dw_tile_kernel<T, true>), g.ntiles * g.cblocks, 256, smem, st, dview<const T>(dy), w, dview<T>(dx),
                                                                     dview<const T>(x), g, relu_in);
   NPP_CHECK_LAUNCH("dw_tile_dgrad");
   return NPP_OK;
@@ -561,7 +565,7 @@ int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride
     int rc = dw_set_smem2<sizeof(T) * 10 + 5>(dw_pipe_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_pipe_wgrad)");
     if (rc) return rc;
     dw_pipe_slots(g);
-    dw_pipe_wgrad_kernel<T><<<g.slots * g.cblocks, 256, 2 * smem, st>>>(dview<const T>(x), dview<const T>(dy), dw, g,
+    NPP_LAUNCH((dw_pipe_wgrad_kernel<T>), g.slots * g.cblocks, 256, 2 * smem, st, dview<const T>(x), dview<const T>(dy), dw, g,
                                                                         relu_in, (int)(smem / 16));
     NPP_CHECK_LAUNCH("dw_pipe_wgrad");
     return NPP_OK;
@@ -572,7 +576,7 @@ int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride
   if (slots < 1) slots = 1;
   if (slots > g.ntiles) slots = g.ntiles;
   g.slots = slots;
-  dw_tile_wgrad_kernel<T><<<slots * g.cblocks, 256, smem, st>>>(dview<const T>(x), dview<const T>(dy), dw, g, relu_in);
+  NPP_LAUNCH((dw_tile_wgrad_kernel<T>), slots * g.cblocks, 256, smem, st, dview<const T>(x), dview<const T>(dy), dw, g, relu_in);
   NPP_CHECK_LAUNCH("dw_tile_wgrad");
   return NPP_OK;
 }

@@ -98,6 +98,7 @@ int fill_zero_view_bf16(const npp_view4* v, cudaStream_t st) { return fill_zero_
 
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = from_f<D>(to_f<S>(s[i]));
 }
@@ -106,6 +107,7 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
 // of the destination view are written as zero (channel padding).
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, DView<T> dst, int C) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int hw = dst.h * dst.w;
@@ -127,6 +129,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, DView<T> dst,
 template <int DUMMY>
 __global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restrict__ src, DView<__nv_bfloat16> dst,
                                                             int C) {
+  pdl_wait();
   const int hw = dst.h * dst.w;
   const int n = blockIdx.y;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restr
 // weight — the implicit-GEMM kernel otherwise spends nine 64-wide K blocks on 3 real channels each (7.6 TFLOP/s).
 __global__ void __launch_bounds__(256) im2col3x3_c3_kernel(DView<const __nv_bfloat16> X, DView<__nv_bfloat16> Y,
                                                            int stride, int pad) {
+  pdl_wait();
   const int npix = Y.n * Y.h * Y.w;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
     const int wo = p % Y.w;
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(256) im2col3x3_c3_kernel(DView<const __nv_bflo
 
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(DView<const T> src, float* __restrict__ dst, int C) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int hw = src.h * src.w;
@@ -276,13 +281,13 @@ int npp_cast(const void* src, int sd, void* dst, int dd, int64_t n, npp_stream_t
   if (grid > 148 * 16) grid = 148 * 16;
   cudaStream_t st = as_stream(s);
   if (sd == NPP_F32 && dd == NPP_BF16)
-    cast_kernel<float, __nv_bfloat16><<<(int)grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    NPP_LAUNCH((cast_kernel<float, __nv_bfloat16>), (int)grid, 256, 0, st, (const float*)src, (__nv_bfloat16*)dst, n);
   else if (sd == NPP_BF16 && dd == NPP_F32)
-    cast_kernel<__nv_bfloat16, float><<<(int)grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    NPP_LAUNCH((cast_kernel<__nv_bfloat16, float>), (int)grid, 256, 0, st, (const __nv_bfloat16*)src, (float*)dst, n);
   else if (sd == NPP_F32 && dd == NPP_F32)
-    cast_kernel<float, float><<<(int)grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    NPP_LAUNCH((cast_kernel<float, float>), (int)grid, 256, 0, st, (const float*)src, (float*)dst, n);
   else if (sd == NPP_BF16 && dd == NPP_BF16)
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+    NPP_LAUNCH((cast_kernel<__nv_bfloat16, __nv_bfloat16>), (int)grid, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
   else
     return NPP_E_UNSUPPORTED;
   NPP_CHECK_LAUNCH("cast_kernel");
@@ -294,12 +299,12 @@ int npp_nchw_to_nhwc(const float* src, int src_c, const npp_view4* dst, int dtyp
     const int hw = dst->h * dst->w;
     int gx = (hw + 255) / 256;
     if (gx > 2048) gx = 2048;
-    nchw_to_nhwc8_kernel<0><<<dim3(gx, dst->n), 256, 0, as_stream(s)>>>(src, dview<__nv_bfloat16>(dst), src_c);
+    NPP_LAUNCH((nchw_to_nhwc8_kernel<0>), dim3(gx, dst->n), 256, 0, as_stream(s), src, dview<__nv_bfloat16>(dst), src_c);
     NPP_CHECK_LAUNCH("nchw_to_nhwc8_kernel");
     return NPP_OK;
   }
   dim3 grid((dst->h * dst->w + 31) / 32, (dst->c + 31) / 32, dst->n), block(32, 8);
-  NPP_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, as_stream(s)>>>(src, dview<T>(dst), src_c););
+  NPP_DISPATCH_DTYPE(dtype, NPP_LAUNCH((nchw_to_nhwc_kernel<T>), grid, block, 0, as_stream(s), src, dview<T>(dst), src_c););
   NPP_CHECK_LAUNCH("nchw_to_nhwc_kernel");
   return NPP_OK;
 }
@@ -311,7 +316,7 @@ int npp_im2col3x3_c3(const npp_view4* x, const npp_view4* y, int stride, int pad
   if (npix > 0x7fffffff) return NPP_E_UNSUPPORTED;
   int64_t grid = (npix + 255) / 256;
   if (grid > (int64_t)sm_count() * 32) grid = (int64_t)sm_count() * 32;
-  im2col3x3_c3_kernel<<<(unsigned)grid, 256, 0, as_stream(s)>>>(dview<const __nv_bfloat16>(x), dview<__nv_bfloat16>(y),
+  NPP_LAUNCH((im2col3x3_c3_kernel), (unsigned)grid, 256, 0, as_stream(s), dview<const __nv_bfloat16>(x), dview<__nv_bfloat16>(y),
                                                                stride, pad);
   NPP_CHECK_LAUNCH("im2col3x3_c3_kernel");
   return NPP_OK;
@@ -319,7 +324,7 @@ int npp_im2col3x3_c3(const npp_view4* x, const npp_view4* y, int stride, int pad
 int npp_nhwc_to_nchw(const npp_view4* src, float* dst, int dst_c, int dtype, npp_stream_t s) {
   if (!dst || !view_ok(src, dtype) || dst_c <= 0 || dst_c > src->c) return NPP_E_INVALID;
   dim3 grid((src->h * src->w + 31) / 32, (dst_c + 31) / 32, src->n), block(32, 8);
-  NPP_DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, as_stream(s)>>>(dview<const T>(src), dst, dst_c););
+  NPP_DISPATCH_DTYPE(dtype, NPP_LAUNCH((nhwc_to_nchw_kernel<T>), grid, block, 0, as_stream(s), dview<const T>(src), dst, dst_c););
   NPP_CHECK_LAUNCH("nhwc_to_nchw_kernel");
   return NPP_OK;
 }

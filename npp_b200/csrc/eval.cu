@@ -16,6 +16,7 @@ namespace npp {
 __global__ void __launch_bounds__(256)
 confusion_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label, int C, int H, int W, int LH,
                  int LW, int ignore, unsigned long long* __restrict__ hist) {
+  pdl_wait();
   extern __shared__ unsigned int sh[];  // C*C
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -45,6 +46,7 @@ confusion_kernel(const float* __restrict__ logits, const int64_t* __restrict__ l
 __global__ void __launch_bounds__(256)
 tta_merge_kernel(const float* __restrict__ pred, const float* __restrict__ flip, int N, int C, int H, int W, int OH,
                  int OW, Axis ah, Axis aw, int swap_lr, float* __restrict__ out) {
+  pdl_wait();
   const int64_t total = (int64_t)N * C * OH * OW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % OW);
@@ -95,6 +97,7 @@ struct FlipIdx { int idx[32]; };
 __global__ void __launch_bounds__(256)
 pose_merge_kernel(const float* __restrict__ pred, const float* __restrict__ flip, int N, int J, int H, int W, int OH,
                   int OW, FlipIdx fi, float* __restrict__ out) {
+  pdl_wait();
   const double sy = (double)H / (double)OH, sx = (double)W / (double)OW;
   const int64_t total = (int64_t)N * J * OH * OW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -125,6 +128,7 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
 __global__ void __launch_bounds__(256)
 gauss1d_reflect_kernel(const float* __restrict__ src, float* __restrict__ dst, int planes, int H, int W, int axis,
                        GaussTaps g) {
+  pdl_wait();
   const int64_t total = (int64_t)planes * H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % W);
@@ -143,6 +147,7 @@ gauss1d_reflect_kernel(const float* __restrict__ src, float* __restrict__ dst, i
 // ---- heat-map arg-max ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 heatmap_argmax_kernel(const float* __restrict__ hm, int hw, int32_t* __restrict__ idx, float* __restrict__ maxval) {
+  pdl_wait();
   __shared__ float sv[256];
   __shared__ int si[256];
   const float* p = hm + (int64_t)blockIdx.x * hw;
@@ -171,6 +176,7 @@ __global__ void pck_counts_kernel(const int32_t* __restrict__ pidx, const float*
                                   const int32_t* __restrict__ gidx, const float* __restrict__ gmax, int N, int J, int H,
                                   int W, double thr, unsigned long long* __restrict__ hit,
                                   unsigned long long* __restrict__ valid) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * J) return;
   const int j = i % J;
@@ -191,6 +197,7 @@ __global__ void pck_counts_kernel(const int32_t* __restrict__ pidx, const float*
 __global__ void pckh_counts_kernel(const double* __restrict__ pred, const double* __restrict__ gt, int N, int P,
                                    double thr, unsigned long long* __restrict__ hit,
                                    unsigned long long* __restrict__ valid) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * P) return;
   const int n = i / P, p = i % P;
@@ -212,6 +219,7 @@ __global__ void pckh_counts_kernel(const double* __restrict__ pred, const double
 // in heat-map space — the mirrored image's maps are joint-permuted but NOT mirrored back (reference behaviour).
 __global__ void heatmap_flip_avg_kernel(const float* __restrict__ pred, const float* __restrict__ flip, int nj, int hw,
                                         FlipIdx fi, int64_t total, float* __restrict__ out) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int px = (int)(i % hw);
     const int64_t t = i / hw;
@@ -235,7 +243,7 @@ int npp_confusion_hist(const float* logits, const int64_t* label, int n, int c, 
   const int cap = sm_count() * 8 / n + 1;
   if (gx > cap) gx = cap;
   dim3 grid(gx, n);
-  confusion_kernel<<<grid, 256, (size_t)c * c * sizeof(unsigned int), as_stream(s)>>>(
+  NPP_LAUNCH((confusion_kernel), grid, 256, (size_t)c * c * sizeof(unsigned int), as_stream(s), 
       logits, label, c, h, w, label_h, label_w, ignore, reinterpret_cast<unsigned long long*>(hist));
   NPP_CHECK_LAUNCH("confusion_kernel");
   return NPP_OK;
@@ -249,7 +257,7 @@ int npp_tta_merge(const float* pred, const float* flip_pred, int n, int c, int h
   const int64_t total = (int64_t)n * c * oh * ow;
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  tta_merge_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, n, c, h, w, oh, ow, ah, aw, swap_lr, out);
+  NPP_LAUNCH((tta_merge_kernel), (int)grid, 256, 0, as_stream(s), pred, flip_pred, n, c, h, w, oh, ow, ah, aw, swap_lr, out);
   NPP_CHECK_LAUNCH("tta_merge_kernel");
   return NPP_OK;
 }
@@ -267,7 +275,7 @@ int npp_pose_merge(const float* pred, const float* flip_pred, int n, int nj, int
   const int64_t total = (int64_t)n * nj * oh * ow;
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  pose_merge_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, n, nj, h, w, oh, ow, fi, out);
+  NPP_LAUNCH((pose_merge_kernel), (int)grid, 256, 0, as_stream(s), pred, flip_pred, n, nj, h, w, oh, ow, fi, out);
   NPP_CHECK_LAUNCH("pose_merge_kernel");
   return NPP_OK;
 }
@@ -284,7 +292,7 @@ int npp_heatmap_flip_avg(const float* pred, const float* flip_pred, int n, int n
   const int64_t total = (int64_t)n * nj * h * w;
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  heatmap_flip_avg_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(pred, flip_pred, nj, h * w, fi, total, out);
+  NPP_LAUNCH((heatmap_flip_avg_kernel), (int)grid, 256, 0, as_stream(s), pred, flip_pred, nj, h * w, fi, total, out);
   NPP_CHECK_LAUNCH("heatmap_flip_avg_kernel");
   return NPP_OK;
 }
@@ -306,16 +314,16 @@ int npp_gaussian_filter(const float* src, float* tmp, float* dst, int planes, in
   const int64_t total = (int64_t)planes * h * w;
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  gauss1d_reflect_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(src, tmp, planes, h, w, 0, g);
+  NPP_LAUNCH((gauss1d_reflect_kernel), (int)grid, 256, 0, as_stream(s), src, tmp, planes, h, w, 0, g);
   NPP_CHECK_LAUNCH("gauss1d_reflect_kernel(axis 0)");
-  gauss1d_reflect_kernel<<<(int)grid, 256, 0, as_stream(s)>>>(tmp, dst, planes, h, w, 1, g);
+  NPP_LAUNCH((gauss1d_reflect_kernel), (int)grid, 256, 0, as_stream(s), tmp, dst, planes, h, w, 1, g);
   NPP_CHECK_LAUNCH("gauss1d_reflect_kernel(axis 1)");
   return NPP_OK;
 }
 
 int npp_heatmap_argmax(const float* hm, int nj, int h, int w, int32_t* idx, float* maxval, npp_stream_t s) {
   if (!hm || !idx || !maxval || nj <= 0 || h <= 0 || w <= 0) return NPP_E_INVALID;
-  heatmap_argmax_kernel<<<nj, 256, 0, as_stream(s)>>>(hm, h * w, idx, maxval);
+  NPP_LAUNCH((heatmap_argmax_kernel), nj, 256, 0, as_stream(s), hm, h * w, idx, maxval);
   NPP_CHECK_LAUNCH("heatmap_argmax_kernel");
   return NPP_OK;
 }
@@ -323,7 +331,7 @@ int npp_heatmap_argmax(const float* hm, int nj, int h, int w, int32_t* idx, floa
 int npp_pck_counts(const int32_t* pred_idx, const float* pred_max, const int32_t* gt_idx, const float* gt_max, int n,
                    int j, int h, int w, float thr, int64_t* hit, int64_t* valid, npp_stream_t s) {
   if (!pred_idx || !pred_max || !gt_idx || !gt_max || !hit || !valid || n <= 0 || j <= 0) return NPP_E_INVALID;
-  pck_counts_kernel<<<(n * j + 127) / 128, 128, 0, as_stream(s)>>>(
+  NPP_LAUNCH((pck_counts_kernel), (n * j + 127) / 128, 128, 0, as_stream(s), 
       pred_idx, pred_max, gt_idx, gt_max, n, j, h, w, (double)thr, reinterpret_cast<unsigned long long*>(hit),
       reinterpret_cast<unsigned long long*>(valid));
   NPP_CHECK_LAUNCH("pck_counts_kernel");
@@ -333,7 +341,7 @@ int npp_pck_counts(const int32_t* pred_idx, const float* pred_max, const int32_t
 int npp_pckh_counts(const double* pred, const double* gt, int n, int p, double thr, int64_t* hit, int64_t* valid,
                     npp_stream_t s) {
   if (!pred || !gt || !hit || !valid || n <= 0 || p < 10) return NPP_E_INVALID;
-  pckh_counts_kernel<<<(n * p + 127) / 128, 128, 0, as_stream(s)>>>(pred, gt, n, p, thr,
+  NPP_LAUNCH((pckh_counts_kernel), (n * p + 127) / 128, 128, 0, as_stream(s), pred, gt, n, p, thr,
                                                                      reinterpret_cast<unsigned long long*>(hit),
                                                                      reinterpret_cast<unsigned long long*>(valid));
   NPP_CHECK_LAUNCH("pckh_counts_kernel");

@@ -17,6 +17,7 @@ namespace npp {
 __global__ void __launch_bounds__(256)
 pose_target_kernel(const double* __restrict__ joints, const int* __restrict__ vis, int B, int J, double stride, int gx,
                    int gy, double sigma, float* __restrict__ out) {
+  pdl_wait();
   const int64_t total = (int64_t)B * gy * gx;
   const double start = stride / 2.0 - 0.5;
   const double max_dist = ceil(sqrt(4.6052 * sigma * sigma * 2.0));
@@ -76,6 +77,7 @@ __device__ __forceinline__ int edge_seed(const int64_t* __restrict__ lab, int h,
 
 __global__ void __launch_bounds__(256)
 edge_label_kernel(const int64_t* __restrict__ label, int B, int h, int w, int radius, int64_t* __restrict__ out) {
+  pdl_wait();
   const int64_t total = (int64_t)B * h * w;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
@@ -97,6 +99,7 @@ edge_label_kernel(const int64_t* __restrict__ label, int B, int h, int w, int ra
 
 __global__ void __launch_bounds__(256)
 flip_parsing_kernel(const int64_t* __restrict__ label, int64_t total, int w, int64_t* __restrict__ out) {
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     int64_t v = label[i - x + (w - 1 - x)];
@@ -121,7 +124,7 @@ int npp_pose_target(const double* joints, const int* visible, int b, int j, doub
                     double sigma, float* out, npp_stream_t s) {
   if (!joints || !visible || !out || b <= 0 || j <= 0 || grid_x <= 0 || grid_y <= 0 || !(stride > 0) || !(sigma > 0))
     return NPP_E_INVALID;
-  pose_target_kernel<<<grid_for((int64_t)b * grid_x * grid_y), 256, 0, as_stream(s)>>>(joints, visible, b, j, stride, grid_x,
+  NPP_LAUNCH((pose_target_kernel), grid_for((int64_t)b * grid_x * grid_y), 256, 0, as_stream(s), joints, visible, b, j, stride, grid_x,
                                                                                     grid_y, sigma, out);
   NPP_CHECK_LAUNCH("pose_target_kernel");
   return NPP_OK;
@@ -130,7 +133,7 @@ int npp_pose_target(const double* joints, const int* visible, int b, int j, doub
 int npp_edge_label(const int64_t* label, int b, int h, int w, int edge_width, int64_t* out, npp_stream_t s) {
   if (!label || !out || b <= 0 || h <= 0 || w <= 0 || edge_width < 1 || edge_width % 2 == 0 || edge_width > 15)
     return NPP_E_INVALID;
-  edge_label_kernel<<<grid_for((int64_t)b * h * w), 256, 0, as_stream(s)>>>(label, b, h, w, edge_width / 2, out);
+  NPP_LAUNCH((edge_label_kernel), grid_for((int64_t)b * h * w), 256, 0, as_stream(s), label, b, h, w, edge_width / 2, out);
   NPP_CHECK_LAUNCH("edge_label_kernel");
   return NPP_OK;
 }
@@ -138,7 +141,7 @@ int npp_edge_label(const int64_t* label, int b, int h, int w, int edge_width, in
 int npp_flip_parsing(const int64_t* label, int b, int h, int w, int64_t* out, npp_stream_t s) {
   if (!label || !out || label == out || b <= 0 || h <= 0 || w <= 0) return NPP_E_INVALID;
   const int64_t total = (int64_t)b * h * w;
-  flip_parsing_kernel<<<grid_for(total), 256, 0, as_stream(s)>>>(label, total, w, out);
+  NPP_LAUNCH((flip_parsing_kernel), grid_for(total), 256, 0, as_stream(s), label, total, w, out);
   NPP_CHECK_LAUNCH("flip_parsing_kernel");
   return NPP_OK;
 }

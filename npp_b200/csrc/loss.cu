@@ -39,6 +39,7 @@ ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targ
               const float* __restrict__ class_w, const int64_t* __restrict__ posneg, int ignore,
               float* __restrict__ prob, float* __restrict__ loss, unsigned long long* __restrict__ n_valid,
               float* __restrict__ out2) {
+  pdl_wait();
   extern __shared__ float patch[];  // [c][HR][WR]
   __shared__ float red[2][kLossThreads / 32];
   __shared__ unsigned int cnt_sh;
@@ -131,6 +132,7 @@ ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targ
               const float* __restrict__ class_w, const int64_t* __restrict__ posneg, int ignore,
               const float* __restrict__ prob, const float* __restrict__ sel, const float* __restrict__ gscale,
               float* __restrict__ dlogits) {
+  pdl_wait();
   extern __shared__ float sm[];
   const int plane = g.HR * g.WR;
   float* patch = sm;                 // [c][HR][WR]
@@ -227,6 +229,7 @@ ce_bwd_gather_kernel(const float* __restrict__ logits, const int64_t* __restrict
                      const float* __restrict__ class_w, const int64_t* __restrict__ posneg, int ignore,
                      const float* __restrict__ prob, const float* __restrict__ sel, const float* __restrict__ gscale,
                      float* __restrict__ dlogits) {
+  pdl_wait();
   constexpr int ROWS = kLossThreads / TILE;   // 8 label rows per chunk
   constexpr int GP = TILE + 1;                // padded row of G
   extern __shared__ float sm[];
@@ -384,6 +387,7 @@ ce_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ tar
                const float* __restrict__ class_w, const int64_t* __restrict__ posneg, int ignore,
                const float* __restrict__ prob, const float* __restrict__ sel, const float* __restrict__ gscale,
                float* __restrict__ G, int CQ) {
+  pdl_wait();
   extern __shared__ float patch[];  // [c][HR][WR]
   const int plane = g.HR * g.WR;
   const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE, n = blockIdx.z;
@@ -477,6 +481,7 @@ static int make_geom(LossGeom* g, int n, int c, int h, int w, int lh, int lw, in
 // workspace layout (uint32): [0..255] histogram, [256] prefix, [257] k remaining, [258] pass index
 // ------------------------------------------------------------------------------------------------
 __global__ void ohem_init_kernel(unsigned int* ws, const unsigned long long* n_valid, int min_kept) {
+  pdl_wait();
   if (threadIdx.x < 256) ws[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     const long long nv = (long long)*n_valid;
@@ -489,6 +494,7 @@ __global__ void ohem_init_kernel(unsigned int* ws, const unsigned long long* n_v
 }
 
 __global__ void __launch_bounds__(256) ohem_hist_kernel(const float* __restrict__ prob, int64_t npix, unsigned int* ws) {
+  pdl_wait();
   __shared__ unsigned int h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -504,7 +510,8 @@ __global__ void __launch_bounds__(256) ohem_hist_kernel(const float* __restrict_
   if (h[threadIdx.x]) atomicAdd(&ws[threadIdx.x], h[threadIdx.x]);
 }
 
-__global__ void ohem_scan_kernel(unsigned int* ws) {  // 1 block of 256 threads
+__global__ void ohem_scan_kernel(unsigned int* ws) {
+  pdl_wait();  // 1 block of 256 threads
   __shared__ unsigned int h[256];
   h[threadIdx.x] = ws[threadIdx.x];
   __syncthreads();
@@ -529,6 +536,7 @@ __global__ void ohem_scan_kernel(unsigned int* ws) {  // 1 block of 256 threads
 __global__ void __launch_bounds__(256)
 ohem_sum_kernel(const float* __restrict__ prob, const float* __restrict__ loss, int64_t npix, const unsigned int* ws,
                 float thres, float* __restrict__ out3) {
+  pdl_wait();
   __shared__ float rs[8], rc[8];
   const float kth = ws[257] == 0xffffffffu ? 0.f : __uint_as_float(ws[256]);
   const float thr = fmaxf(kth, thres);
@@ -551,6 +559,7 @@ ohem_sum_kernel(const float* __restrict__ prob, const float* __restrict__ loss, 
 
 __global__ void __launch_bounds__(256)
 edge_count_kernel(const int64_t* __restrict__ t, int64_t npix, unsigned long long* __restrict__ posneg) {
+  pdl_wait();
   unsigned int p = 0, q = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = t[i];
@@ -568,6 +577,7 @@ edge_count_kernel(const int64_t* __restrict__ t, int64_t npix, unsigned long lon
 __global__ void __launch_bounds__(256)
 mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, const float* __restrict__ row_w,
                int64_t row_len, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float rs[8];
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -588,6 +598,7 @@ mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t
 __global__ void __launch_bounds__(256)
 mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, const float* __restrict__ row_w,
                int64_t row_len, const float* __restrict__ gscale, float* __restrict__ da) {
+  pdl_wait();
   const float g2 = 2.f * gscale[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float w = row_w ? row_w[i / row_len] : 1.f;
@@ -619,7 +630,7 @@ int npp_par_loss_pixels(const float* logits, int n, int c, int h, int w, const i
   const size_t smem = (size_t)c * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_fwd_kernel<0>, smem))) return rc;
   dim3 grid(g.tiles_x, g.tiles_y, n);
-  ce_fwd_kernel<0><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index, prob,
+  NPP_LAUNCH((ce_fwd_kernel<0>), grid, kLossThreads, smem, as_stream(s), logits, target, g, class_w, nullptr, ignore_index, prob,
                                                                loss, reinterpret_cast<unsigned long long*>(n_valid),
                                                                nullptr);
   NPP_CHECK_LAUNCH("ce_fwd_kernel<par>");
@@ -632,13 +643,13 @@ int npp_ohem_select(const float* prob, const float* loss, int64_t npix, const in
   cudaStream_t st = as_stream(s);
   unsigned int* ws = static_cast<unsigned int*>(workspace);
   if (min_kept < 1) min_kept = 1;  // criterion.py:48 max(1, min_kept)
-  ohem_init_kernel<<<1, 256, 0, st>>>(ws, reinterpret_cast<const unsigned long long*>(n_valid), min_kept);
+  NPP_LAUNCH((ohem_init_kernel), 1, 256, 0, st, ws, reinterpret_cast<const unsigned long long*>(n_valid), min_kept);
   const int grid = flat_grid(npix);
   for (int pass = 0; pass < 4; ++pass) {
-    ohem_hist_kernel<<<grid, 256, 0, st>>>(prob, npix, ws);
-    ohem_scan_kernel<<<1, 256, 0, st>>>(ws);
+    NPP_LAUNCH((ohem_hist_kernel), grid, 256, 0, st, prob, npix, ws);
+    NPP_LAUNCH((ohem_scan_kernel), 1, 256, 0, st, ws);
   }
-  ohem_sum_kernel<<<grid, 256, 0, st>>>(prob, loss, npix, ws, thres, out3);
+  NPP_LAUNCH((ohem_sum_kernel), grid, 256, 0, st, prob, loss, npix, ws, thres, out3);
   NPP_CHECK_LAUNCH("ohem_select");
   count_launch(9);  // init + 4 x (hist, scan); the sum kernel is counted by the check above
   return NPP_OK;
@@ -655,14 +666,14 @@ int npp_par_loss_bwd(const float* logits, int n, int c, int h, int w, const int6
   if (!ce_bwd_atomic() && g.WR <= TILE) {
     const size_t smem2 = ce_bwd_gather_smem(g);
     if ((rc = ensure_smem(ce_bwd_gather_kernel<0>, smem2))) return rc;
-    ce_bwd_gather_kernel<0><<<grid, kLossThreads, smem2, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index,
+    NPP_LAUNCH((ce_bwd_gather_kernel<0>), grid, kLossThreads, smem2, as_stream(s), logits, target, g, class_w, nullptr, ignore_index,
                                                                         prob, out3, gscale, dlogits);
     NPP_CHECK_LAUNCH("ce_bwd_gather_kernel<par>");
     return NPP_OK;
   }
   const size_t smem = 2 * (size_t)c * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_bwd_kernel<0>, smem))) return rc;
-  ce_bwd_kernel<0><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index, prob,
+  NPP_LAUNCH((ce_bwd_kernel<0>), grid, kLossThreads, smem, as_stream(s), logits, target, g, class_w, nullptr, ignore_index, prob,
                                                                out3, gscale, dlogits);
   NPP_CHECK_LAUNCH("ce_bwd_kernel<par>");
   return NPP_OK;
@@ -680,7 +691,7 @@ int npp_par_loss_grad_pixels(const float* logits, int n, int c, int h, int w, co
   const size_t smem = (size_t)c * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_grad_kernel<0>, smem))) return rc;
   dim3 grid(g.tiles_x, g.tiles_y, n);
-  ce_grad_kernel<0><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, class_w, nullptr, ignore_index, prob,
+  NPP_LAUNCH((ce_grad_kernel<0>), grid, kLossThreads, smem, as_stream(s), logits, target, g, class_w, nullptr, ignore_index, prob,
                                                                 out3, gscale, G, cq);
   NPP_CHECK_LAUNCH("ce_grad_kernel<par>");
   return NPP_OK;
@@ -697,7 +708,7 @@ int npp_edge_loss_grad_pixels(const float* logits, int n, int h, int w, const in
   const size_t smem = (size_t)2 * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_grad_kernel<1>, smem))) return rc;
   dim3 grid(g.tiles_x, g.tiles_y, n);
-  ce_grad_kernel<1><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
+  NPP_LAUNCH((ce_grad_kernel<1>), grid, kLossThreads, smem, as_stream(s), logits, target, g, nullptr, posneg, ignore_index,
                                                                 nullptr, out2, gscale, G, cq);
   NPP_CHECK_LAUNCH("ce_grad_kernel<edge>");
   return NPP_OK;
@@ -705,7 +716,7 @@ int npp_edge_loss_grad_pixels(const float* logits, int n, int h, int w, const in
 
 int npp_edge_count(const int64_t* target, int64_t npix, int64_t* posneg, npp_stream_t s) {
   if (!target || !posneg || npix <= 0) return NPP_E_INVALID;
-  edge_count_kernel<<<flat_grid(npix), 256, 0, as_stream(s)>>>(target, npix,
+  NPP_LAUNCH((edge_count_kernel), flat_grid(npix), 256, 0, as_stream(s), target, npix,
                                                               reinterpret_cast<unsigned long long*>(posneg));
   NPP_CHECK_LAUNCH("edge_count_kernel");
   return NPP_OK;
@@ -720,7 +731,7 @@ int npp_edge_loss_fwd(const float* logits, int n, int h, int w, const int64_t* t
   const size_t smem = (size_t)2 * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_fwd_kernel<1>, smem))) return rc;
   dim3 grid(g.tiles_x, g.tiles_y, n);
-  ce_fwd_kernel<1><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
+  NPP_LAUNCH((ce_fwd_kernel<1>), grid, kLossThreads, smem, as_stream(s), logits, target, g, nullptr, posneg, ignore_index,
                                                                nullptr, nullptr, nullptr, out2);
   NPP_CHECK_LAUNCH("ce_fwd_kernel<edge>");
   return NPP_OK;
@@ -737,14 +748,14 @@ int npp_edge_loss_bwd(const float* logits, int n, int h, int w, const int64_t* t
   if (!ce_bwd_atomic() && g.WR <= TILE) {
     const size_t smem2 = ce_bwd_gather_smem(g);
     if ((rc = ensure_smem(ce_bwd_gather_kernel<1>, smem2))) return rc;
-    ce_bwd_gather_kernel<1><<<grid, kLossThreads, smem2, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
+    NPP_LAUNCH((ce_bwd_gather_kernel<1>), grid, kLossThreads, smem2, as_stream(s), logits, target, g, nullptr, posneg, ignore_index,
                                                                         nullptr, out2, gscale, dlogits);
     NPP_CHECK_LAUNCH("ce_bwd_gather_kernel<edge>");
     return NPP_OK;
   }
   const size_t smem = 2 * (size_t)2 * g.HR * g.WR * sizeof(float);
   if ((rc = ensure_smem(ce_bwd_kernel<1>, smem))) return rc;
-  ce_bwd_kernel<1><<<grid, kLossThreads, smem, as_stream(s)>>>(logits, target, g, nullptr, posneg, ignore_index,
+  NPP_LAUNCH((ce_bwd_kernel<1>), grid, kLossThreads, smem, as_stream(s), logits, target, g, nullptr, posneg, ignore_index,
                                                                nullptr, out2, gscale, dlogits);
   NPP_CHECK_LAUNCH("ce_bwd_kernel<edge>");
   return NPP_OK;
@@ -753,7 +764,7 @@ int npp_edge_loss_bwd(const float* logits, int n, int h, int w, const int64_t* t
 int npp_mse_fwd(const float* pred, const float* target, int64_t n, const float* row_w, int64_t row_len, float* out,
                 npp_stream_t s) {
   if (!pred || !target || !out || n <= 0 || (row_w && row_len <= 0)) return NPP_E_INVALID;
-  mse_fwd_kernel<<<flat_grid(n), 256, 0, as_stream(s)>>>(pred, target, n, row_w, row_len, out);
+  NPP_LAUNCH((mse_fwd_kernel), flat_grid(n), 256, 0, as_stream(s), pred, target, n, row_w, row_len, out);
   NPP_CHECK_LAUNCH("mse_fwd_kernel");
   return NPP_OK;
 }
@@ -761,7 +772,7 @@ int npp_mse_fwd(const float* pred, const float* target, int64_t n, const float* 
 int npp_mse_bwd(const float* pred, const float* target, int64_t n, const float* row_w, int64_t row_len,
                 const float* gscale, float* dpred, npp_stream_t s) {
   if (!pred || !target || !gscale || !dpred || n <= 0 || (row_w && row_len <= 0)) return NPP_E_INVALID;
-  mse_bwd_kernel<<<flat_grid(n), 256, 0, as_stream(s)>>>(pred, target, n, row_w, row_len, gscale, dpred);
+  NPP_LAUNCH((mse_bwd_kernel), flat_grid(n), 256, 0, as_stream(s), pred, target, n, row_w, row_len, gscale, dpred);
   NPP_CHECK_LAUNCH("mse_bwd_kernel");
   return NPP_OK;
 }

@@ -104,6 +104,7 @@ __device__ __forceinline__ void load_g(const MView<const T>& g, int interleave, 
 // ------------------------------------------------------------------------------------------------ forward
 template <typename T>
 __global__ void __launch_bounds__(256) mix_fwd_kernel(const MixArgs<T> A) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   const int tcv = threadIdx.x % A.geom.cvb;
   const int trow = threadIdx.x / A.geom.cvb;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) mix_fwd_kernel(const MixArgs<T> A) {
 // ------------------------------------------------------------------------------------------------ backward 1/2
 template <typename T>
 __global__ void __launch_bounds__(256) mix_bwd_reduce_kernel(const MixArgs<T> A) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   __shared__ float red[256 * V];
   const int tcv = threadIdx.x % A.geom.cvb;
@@ -241,6 +243,7 @@ struct MixDwArgs {
   float* dw;
 };
 __global__ void mix_dw_kernel(const MixDwArgs A) {
+  pdl_wait();
   const int j = blockIdx.x;
   if (j >= A.k) return;
   float t = 0.f;
@@ -264,6 +267,7 @@ __global__ void mix_dw_kernel(const MixDwArgs A) {
 // ------------------------------------------------------------------------------------------------ backward 2/2
 template <typename T>
 __global__ void __launch_bounds__(256) mix_bwd_apply_kernel(const MixArgs<T> A) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   const int tcv = threadIdx.x % A.geom.cvb;
   const int trow = threadIdx.x / A.geom.cvb;
@@ -386,7 +390,7 @@ int npp_mix_fwd(const npp_mix_desc* d, const float* wts, const npp_view4* pass, 
   NPP_DISPATCH_DTYPE(
       dtype, MixArgs<T> A; mix_fill<T>(A, d, true); A.wts = wts; A.pass = mview<const T>(d->interleave ? pass : nullptr);
       A.out = mview<T>(out); dim3 grid((unsigned)mix_grid(A.npix, A.geom, 2, 8), (unsigned)A.geom.gy);
-      mix_fwd_kernel<T><<<grid, 256, 0, as_stream(s)>>>(A); NPP_CHECK_LAUNCH("mix_fwd_kernel"); return NPP_OK;);
+      NPP_LAUNCH((mix_fwd_kernel<T>), grid, 256, 0, as_stream(s), A); NPP_CHECK_LAUNCH("mix_fwd_kernel"); return NPP_OK;);
 }
 
 int npp_mix_bwd_reduce(const npp_mix_desc* d, const npp_view4* g, float* partials, int dtype, npp_stream_t s) {
@@ -401,8 +405,7 @@ int npp_mix_bwd_reduce(const npp_mix_desc* d, const npp_view4* g, float* partial
   if (blocks <= 0) return NPP_E_INVALID;
   NPP_DISPATCH_DTYPE(
       dtype, MixArgs<T> A; mix_fill<T>(A, d, false); if (A.geom.gy != 1) return NPP_E_UNSUPPORTED;
-      A.g = mview<const T>(g); A.partials = partials; mix_bwd_reduce_kernel<T><<<dim3((unsigned)blocks, 1), 256, 0,
-                                                                                 as_stream(s)>>>(A);
+      A.g = mview<const T>(g); A.partials = partials; NPP_LAUNCH((mix_bwd_reduce_kernel<T>), dim3((unsigned)blocks, 1), 256, 0, as_stream(s), A);
       NPP_CHECK_LAUNCH("mix_bwd_reduce_kernel"); return NPP_OK;);
 }
 
@@ -415,7 +418,7 @@ int npp_mix_dw(const npp_mix_desc* d, const float* sums, const float* const* bet
     A.gamma[j] = bn ? d->gamma[j] : nullptr;
     A.beta[j] = (bn && beta) ? beta[j] : nullptr;
   }
-  mix_dw_kernel<<<d->k, 256, 0, as_stream(s)>>>(A);
+  NPP_LAUNCH((mix_dw_kernel), d->k, 256, 0, as_stream(s), A);
   NPP_CHECK_LAUNCH("mix_dw_kernel");
   return NPP_OK;
 }
@@ -440,7 +443,7 @@ int npp_mix_bwd_apply(const npp_mix_desc* d, const npp_view4* g, const float* wt
       dtype, MixArgs<T> A; mix_fill<T>(A, d, false); A.g = mview<const T>(g); A.wts = wts; A.sums = sums;
       A.inv_count = (float)(1.0 / count); A.dpass = mview<T>(dpass);
       dim3 grid((unsigned)mix_grid(A.npix, A.geom, 2, 8), (unsigned)A.geom.gy);
-      mix_bwd_apply_kernel<T><<<grid, 256, 0, as_stream(s)>>>(A); NPP_CHECK_LAUNCH("mix_bwd_apply_kernel");
+      NPP_LAUNCH((mix_bwd_apply_kernel<T>), grid, 256, 0, as_stream(s), A); NPP_CHECK_LAUNCH("mix_bwd_apply_kernel");
       return NPP_OK;);
 }
 

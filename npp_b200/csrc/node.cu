@@ -114,6 +114,7 @@ __device__ __forceinline__ void bn_fin_channel(const BnFin& f, double count, int
 
 template <typename T, int U>
 __global__ void __launch_bounds__(256, 2) node_fwd_kernel(const NodeFwdArgs<T> A) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   extern __shared__ float node_coef_smem[];  // [4][cvb * V] when a side is finalized here
   const int tcv = threadIdx.x % A.g.cvb;
@@ -226,7 +227,7 @@ static int node_fwd_t(const npp_view4* a, const float* sa, const float* ta, cons
   A.g = vec_geom(a->c, V);
   dim3 grid((unsigned)stream_grid(npix, A.g, 4, 8), (unsigned)A.g.gy);
   const size_t smem = (A.fa.stats || A.fb.stats) ? (size_t)4 * A.g.cvb * V * sizeof(float) : 0;
-  node_fwd_kernel<T, 4><<<grid, 256, smem, st>>>(A);
+  NPP_LAUNCH((node_fwd_kernel<T, 4>), grid, 256, smem, st, A);
   NPP_CHECK_LAUNCH("node_fwd_kernel");
   return NPP_OK;
 }
@@ -257,6 +258,7 @@ struct NodeBwdReduceArgs {
 // two resident blocks per SM and it spilled (ptxas: 168 bytes), slowing every node backward of the step.
 template <typename T, int U, bool HAS2>
 __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdReduceArgs<T> A) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   __shared__ float red[256 * V];
   const int tcv = threadIdx.x % A.g.cvb;
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(256, 2) node_bwd_reduce_kernel(const NodeBwdRe
 // out[j] = sum_i partials[i][j]   (rows x len), 32 columns x 8 row groups per block
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int rows, int len,
                                                               float* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rg = threadIdx.x >> 5;
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // optimizer's flat gradient buffer instead of going through one autograd accumulation kernel per parameter).
 __global__ void __launch_bounds__(256) reduce_partials_acc_kernel(const float* __restrict__ partials, int rows, int len,
                                                                   float* __restrict__ out, int seg_len, AccSegs acc) {
+  pdl_wait();
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rg = threadIdx.x >> 5;
@@ -502,9 +506,9 @@ static int node_bwd_reduce_t(const npp_view4* graw, const npp_view4* grelu, cons
   if (A.g.gy != 1) return NPP_E_UNSUPPORTED;
   dim3 grid((unsigned)node_bwd_blocks(npix, ref->c, V), 1);
   if (graw2 || grelu2)
-    node_bwd_reduce_kernel<T, 1, true><<<grid, 256, 0, st>>>(A);
+    NPP_LAUNCH((node_bwd_reduce_kernel<T, 1, true>), grid, 256, 0, st, A);
   else
-    node_bwd_reduce_kernel<T, 2, false><<<grid, 256, 0, st>>>(A);
+    NPP_LAUNCH((node_bwd_reduce_kernel<T, 2, false>), grid, 256, 0, st, A);
   NPP_CHECK_LAUNCH("node_bwd_reduce_kernel");
   return NPP_OK;
 }
@@ -565,6 +569,7 @@ __device__ __forceinline__ void bn_bwd_coef(const float* gamma, const float* mea
 // for the same register-budget reason as HAS2 above.
 template <typename T, int U, bool STRIPED>
 __global__ void __launch_bounds__(256, 2) node_bwd_apply_kernel(const NodeBwdApplyArgs<T> A) {
+  pdl_wait();
   constexpr int V = Pack<T>::N;
   const int tcv = threadIdx.x % A.geom.cvb;
   const int trow = threadIdx.x / A.geom.cvb;
@@ -643,9 +648,9 @@ static int node_bwd_apply_t(const npp_view4* g, const npp_view4* a, const float*
   A.geom = vec_geom(g->c, V);
   dim3 grid((unsigned)stream_grid(npix, A.geom, 4, 8), (unsigned)A.geom.gy);
   if (A.stripes > 1 || acc)
-    node_bwd_apply_kernel<T, 4, true><<<grid, 256, 0, st>>>(A);
+    NPP_LAUNCH((node_bwd_apply_kernel<T, 4, true>), grid, 256, 0, st, A);
   else
-    node_bwd_apply_kernel<T, 4, false><<<grid, 256, 0, st>>>(A);
+    NPP_LAUNCH((node_bwd_apply_kernel<T, 4, false>), grid, 256, 0, st, A);
   NPP_CHECK_LAUNCH("node_bwd_apply_kernel");
   return NPP_OK;
 }
@@ -847,7 +852,7 @@ int npp_node_bwd_apply_striped(const npp_view4* g, const npp_view4* a, const flo
 
 int npp_reduce_partials(const float* partials, int rows, int len, float* out, npp_stream_t s) {
   if (!partials || !out || rows <= 0 || len <= 0) return NPP_E_INVALID;
-  reduce_partials_kernel<<<(len + 31) / 32, 256, 0, as_stream(s)>>>(partials, rows, len, out);
+  NPP_LAUNCH((reduce_partials_kernel), (len + 31) / 32, 256, 0, as_stream(s), partials, rows, len, out);
   NPP_CHECK_LAUNCH("reduce_partials_kernel");
   return NPP_OK;
 }
@@ -864,7 +869,7 @@ int npp_reduce_partials_acc(const float* partials, int rows, int len, float* out
     A.s[i].valid = on ? acc_valid[i] : 0;
     if (on && (acc_valid[i] < 0 || acc_valid[i] > seg_len)) return NPP_E_INVALID;
   }
-  reduce_partials_acc_kernel<<<(len + 31) / 32, 256, 0, as_stream(s)>>>(partials, rows, len, out, seg_len, A);
+  NPP_LAUNCH((reduce_partials_acc_kernel), (len + 31) / 32, 256, 0, as_stream(s), partials, rows, len, out, seg_len, A);
   NPP_CHECK_LAUNCH("reduce_partials_acc_kernel");
   return NPP_OK;
 }

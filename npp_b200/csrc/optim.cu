@@ -21,6 +21,7 @@ static_assert(sizeof(AdamTensor) == 56, "table layout is part of the ABI (npp_b2
 __global__ void __launch_bounds__(256)
 adam_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
             const int* __restrict__ chunk_index, int chunk_elems, float beta1, float beta2, float eps) {
+  pdl_wait();
   const AdamTensor t = tensors[chunk_tensor[blockIdx.x]];
   const int64_t begin = (int64_t)chunk_index[blockIdx.x] * chunk_elems;
   int64_t end = begin + chunk_elems;
@@ -43,6 +44,7 @@ adam_kernel(const AdamTensor* __restrict__ tensors, const int* __restrict__ chun
 }
 
 __global__ void adam_bump_step_kernel(const AdamTensor* __restrict__ tensors, int ntensors) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ntensors) *tensors[i].step += 1;
 }
@@ -59,10 +61,10 @@ int npp_adam_step(const void* tensor_table, int ntensors, const int32_t* chunk_t
     return NPP_E_INVALID;
   if (nchunks == 0) return NPP_OK;
   cudaStream_t st = as_stream(s);
-  adam_kernel<<<nchunks, 256, 0, st>>>(static_cast<const AdamTensor*>(tensor_table), chunk_tensor, chunk_index,
+  NPP_LAUNCH((adam_kernel), nchunks, 256, 0, st, static_cast<const AdamTensor*>(tensor_table), chunk_tensor, chunk_index,
                                        chunk_elems, beta1, beta2, eps);
   NPP_CHECK_LAUNCH("adam_kernel");
-  adam_bump_step_kernel<<<(ntensors + 255) / 256, 256, 0, st>>>(static_cast<const AdamTensor*>(tensor_table), ntensors);
+  NPP_LAUNCH((adam_bump_step_kernel), (ntensors + 255) / 256, 256, 0, st, static_cast<const AdamTensor*>(tensor_table), ntensors);
   NPP_CHECK_LAUNCH("adam_bump_step_kernel");
   return NPP_OK;
 }

@@ -67,6 +67,7 @@ struct PeerArgs {
 // element carries the current sequence number (one NVLink one-way latency after the slowest peer started), then adds
 // the rows in rank order.
 __global__ void __launch_bounds__(512, 1) peer_allreduce_kernel(const PeerArgs A) {
+  pdl_wait();
   __shared__ unsigned int s_seq;
   PeerBuf* me = A.bufs[A.rank];
   if (threadIdx.x == 0) s_seq = me->seq + 1u;
@@ -180,7 +181,7 @@ int npp_peer_allreduce(const npp_peer_comm* comm, const float* src0, float* dst0
   A.src0 = src0; A.dst0 = dst0; A.n0 = n0;
   A.src1 = src1; A.dst1 = dst1; A.n1 = n1;
   A.timeout_ns = comm->timeout_ms > 0 ? (unsigned long long)comm->timeout_ms * 1000000ull : 30000000000ull;
-  npp::peer_allreduce_kernel<<<1, 512, 0, npp::as_stream(stream)>>>(A);
+  NPP_LAUNCH((npp::peer_allreduce_kernel), 1, 512, 0, npp::as_stream(stream), A);
   NPP_CHECK_LAUNCH("peer_allreduce_kernel");
   return NPP_OK;
 }

@@ -1,5 +1,6 @@
 // Library-level state: version string, thread-local error text, cached SM count.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 
@@ -15,6 +16,15 @@ void set_error(const char* what, cudaError_t e) {
 void set_error_str(const char* what) {
   strncpy(g_err, what, sizeof g_err - 1);
   g_err[sizeof g_err - 1] = 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NPP_PDL");
+    v = (e && *e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int sm_count() {

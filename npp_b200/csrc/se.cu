@@ -25,6 +25,7 @@ static int gap_fwd_t(const npp_view4* x, float* g, cudaStream_t st) {
 __global__ void __launch_bounds__(1024) se_fc_fwd_kernel(const float* __restrict__ g, const float* __restrict__ w1, const float* __restrict__ b1,
                                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ hbuf,
                                  float* __restrict__ s, int C) {
+  pdl_wait();
   extern __shared__ float sm[];
   float* sg = sm;       // C
   float* sh = sm + C;   // C/2
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(1024) se_fc_bwd_kernel(const float* __restrict
                                  const float* __restrict__ ds, const float* __restrict__ w1, const float* __restrict__ w2,
                                  float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
                                  float* __restrict__ db2, float* __restrict__ dg, int C) {
+  pdl_wait();
   extern __shared__ float sm[];
   float* dz2 = sm;            // C
   float* sg = sm + C;         // C
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(1024) se_fc_bwd_vec_kernel(const float* __rest
                                                              const float* __restrict__ w2, float* __restrict__ db1,
                                                              float* __restrict__ db2, float* __restrict__ dz2g,
                                                              float* __restrict__ dz1g, float* __restrict__ dg, int C) {
+  pdl_wait();
   extern __shared__ float sm[];
   float* dz2 = sm;          // C
   float* sh = sm + C;       // C/2
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_outer_kernel(const float* __res
                                                               const float* __restrict__ dz2g,
                                                               const float* __restrict__ dz1g, float* __restrict__ dw1,
                                                               float* __restrict__ dw2, int N, int C) {
+  pdl_wait();
   const int Ch = C / 2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 2 * C * Ch) return;
@@ -214,7 +218,7 @@ int npp_se_fc_fwd(const float* g, const float* w1, const float* b1, const float*
   if (!g || !w1 || !w2 || !hbuf || !sg || n <= 0 || c <= 1 || (c & 1)) return NPP_E_INVALID;
   const size_t smem = (size_t)(c + c / 2) * sizeof(float);
   if (smem > 48 * 1024) return NPP_E_UNSUPPORTED;
-  se_fc_fwd_kernel<<<n, 1024, smem, as_stream(s)>>>(g, w1, b1, w2, b2, hbuf, sg, c);
+  NPP_LAUNCH((se_fc_fwd_kernel), n, 1024, smem, as_stream(s), g, w1, b1, w2, b2, hbuf, sg, c);
   NPP_CHECK_LAUNCH("se_fc_fwd_kernel");
   return NPP_OK;
 }
@@ -224,7 +228,7 @@ int npp_se_fc_bwd(const float* g, const float* hbuf, const float* sg, const floa
     return NPP_E_INVALID;
   const size_t smem = (size_t)(3 * c) * sizeof(float);
   if (smem > 48 * 1024) return NPP_E_UNSUPPORTED;
-  se_fc_bwd_kernel<<<n, 1024, smem, as_stream(s)>>>(g, hbuf, sg, ds, w1, w2, dw1, db1, dw2, db2, dg, c);
+  NPP_LAUNCH((se_fc_bwd_kernel), n, 1024, smem, as_stream(s), g, hbuf, sg, ds, w1, w2, dw1, db1, dw2, db2, dg, c);
   NPP_CHECK_LAUNCH("se_fc_bwd_kernel");
   return NPP_OK;
 }
@@ -237,10 +241,10 @@ int npp_se_fc_bwd2(const float* g, const float* hbuf, const float* sg, const flo
   if (smem > 48 * 1024) return NPP_E_UNSUPPORTED;
   float* dz2g = scratch;                      // [n][c]
   float* dz1g = scratch + (size_t)n * c;      // [n][c/2]
-  se_fc_bwd_vec_kernel<<<n, 1024, smem, as_stream(s)>>>(hbuf, sg, ds, w1, w2, db1, db2, dz2g, dz1g, dg, c);
+  NPP_LAUNCH((se_fc_bwd_vec_kernel), n, 1024, smem, as_stream(s), hbuf, sg, ds, w1, w2, db1, db2, dz2g, dz1g, dg, c);
   NPP_CHECK_LAUNCH("se_fc_bwd_vec_kernel");
   const int total = c * c;                    // 2 * c * c/2 weight-gradient elements
-  se_fc_bwd_outer_kernel<<<(total + 255) / 256, 256, 0, as_stream(s)>>>(g, hbuf, dz2g, dz1g, dw1, dw2, n, c);
+  NPP_LAUNCH((se_fc_bwd_outer_kernel), (total + 255) / 256, 256, 0, as_stream(s), g, hbuf, dz2g, dz1g, dw1, dw2, n, c);
   NPP_CHECK_LAUNCH("se_fc_bwd_outer_kernel");
   return NPP_OK;
 }

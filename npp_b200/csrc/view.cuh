@@ -46,6 +46,7 @@ static inline VecGeom vec_geom(int C, int VEC) {
 // f(n, h, w, c0) for every pixel and every channel vector (c0 multiple of VEC).
 template <int VEC, typename F>
 __global__ void __launch_bounds__(256) foreach_vec_kernel(int npix, int H, int W, VecGeom g, F f) {
+  pdl_wait();
   const int tcv = threadIdx.x % g.cvb;
   const int trow = threadIdx.x / g.cvb;
   const int mycv = blockIdx.y * g.cvb + tcv;
@@ -71,7 +72,7 @@ static inline int foreach_vec(int N, int H, int W, int C, cudaStream_t st, const
   const int64_t cap = ((int64_t)sm_count() * 16 + g.gy - 1) / g.gy;  // ~16 resident 256-thread blocks per SM
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)g.gy);
-  foreach_vec_kernel<VEC, F><<<grid, 256, 0, st>>>((int)npix64, H, W, g, f);
+  NPP_LAUNCH((foreach_vec_kernel<VEC, F>), grid, 256, 0, st, (int)npix64, H, W, g, f);
   NPP_CHECK_LAUNCH(name);
   return NPP_OK;
 }
@@ -120,6 +121,7 @@ __device__ __forceinline__ void block_colsum(float* red, int rows, int ncol) {
 template <int VEC, int K, typename F>
 __global__ void __launch_bounds__(256) reduce_ch_kernel(int npix, int H, int W, int C, VecGeom g, int per_image,
                                                         float* out, int64_t out_kstride, int64_t out_cstride, F f) {
+  pdl_wait();
   __shared__ float red[256 * VEC];
   const int tcv = threadIdx.x % g.cvb;
   const int trow = threadIdx.x / g.cvb;
@@ -177,7 +179,7 @@ static inline int reduce_ch(int N, int H, int W, int C, bool per_image, float* o
   if (gx > max_by_work) gx = max_by_work;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)g.gy, (unsigned)z);
-  reduce_ch_kernel<VEC, K, F><<<grid, 256, 0, st>>>((int)npix, H, W, C, g, per_image ? 1 : 0, out, out_kstride,
+  NPP_LAUNCH((reduce_ch_kernel<VEC, K, F>), grid, 256, 0, st, (int)npix, H, W, C, g, per_image ? 1 : 0, out, out_kstride,
                                                     out_cstride, f);
   NPP_CHECK_LAUNCH(name);
   return NPP_OK;
