@@ -33,7 +33,12 @@ static inline cudaStream_t as_stream(npp_stream_t s) { return reinterpret_cast<c
 // completed and its memory is visible.  Every thread of every block executes the wait before it touches global
 // memory or exits, so completion stays transitive along the stream (C after B after A).  The launch attribute is
 // captured into CUDA graphs as a programmatic edge.  NPP_PDL=0 launches everything fully serialized (A/B, bisecting).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// wait, then let the NEXT grid in the stream be scheduled as soon as every block of this grid has got this far: its
+// blocks take the SMs this grid frees while its last wave drains and sit in their own wait until this grid is done.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

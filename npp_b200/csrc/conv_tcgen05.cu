@@ -77,7 +77,6 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
                  const float* __restrict__ bias, float* __restrict__ stats) {
-  pdl_wait();
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -120,6 +119,8 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (tensor-map prefetch, mbarrier init, TMEM allocation) overlaps the tail of the previous kernel
+  pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int num_k = g.num_taps * g.kc_blocks;
@@ -444,7 +445,6 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
                   const float* __restrict__ bias, float* __restrict__ stats) {
-  pdl_wait();
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -486,6 +486,8 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (tensor-map prefetch, mbarrier init, TMEM allocation) overlaps the tail of the previous kernel
+  pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int num_k = g.num_taps * g.kc_blocks;
@@ -633,7 +635,6 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* __restrict__ bias,
              float* __restrict__ stats) {
-  pdl_wait();
   constexpr int B_BYTES = BN * 128;
   constexpr int TMEM_COLS = 4 * BN;  // 2 accumulator stages x 2 pixel halves; 128 / 256 / 512
   constexpr int SLABS = BN >= 64 ? BN / 64 : 1;
@@ -683,6 +684,8 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (tensor-map prefetch, mbarrier init, TMEM allocation) overlaps the tail of the previous kernel
+  pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp == 0) {
@@ -865,7 +868,6 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTable taps,
                   float* __restrict__ dw, float* __restrict__ ws) {
-  pdl_wait();
   using Cfg = WgradCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int SLAB = Cfg::KP * 128;  // bytes of one [64 pixels x 64 channels] slab
@@ -913,6 +915,8 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (tensor-map prefetch, mbarrier init, TMEM allocation) overlaps the tail of the previous kernel
+  pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (num_k > 0) {
@@ -1033,7 +1037,6 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                    const W3Geom g, float* __restrict__ dw, float* __restrict__ ws) {
-  pdl_wait();
   constexpr int A_BYTES = 2 * 64 * 128;  // two 64-channel slabs of dY, 64 pixels each
   constexpr int ASLAB = 64 * 128;
   constexpr int TMEM_COLS = (3 * BN <= 256) ? 256 : 512;
@@ -1078,6 +1081,8 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (tensor-map prefetch, mbarrier init, TMEM allocation) overlaps the tail of the previous kernel
+  pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (num_k > 0) {
