@@ -33,12 +33,10 @@ static inline cudaStream_t as_stream(npp_stream_t s) { return reinterpret_cast<c
 // completed and its memory is visible.  Every thread of every block executes the wait before it touches global
 // memory or exits, so completion stays transitive along the stream (C after B after A).  The launch attribute is
 // captured into CUDA graphs as a programmatic edge.  NPP_PDL=0 launches everything fully serialized (A/B, bisecting).
-// wait, then let the NEXT grid in the stream be scheduled as soon as every block of this grid has got this far: its
-// blocks take the SMs this grid frees while its last wave drains and sit in their own wait until this grid is done.
-__device__ __forceinline__ void pdl_wait() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
+// (An early `griddepcontrol.launch_dependents` right after the wait — next grid's blocks resident while this grid's last
+// wave drains — was measured SLOWER on B200: 101.7 vs 99.7 ms per training step, profiles/r02_pdl_ab.txt; the waiting
+// blocks take registers / shared memory away from the draining grid.  Wait-only PDL: 99.9 vs 100.15 ms.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

@@ -533,27 +533,39 @@ __global__ void ohem_scan_kernel(unsigned int* ws) {
   ws[threadIdx.x] = 0;
 }
 
+// out3 = {sum of kept losses, number of kept pixels, threshold}.  The kept count is accumulated as a 64-bit INTEGER in
+// the workspace (ws[260..261]; exact beyond 2^24 pixels and independent of the atomic order) and converted to fp32 once
+// by the last block to finish (ticket in ws[262]); the workspace arrives zeroed.
 __global__ void __launch_bounds__(256)
-ohem_sum_kernel(const float* __restrict__ prob, const float* __restrict__ loss, int64_t npix, const unsigned int* ws,
+ohem_sum_kernel(const float* __restrict__ prob, const float* __restrict__ loss, int64_t npix, unsigned int* ws,
                 float thres, float* __restrict__ out3) {
   pdl_wait();
-  __shared__ float rs[8], rc[8];
+  __shared__ float rs[8];
+  __shared__ unsigned int rc[8];
   const float kth = ws[257] == 0xffffffffu ? 0.f : __uint_as_float(ws[256]);
   const float thr = fmaxf(kth, thres);
-  float s = 0.f, c = 0.f;
+  float s = 0.f;
+  unsigned int c = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
-    if (prob[i] < thr) { s += loss[i]; c += 1.f; }
+    if (prob[i] < thr) { s += loss[i]; ++c; }
   }
   s = warp_sum(s);
-  c = warp_sum(c);
+  c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rc[threadIdx.x >> 5] = c; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f;
+    unsigned long long b = 0;
     for (int i = 0; i < 8; ++i) { a += rs[i]; b += rc[i]; }
+    unsigned long long* kept = reinterpret_cast<unsigned long long*>(ws + 260);
     atomicAdd(out3, a);
-    atomicAdd(out3 + 1, b);
+    if (b) atomicAdd(kept, b);
     if (blockIdx.x == 0) out3[2] = thr;
+    __threadfence();
+    if (atomicAdd(ws + 262, 1u) == gridDim.x - 1) {   // last block: every count has landed
+      __threadfence();
+      out3[1] = (float)*reinterpret_cast<volatile unsigned long long*>(kept);
+    }
   }
 }
 

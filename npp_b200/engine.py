@@ -103,6 +103,16 @@ class TrainStep:
         self.packer = F_.WeightPacker(model) if dev.type == "cuda" else None   # all conv weights: one launch per step
         self._stage = None       # prefetch(): staging copies of the inputs, filled on a side stream
         self._staged = False
+        if world_size > 1:
+            # SyncBN here scales the local pixel count by the group size (one 2C-float message per BatchNorm instead of
+            # torch's (mean, invstd, count) gather), which is only right when every rank holds the same batch
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                sizes = [None] * dist.get_world_size()
+                dist.all_gather_object(sizes, (int(batch), int(size)))
+                if len(set(sizes)) != 1:
+                    raise RuntimeError("TrainStep needs the same per-rank batch on every rank (SyncBN statistics assume "
+                                       "equal sample counts; use drop_last), got %s" % (sizes,))
 
     # ---- pieces ------------------------------------------------------------------------------------
     def load(self, images, par_lab, edge_lab, pose_gt, pose_aux_gt, non_blocking=True):
