@@ -130,10 +130,11 @@ def enable_sync_bn(group=True, peer=None):
     `group`: True for the default process group, a ProcessGroup, or None/False to disable.
     `peer`: exchange the statistic vectors over NVLink peer memory (PeerComm) instead of NCCL all-reduces; default =
     whenever the process group is NCCL on CUDA with 2..8 ranks (NPP_SYNCBN_PEER=0 forces NCCL)."""
-    old = F_._state.get("peer_comm")
-    if old is not None:
-        F_._state["peer_comm"] = None
-        old.close()
+    for key in ("peer_comm", "peer_comm_side"):
+        old = F_._state.get(key)
+        if old is not None:
+            F_._state[key] = None
+            old.close()
     F_._state["sync_bn"] = group if group else None
     if not group or not (dist.is_available() and dist.is_initialized()):
         return
@@ -144,9 +145,11 @@ def enable_sync_bn(group=True, peer=None):
     if peer:
         try:
             F_._state["peer_comm"] = PeerComm(pg)
+            if F_._state.get("two_streams"):     # the second task stream issues its own sequence of exchanges
+                F_._state["peer_comm_side"] = PeerComm(pg)
         except Exception as exc:   # no peer access / IPC unavailable: the NCCL transport still works
             warnings.warn("SyncBN peer-memory exchange unavailable (%r): using NCCL all-reduces" % (exc,))
-            F_._state["peer_comm"] = None
+            F_._state["peer_comm"] = F_._state["peer_comm_side"] = None
 
 
 def peer_comm():

@@ -38,7 +38,12 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           "pack_tiles": os.environ.get("NPP_PACK_TILES", "0") != "0",
           # NPP_CE_BWD_SEP=1 -> cross-entropy backward as per-pixel gradient + separable bilinear backward instead of
           # the shared-memory-atomic kernel (round-2 candidate; core/criterion.py, csrc/loss.cu ce_grad_kernel)
-          "ce_bwd_sep": os.environ.get("NPP_CE_BWD_SEP", "0") != "0"}
+          "ce_bwd_sep": os.environ.get("NPP_CE_BWD_SEP", "0") != "0",
+          # NPP_TWO_STREAMS=1 -> the two task streams of the networks (cells1 / cells2, upsamples1 / upsamples2: the
+          # same shapes, independent between the interaction points) are issued on two CUDA streams, so that inside a
+          # captured step they are parallel graph branches: the small 12^2 / 24^2 / 48^2 launches of one stream fill
+          # the SMs the other leaves idle (see TaskStreams below)
+          "two_streams": os.environ.get("NPP_TWO_STREAMS", "0") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -135,6 +140,77 @@ def zeros_f32(n, device):
         if t is not None:
             return t
     return torch.zeros(int(n), dtype=torch.float32, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# two task streams on two CUDA streams
+# ------------------------------------------------------------------------------------------------
+class TaskStreams:
+    """Issues the second task stream of a network (parsing: cells2, upsamples2, their stems) on a side CUDA stream.
+    The two streams are independent between the interaction points of Network.forward, so inside a captured training
+    step they become parallel graph branches; autograd runs every backward node on the stream of its forward, so the
+    backward pass is parallel too.
+
+        ts = TaskStreams(x)                 # main = the current stream
+        ts.fork(x)                          # side waits for main; x (produced on main) may now be read on side
+        with ts.side(): s3 = cell2(s2, s3)  # kernels + allocations of the block go to the side stream
+        ts.join(s3)                         # main waits for side; s3 (produced on side) may now be read on main
+
+    Memory safety: a tensor lives in the caching allocator's pool of the stream it was allocated on; every handle that
+    crosses (fork / join arguments) is marked with record_stream for the other stream, so its block is not reused
+    before that stream is done with it (during CUDA-graph capture: not before the capture ends).  Persistent scratch
+    is per stream (_wgrad_workspace) or handed out once per step (ZeroArena); SyncBN exchanges of the side stream use
+    their own communicator (distributed.enable_sync_bn creates two)."""
+    _side = {}
+
+    def __init__(self, ref, enabled=True):
+        self.on = bool(enabled) and bool(_state.get("two_streams")) and ref.is_cuda
+        if not self.on:
+            return
+        self.main = torch.cuda.current_stream()
+        idx = ref.device.index
+        if idx not in TaskStreams._side:
+            TaskStreams._side[idx] = torch.cuda.Stream(device=ref.device)
+        self.b = TaskStreams._side[idx]
+
+    @staticmethod
+    def side_stream_of(device_index):
+        return TaskStreams._side.get(device_index)
+
+    def fork(self, *handles):
+        if self.on:
+            share(handles, self.b)
+            self.b.wait_stream(self.main)
+
+    def join(self, *handles):
+        if self.on:
+            share(handles, self.main)
+            self.main.wait_stream(self.b)
+
+    def side(self):
+        import contextlib
+        return torch.cuda.stream(self.b) if self.on else contextlib.nullcontext()
+
+
+def share(h, stream):
+    """record_stream on every tensor behind a handle (tensor, relu-only handle, Pending, list of handles)."""
+    if h is None:
+        return
+    if isinstance(h, (list, tuple)):
+        for e in h:
+            share(e, stream)
+        return
+    if isinstance(h, Pending):
+        share([h.y, h.stats, h.raw, h.relu] + list(h.spare), stream)
+        return
+    if torch.is_tensor(h) and h.is_cuda and h.numel():
+        h.record_stream(stream)
+        for attr in ("_npp_relu", "_npp_im2col"):
+            t = getattr(h, attr, None)
+            if isinstance(t, tuple):        # the im2col cache: (key, tensor)
+                t = t[1]
+            if torch.is_tensor(t) and t is not h and t.is_cuda:
+                t.record_stream(stream)
 
 
 def grad_slot(p):
@@ -263,9 +339,9 @@ def check_raw(x, what):
 # dense convolution
 # ------------------------------------------------------------------------------------------------
 def _wgrad_workspace(device):
-    """One persistent fp32 workspace per device for the split-K partial tiles of npp_conv2d_wgrad_ws (every wgrad
-    call of a stream reuses it; stream order keeps the calls apart)."""
-    key = ("wgrad_ws", torch.device(device).index)
+    """One persistent fp32 workspace per (device, stream) for the split-K partial tiles of npp_conv2d_wgrad_ws (every
+    wgrad call of a stream reuses it; stream order keeps the calls apart)."""
+    key = ("wgrad_ws", torch.device(device).index, torch.cuda.current_stream().cuda_stream)
     ws = _state.get(key)
     if ws is None:
         L.lib().npp_conv2d_wgrad_workspace_bytes.restype = ctypes.c_int64
@@ -624,6 +700,9 @@ def _allreduce_sum(t, t2=None):
     grp = None if g is True else g
     comm = _state.get("peer_comm")
     if comm is not None and t.is_cuda:
+        side = TaskStreams.side_stream_of(t.device.index)
+        if side is not None and _state.get("peer_comm_side") is not None and torch.cuda.current_stream() == side:
+            comm = _state["peer_comm_side"]     # exchanges of the second task stream: own sequence counter
         comm.allreduce(t, t2)
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=grp)

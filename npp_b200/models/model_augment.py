@@ -468,10 +468,19 @@ class Network(nn.Module):
 
     def forward(self, x):
         x = F_.to_internal(x)
+        # The pose stream (stem0-2, cells1, upsamples1) runs on the current CUDA stream, the parsing stream (stem3-5,
+        # cells2, upsamples2) on a side stream when F_._state["two_streams"] is set: they only meet at the interaction
+        # points, where the side stream is joined, the cross-task messages are computed and the side stream is forked
+        # again.  ts.fork / ts.join also mark the handles that cross for the caching allocator.
+        ts = F_.TaskStreams(x, enabled=self._trace is None)
+        if ts.on and x.dtype == torch.bfloat16 and x.shape[1] == 8 and not x.requires_grad and F_._state.get("stem_im2col", True):
+            F_.im2col3x3_c3(x, 2, 1)        # the tap-folded image both stems read: computed once, before the fork
+        ts.fork(x)
         s0 = self.stem1(self.stem0(x))
         s1 = self.stem2(s0)
-        s2 = self.stem4(self.stem3(x))
-        s3 = self.stem5(s2)
+        with ts.side():
+            s2 = self.stem4(self.stem3(x))
+            s3 = self.stem5(s2)
         self._tr("stem2", s1)
         self._tr("stem5", s3)
         f1, f2 = [], []           # per-stream feature pyramids (fine -> coarse, then decoder outputs)
@@ -485,12 +494,14 @@ class Network(nn.Module):
             tap = i in self._tap_layers
             two = (not tap) and i + 2 < len(self.cells1) and self._trace is None
             o1 = cell1(s0, s1, out_raw=tap, out_relu=True, n_out=2 if two else None)
-            o3 = cell2(s2, s3, out_raw=tap, out_relu=True, n_out=2 if two else None)
+            with ts.side():
+                o3 = cell2(s2, s3, out_raw=tap, out_relu=True, n_out=2 if two else None)
             s0, s2 = (n1 if n1 is not None else s1), (n3 if n3 is not None else s3)
             (s1, n1), (s3, n3) = (o1, o3) if two else ((o1, None), (o3, None))
             self._tr("relu(cells1.%d)" % i, s1, relu=True)
             self._tr("relu(cells2.%d)" % i, s3, relu=True)
             if i in self._tap_layers:
+                ts.join(s3)                  # the parsing stream's stage output is read by the interaction ops below
                 f1.append(s1)
                 f2.append(s3)
                 z1, c1 = self._exchange(self._ops1, c1, self._indices1[stage], f2)
@@ -501,13 +512,16 @@ class Network(nn.Module):
                 self._tr("f2.%d" % stage, s3)
                 stage += 1
                 f1[-1], f2[-1] = s1, s3
+                ts.fork(s3)                  # ... and its updated state goes back to the side stream
 
         # decoder: three upsample cells per stream with interaction after each (:453-533)
         c1 = c2 = 0
         prev1, prev2 = f1[3], f2[3]
         for d in range(3):
             o1 = self.upsamples1[d](prev1, f1[2 - d])
-            o2 = self.upsamples2[d](prev2, f2[2 - d])
+            with ts.side():
+                o2 = self.upsamples2[d](prev2, f2[2 - d])
+            ts.join(o2)
             f1.append(o1)
             f2.append(o2)
             z1, c1 = self._exchange(self.up_ops1, c1, self.up_indices1[d], f2)
@@ -517,6 +531,8 @@ class Network(nn.Module):
             self._tr("f1.%d" % (4 + d), o1)
             self._tr("f2.%d" % (4 + d), o2)
             f1[-1], f2[-1] = o1, o2
+            if d < 2:
+                ts.fork(o2)
             prev1, prev2 = o1, o2
 
         def pyramid(f):  # (:538-543); only read through the nn.ReLU of the four 1x1 layers: relu(cat) is written directly
