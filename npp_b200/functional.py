@@ -211,6 +211,8 @@ def share(h, stream):
                 t = t[1]
             if torch.is_tensor(t) and t is not h and t.is_cuda:
                 t.record_stream(stream)
+                if getattr(t, "_npp_home", None) is not None:
+                    t._npp_ok = set(getattr(t, "_npp_ok", ())) | {stream.cuda_stream}
 
 
 def grad_slot(p):
@@ -304,27 +306,32 @@ def relu(x):
     state (each starts with its own nn.ReLU, operations.py:76,212) share one pass — and normally it already
     exists: the kernel that produced the state wrote relu(state) next to it (node())."""
     if isinstance(x, Pending):
-        if x.relu is None:
-            if x.fan > 1:    # several consumers announced (set_fanout): one handle each, gradients summed in the node
-                _, rels = node(x, None, want_raw=False, want_relu=True, fan=(1, x.fan))
-                x.relu, x.spare = rels[0], list(rels[1:])
-            else:
-                _, x.relu = node(x, None, want_raw=False, want_relu=True)
-            return x.relu
+        materialize(x)
         return x.spare.pop(0) if x.spare else x.relu
     y = relu_of(x)
     if y is None:
         y = _ReluFn.apply(x)
         y._npp_is_relu = True
+        if _state.get("two_streams") and y.is_cuda:
+            y._npp_home = torch.cuda.current_stream().cuda_stream    # a lazily created cache entry: see relu_of
         x._npp_relu = y
     return y
 
 
 def relu_of(x):
-    """relu(x) if it already exists (written by the producer of x, or x is itself a ReLU output), else None."""
+    """relu(x) if it already exists (written by the producer of x, or x is itself a ReLU output), else None.
+    With two task streams a relu that was created lazily by a consumer on ONE stream is not visible to the other
+    (no ordering, no allocator mark) unless the handle has crossed a TaskStreams fork / join since (share())."""
     if getattr(x, "_npp_is_relu", False):
         return x
-    return getattr(x, "_npp_relu", None)
+    y = getattr(x, "_npp_relu", None)
+    if y is not None:
+        home = getattr(y, "_npp_home", None)
+        if home is not None:
+            cur = torch.cuda.current_stream().cuda_stream
+            if cur != home and cur not in getattr(y, "_npp_ok", ()):
+                return None
+    return y
 
 
 def check_raw(x, what):
@@ -832,6 +839,19 @@ def set_fanout(p, n):
     if isinstance(p, Pending) and p.relu is None:
         p.fan = max(1, int(n))
     return p
+
+
+def materialize(x):
+    """Computes relu(bn(.)) of a Pending BatchNorm output NOW (on the current stream) without handing a consumer
+    handle out; relu(x) then only distributes handles.  Used before a TaskStreams fork so that the tensor exists — and
+    is marked for the other stream — before consumers on both streams ask for it."""
+    if isinstance(x, Pending) and x.relu is None:
+        if x.fan > 1:    # several consumers announced (set_fanout): one handle each, gradients summed in the node
+            _, rels = node(x, None, want_raw=False, want_relu=True, fan=(1, x.fan))
+            x.relu, x.spare = rels[-1], list(rels)       # the canonical handle doubles as the last one handed out
+        else:
+            _, x.relu = node(x, None, want_raw=False, want_relu=True)
+    return x
 
 
 def finish(p):

@@ -531,8 +531,7 @@ class Network(nn.Module):
             self._tr("f1.%d" % (4 + d), o1)
             self._tr("f2.%d" % (4 + d), o2)
             f1[-1], f2[-1] = o1, o2
-            if d < 2:
-                ts.fork(o2)
+            ts.fork(o2)
             prev1, prev2 = o1, o2
 
         def pyramid(f):  # (:538-543); only read through the nn.ReLU of the four 1x1 layers: relu(cat) is written directly
@@ -540,42 +539,58 @@ class Network(nn.Module):
                                 F_.interpolate(f[5], scale_factor=2, mode="bilinear", align_corners=True),
                                 F_.interpolate(f[4], scale_factor=4, mode="bilinear", align_corners=True)])
 
-        x1, x2 = pyramid(f1), pyramid(f2)
         # Pending BatchNorm outputs: the heads and refinement cells all start with nn.ReLU, so relu(bn(.)) is
-        # produced once per tensor and the raw values are never materialised
-        in1 = self.pose_auxlayer.lazy(x1)
-        in2 = self.edge_layer.lazy(x2)
-        in3 = self.pose_layer.lazy(x1)
-        in4 = self.par_layer.lazy(x2)
+        # produced once per tensor and the raw values are never materialised.  The pose half stays on the main stream,
+        # the parsing half (pyramid of f2, edge / parsing layers, heads and ParCell) runs on the side stream.
         split = self.refine_layers == 1 and self._trace is None
+        x1 = pyramid(f1)
+        in1 = self.pose_auxlayer.lazy(x1)
+        in3 = self.pose_layer.lazy(x1)
         if split:   # relu(bn(.)) of the four layer outputs is read by a head and by one / two refinement cells each
-            F_.set_fanout(in1, 2), F_.set_fanout(in2, 2), F_.set_fanout(in3, 3), F_.set_fanout(in4, 3)
+            F_.set_fanout(in1, 2), F_.set_fanout(in3, 3)
+        if ts.on:
+            F_.materialize(in1), F_.materialize(in3)
+        with ts.side():
+            x2 = pyramid(f2)
+            in2 = self.edge_layer.lazy(x2)
+            in4 = self.par_layer.lazy(x2)
+            if split:
+                F_.set_fanout(in2, 2), F_.set_fanout(in4, 3)
+            if ts.on:
+                F_.materialize(in2), F_.materialize(in4)
         for nm, t in (("relu(pose_auxlayer)", in1), ("relu(edge_layer)", in2), ("relu(pose_layer)", in3),
                       ("relu(par_layer)", in4)):
             self._tr(nm, t, relu=True)
 
         pose_list, par_list = [], []
+        side_outputs = []
 
-        def emit(stage_idx):
-            edge = self.edge_head[stage_idx](in2)
-            pose_aux = self.pose_auxnet[stage_idx](in1)
-            pose_map = self.pose_head[stage_idx](in3)
-            par_map = self.par_head[stage_idx](in4)
+        def emit(stage_idx, p1, p2, p3, p4):
+            pose_aux = self.pose_auxnet[stage_idx](p1)
+            pose_map = self.pose_head[stage_idx](p3)
             pose_list.append([F_.from_internal(pose_map, self._num_joints), F_.from_internal(pose_aux, self._num_joints)])
-            par_list.append([F_.from_internal(par_map, self._num_classes), F_.from_internal(edge, 2)])
+            with ts.side():
+                edge = self.edge_head[stage_idx](p2)
+                par_map = self.par_head[stage_idx](p4)
+                par_list.append([F_.from_internal(par_map, self._num_classes), F_.from_internal(edge, 2)])
+            side_outputs.extend(par_list[-1])
 
-        emit(0)
+        emit(0, in1, in2, in3, in4)
         in3b, in4b = in3, in4     # the handles the parsing cell reads (own ones when the outputs were split per consumer)
         for i in range(1, self.refine_layers + 1):
             for j in range(3):
                 # refinement-cell outputs are read by preprocess layers and heads only (nn.ReLU first).  fea2 of either
                 # cell feeds BOTH cells of the next step: two handles (n_out), so the two gradients of these 4C-channel
-                # tensors are summed inside the member nodes' backward kernels, not by an autograd add
+                # tensors are summed inside the member nodes' backward kernels, not by an autograd add.
+                # PoseCell on the main stream, ParCell on the side stream; each reads the other's fea2: barrier first.
+                ts.join(in4)
+                ts.fork(in3b)
                 n_out = (1, 2) if (split and j < 2) else None
                 o1, t3 = self.pose_net[2 * (i - 1) + j](in1, in3, in4, out_raw=False, out_relu=True, n_out=n_out)
-                o2, t4 = self.par_net[2 * (i - 1) + j](in2, in3b, in4b, out_raw=False, out_relu=True, n_out=n_out)
+                with ts.side():
+                    o2, t4 = self.par_net[2 * (i - 1) + j](in2, in3b, in4b, out_raw=False, out_relu=True, n_out=n_out)
                 if n_out:
-                    in1, in2, (in3, in3b), (in4, in4b) = o1[0], o2[0], t3, t4
+                    in1, in2, (in3, in3b), (in4b, in4) = o1[0], o2[0], t3, t4
                 else:
                     in1, in2, in3, in4 = o1, o2, t3, t4
                     in3b, in4b = in3, in4
@@ -583,7 +598,8 @@ class Network(nn.Module):
                 for nm, t in (("relu(pose_net.%d.fea1)" % k, in1), ("relu(pose_net.%d.fea2)" % k, in3),
                               ("relu(par_net.%d.fea1)" % k, in2), ("relu(par_net.%d.fea2)" % k, in4)):
                     self._tr(nm, t, relu=True)
-            emit(i)
+            emit(i, in1, in2, in3, in4b)
+        ts.join(side_outputs)      # the parsing / edge logits were produced on the side stream
         return pose_list, par_list
 
     # ------------------------------------------------------------------ checkpoints

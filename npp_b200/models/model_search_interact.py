@@ -286,17 +286,26 @@ class Network(nn.Module):
 
     def forward(self, x):
         x = F_.to_internal(x)
+        # pose stream on the current CUDA stream, parsing stream on the side stream (functional.TaskStreams; see
+        # models/model_augment.py Network.forward): joined at every interaction point and at the heads
+        ts = F_.TaskStreams(x)
+        if ts.on and x.dtype == torch.bfloat16 and x.shape[1] == 8 and not x.requires_grad and F_._state.get("stem_im2col", True):
+            F_.im2col3x3_c3(x, 2, 1)
+        ts.fork(x)
         s0 = self.stem1(self.stem0(x))
         s1 = self.stem2(s0)
-        s2 = self.stem4(self.stem3(x))
-        s3 = self.stem5(s2)
+        with ts.side():
+            s2 = self.stem4(self.stem3(x))
+            s3 = self.stem5(s2)
         f1, f2 = [], []
         offset = 0
         for i, (cell1, cell2) in enumerate(zip(self.cells1, self.cells2)):
             tap = i in self._tap_layers
             s0, s1 = s1, cell1(s0, s1, out_raw=tap, out_relu=True)
-            s2, s3 = s3, cell2(s2, s3, out_raw=tap, out_relu=True)
+            with ts.side():
+                s2, s3 = s3, cell2(s2, s3, out_raw=tap, out_relu=True)
             if tap:
+                ts.join(s3)
                 f1.append(s1)
                 f2.append(s3)
                 n1 = self._interact(self._ops1, offset, f2, self.alphas1, self.betas1, s1)   # :646-651
@@ -304,12 +313,15 @@ class Network(nn.Module):
                 s1, s3 = n1, n3
                 f1[-1], f2[-1] = s1, s3
                 offset += len(f1)
+                ts.fork(s3)
 
         cont = 0
         prev1, prev2 = f1[3], f2[3]
         for d in range(3):                                                                  # :665-729
             o1 = self.upsamples1[d](prev1, f1[2 - d])
-            o2 = self.upsamples2[d](prev2, f2[2 - d])
+            with ts.side():
+                o2 = self.upsamples2[d](prev2, f2[2 - d])
+            ts.join(o2)
             f1.append(o1)
             f2.append(o2)
             n1 = self._interact(self.up_ops1, cont, f2, self.alphas3, self.betas3, o1)
@@ -317,26 +329,32 @@ class Network(nn.Module):
             f1[-1], f2[-1] = n1, n2
             prev1, prev2 = n1, n2
             cont += len(f1)
+            ts.fork(n2)
 
         def pyramid(f):                                                                     # :733-738
             return F_.cat_relu([f[0], f[6],
                                 F_.interpolate(f[5], scale_factor=2, mode="bilinear", align_corners=True),
                                 F_.interpolate(f[4], scale_factor=4, mode="bilinear", align_corners=True)])
 
-        x1, x2 = pyramid(f1), pyramid(f2)
+        x1 = pyramid(f1)
         in1 = self.pose_auxlayer(x1)
-        in2 = self.edge_layer(x2)
         in3 = self.pose_layer(x1)
-        in4 = self.par_layer(x2)
+        with ts.side():
+            x2 = pyramid(f2)
+            in2 = self.edge_layer(x2)
+            in4 = self.par_layer(x2)
         pose_list, par_list = [], []
+        side_outputs = []
 
         def emit(k):
-            edge = self.edge_head[k](in2)
             pose_aux = self.pose_auxnet[k](in1)
             pose_map = self.pose_head[k](in3)
-            par_map = self.par_head[k](in4)
             pose_list.append([F_.from_internal(pose_map, self._num_joints), F_.from_internal(pose_aux, self._num_joints)])
-            par_list.append([F_.from_internal(par_map, self._num_classes), F_.from_internal(edge, 2)])
+            with ts.side():
+                edge = self.edge_head[k](in2)
+                par_map = self.par_head[k](in4)
+                par_list.append([F_.from_internal(par_map, self._num_classes), F_.from_internal(edge, 2)])
+            side_outputs.extend(par_list[-1])
 
         emit(0)
         w_pose = torch.softmax(self.alphas_pose, dim=-1)
@@ -345,10 +363,15 @@ class Network(nn.Module):
         w_par2 = self.btw(3, self._steps, self.betas_par)
         for i in range(1, self.refine_layers + 1):
             for j in range(3):
+                # PoseCell on the main stream, ParCell on the side stream; each reads the other's fea2: barrier first
+                ts.join(in4)
+                ts.fork(in3, w_par, w_par2)
                 in1, tmp = self.pose_net[2 * (i - 1) + j](in1, in3, in4, w_pose, w_pose2)
-                in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4, w_par, w_par2)
+                with ts.side():
+                    in2, in4 = self.par_net[2 * (i - 1) + j](in2, in3, in4, w_par, w_par2)
                 in3 = tmp
             emit(i)
+        ts.join(side_outputs)
         return pose_list, par_list
 
     # ------------------------------------------------------------------ architecture parameters

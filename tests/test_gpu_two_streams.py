@@ -81,3 +81,35 @@ def test_two_streams_graph_step(lib_built):
         assert abs(l1[0] - l2[0]) < 2e-2 * abs(l1[0]), (l1[0], l2[0])
     finally:
         F_._state["two_streams"] = keep
+
+
+def test_two_streams_supernet_fp32(lib_built):
+    """Search supernet: forward outputs, architecture gradients (first-order in the MixedOp outputs, hence far less
+    amplified than weight gradients) with the parsing stream + ParCells on the side stream."""
+    from npp_b200 import engine
+    from npp_b200 import functional as F_
+    from npp_b200.models.model_search_interact import Network
+    F_.set_compute_dtype(torch.float32)
+    keep = F_._state.get("two_streams")
+    res = {}
+    try:
+        for two in (False, True):
+            F_._state["two_streams"] = two
+            torch.manual_seed(0)
+            net = Network(engine.make_cfg(layers=8, init_channels=16)).cuda().train()
+            gen = torch.Generator().manual_seed(3)
+            x = torch.randn(2, 3, 128, 128, generator=gen).cuda()
+            pl, par = net(x)
+            outs = [t for p in pl + par for t in p]
+            cots = [torch.randn(t.shape, generator=gen).cuda() for t in outs]
+            (sum((t * c).sum() for t, c in zip(outs, cots)) + net.loss_entropy()).backward()
+            torch.cuda.synchronize()
+            res[two] = ([o.detach() for o in outs], [p.grad.detach().clone() for p in net.arch_parameters()])
+        ferr = [rel(a, b) for a, b in zip(res[True][0], res[False][0])]
+        aerr = [rel(a, b) for a, b in zip(res[True][1], res[False][1])]
+        print("supernet two streams vs one (fp32): forward", ["%.1e" % e for e in ferr], "arch grads", ["%.1e" % e for e in aerr])
+        assert max(ferr) < 1e-4, ferr
+        assert sorted(aerr)[len(aerr) // 2] < 5e-2 and max(aerr) < 0.3, aerr
+    finally:
+        F_._state["two_streams"] = keep
+        F_.set_compute_dtype(torch.bfloat16)
