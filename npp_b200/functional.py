@@ -39,11 +39,12 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # NPP_CE_BWD_SEP=1 -> cross-entropy backward as per-pixel gradient + separable bilinear backward instead of
           # the shared-memory-atomic kernel (round-2 candidate; core/criterion.py, csrc/loss.cu ce_grad_kernel)
           "ce_bwd_sep": os.environ.get("NPP_CE_BWD_SEP", "0") != "0",
-          # NPP_TWO_STREAMS=1 -> the two task streams of the networks (cells1 / cells2, upsamples1 / upsamples2: the
+          # NPP_TWO_STREAMS=0 -> single-stream schedule.  Default: the two task streams of the networks (cells1 / cells2, upsamples1 / upsamples2: the
           # same shapes, independent between the interaction points) are issued on two CUDA streams, so that inside a
           # captured step they are parallel graph branches: the small 12^2 / 24^2 / 48^2 launches of one stream fill
-          # the SMs the other leaves idle (see TaskStreams below)
-          "two_streams": os.environ.get("NPP_TWO_STREAMS", "0") != "0"}
+          # the SMs the other leaves idle (see TaskStreams below).  Measured on B200 (profiles/r02_bench_*_two_streams_*):
+          # train 99.6 -> 90.4 ms, search 173.7 -> 159.1 ms, infer512 46.1 -> 41.3 ms per step
+          "two_streams": os.environ.get("NPP_TWO_STREAMS", "1") != "0"}
 
 
 def set_compute_dtype(dtype):

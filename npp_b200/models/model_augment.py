@@ -501,18 +501,23 @@ class Network(nn.Module):
             self._tr("relu(cells1.%d)" % i, s1, relu=True)
             self._tr("relu(cells2.%d)" % i, s3, relu=True)
             if i in self._tap_layers:
-                ts.join(s3)                  # the parsing stream's stage output is read by the interaction ops below
+                # interaction point (:422-446): each stream's message is computed from the OTHER stream's features,
+                # the pose stream's on the main stream, the parsing stream's on the side stream, after a barrier that
+                # hands the feature pyramids across (f1 still holds the pre-interaction state when z2 is formed)
                 f1.append(s1)
                 f2.append(s3)
+                ts.join(f2)
+                ts.fork(f1)
                 z1, c1 = self._exchange(self._ops1, c1, self._indices1[stage], f2)
-                z2, c2 = self._exchange(self._ops2, c2, self._indices2[stage], f1)
-                s1 = F_.node(s1, z1, want_raw=True, want_relu=True)[0]  # read raw (f1) and through nn.ReLU (cells)
-                s3 = F_.node(s3, z2, want_raw=True, want_relu=True)[0]
+                n1 = F_.node(s1, z1, want_raw=True, want_relu=True)[0]  # read raw (f1) and through nn.ReLU (cells)
+                with ts.side():
+                    z2, c2 = self._exchange(self._ops2, c2, self._indices2[stage], f1)
+                    n3 = F_.node(s3, z2, want_raw=True, want_relu=True)[0]
+                s1, s3 = n1, n3
                 self._tr("f1.%d" % stage, s1)
                 self._tr("f2.%d" % stage, s3)
                 stage += 1
                 f1[-1], f2[-1] = s1, s3
-                ts.fork(s3)                  # ... and its updated state goes back to the side stream
 
         # decoder: three upsample cells per stream with interaction after each (:453-533)
         c1 = c2 = 0
@@ -521,17 +526,19 @@ class Network(nn.Module):
             o1 = self.upsamples1[d](prev1, f1[2 - d])
             with ts.side():
                 o2 = self.upsamples2[d](prev2, f2[2 - d])
-            ts.join(o2)
             f1.append(o1)
             f2.append(o2)
+            ts.join(f2)
+            ts.fork(f1)
             z1, c1 = self._exchange(self.up_ops1, c1, self.up_indices1[d], f2)
-            z2, c2 = self._exchange(self.up_ops2, c2, self.up_indices2[d], f1)
-            o1 = F_.node(o1, z1, want_raw=True, want_relu=True)[0]
-            o2 = F_.node(o2, z2, want_raw=True, want_relu=True)[0]
+            n1 = F_.node(o1, z1, want_raw=True, want_relu=True)[0]
+            with ts.side():
+                z2, c2 = self._exchange(self.up_ops2, c2, self.up_indices2[d], f1)
+                n2 = F_.node(o2, z2, want_raw=True, want_relu=True)[0]
+            o1, o2 = n1, n2
             self._tr("f1.%d" % (4 + d), o1)
             self._tr("f2.%d" % (4 + d), o2)
             f1[-1], f2[-1] = o1, o2
-            ts.fork(o2)
             prev1, prev2 = o1, o2
 
         def pyramid(f):  # (:538-543); only read through the nn.ReLU of the four 1x1 layers: relu(cat) is written directly
