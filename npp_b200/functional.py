@@ -44,7 +44,12 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # captured step they are parallel graph branches: the small 12^2 / 24^2 / 48^2 launches of one stream fill
           # the SMs the other leaves idle (see TaskStreams below).  Measured on B200 (profiles/r02_bench_*_two_streams_*):
           # train 99.6 -> 90.4 ms, search 173.7 -> 159.1 ms, infer512 46.1 -> 41.3 ms per step
-          "two_streams": os.environ.get("NPP_TWO_STREAMS", "1") != "0"}
+          "two_streams": os.environ.get("NPP_TWO_STREAMS", "1") != "0",
+          # NPP_WGRAD_STREAM=0 -> wgrad and dgrad of a convolution on one stream.  Default: the weight gradient of a
+          # dense convolution runs on a companion stream while the data gradient runs on the layer's own stream (both
+          # only read dY); the own stream waits for the companion before the backward node returns, so no tensor
+          # outlives its stream order.  Pays off where neither kernel fills the GPU (12^2 ... 48^2 stages)
+          "wgrad_stream": os.environ.get("NPP_WGRAD_STREAM", "1") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -171,7 +176,7 @@ class TaskStreams:
         self.main = torch.cuda.current_stream()
         idx = ref.device.index
         if idx not in TaskStreams._side:
-            TaskStreams._side[idx] = torch.cuda.Stream(device=ref.device)
+            TaskStreams._side[idx] = _register_stream(torch.cuda.Stream(device=ref.device), "side")
         self.b = TaskStreams._side[idx]
 
     @staticmethod
@@ -191,6 +196,52 @@ class TaskStreams:
     def side(self):
         import contextlib
         return torch.cuda.stream(self.b) if self.on else contextlib.nullcontext()
+
+
+_WORKERS = {}     # (device index, "main" | "side") -> [worker streams]
+_N_WORKERS = max(0, min(8, int(os.environ.get("NPP_BRANCH_STREAMS", "3"))))
+
+
+def parallel_branches(fns):
+    """Evaluates independent branches [fn() -> handle] on worker streams forked from the current stream and joins them
+    before returning the results (the MixedOps that feed one node of a search cell, model_search_interact.py:352-356:
+    3-6 chains of ~50 small kernels each, nothing between them to share).  Inside a captured step they are parallel
+    graph branches; autograd keeps every branch's backward on its worker stream.  Inputs the branches read must have
+    been produced on the current stream (they are marked for the workers via `inputs`); with SyncBN the branches stay
+    on one stream (the exchange sequence of a stream has to be the same on every rank AND per communicator).
+    fns: list of (callable, inputs) pairs."""
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+    if (not _state.get("two_streams") or _N_WORKERS < 2 or len(fns) < 2 or dev is None or _sync_group() is not None
+            or not any(torch.is_tensor(t) and t.is_cuda for _, ins in fns for t in _flatten(ins))):
+        return [fn() for fn, _ in fns]
+    home = torch.cuda.current_stream()
+    side = TaskStreams.side_stream_of(dev)
+    key = (dev, "side" if (side is not None and home == side) else "main")   # one worker pool per task stream
+    if key not in _WORKERS:
+        _WORKERS[key] = [_register_stream(torch.cuda.Stream(), "worker:%s:%d" % (key[1], i)) for i in range(_N_WORKERS)]
+    workers = _WORKERS[key]
+    outs, used = [], set()
+    for j, (fn, ins) in enumerate(fns):
+        w = workers[j % len(workers)]
+        share(ins, w)
+        if j % len(workers) not in used:
+            w.wait_stream(home)
+            used.add(j % len(workers))
+        with torch.cuda.stream(w):
+            outs.append(fn())
+    for j, o in enumerate(outs):
+        share(o, home)
+    for k in used:
+        home.wait_stream(workers[k])
+    return outs
+
+
+def _flatten(h):
+    if isinstance(h, (list, tuple)):
+        for e in h:
+            yield from _flatten(e)
+    else:
+        yield h
 
 
 def share(h, stream):
@@ -349,7 +400,7 @@ def check_raw(x, what):
 def _wgrad_workspace(device):
     """One persistent fp32 workspace per (device, stream) for the split-K partial tiles of npp_conv2d_wgrad_ws (every
     wgrad call of a stream reuses it; stream order keeps the calls apart)."""
-    key = ("wgrad_ws", torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    key = ("wgrad_ws", torch.device(device).index, _stream_role())
     ws = _state.get(key)
     if ws is None:
         L.lib().npp_conv2d_wgrad_workspace_bytes.restype = ctypes.c_int64
@@ -357,6 +408,31 @@ def _wgrad_workspace(device):
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
         _state[key] = ws
     return ws
+
+
+_COMPANIONS = {}
+_ROLES = {}       # cuda_stream handle of every persistent helper stream (task side stream, workers, companions) -> role
+
+
+def _stream_role():
+    """'main' for the caller's stream (default, warm-up or graph-capture stream), else the name of the persistent
+    helper stream the code is running on.  Per-stream scratch (wgrad workspace, companions) is keyed by role, so the
+    warm-up and the capture pass of a step share it."""
+    return _ROLES.get(torch.cuda.current_stream().cuda_stream, "main")
+
+
+def _register_stream(s, role):
+    _ROLES[s.cuda_stream] = role
+    return s
+
+
+def _companion_stream():
+    """The wgrad companion of the current stream (one per stream that runs convolutions backward)."""
+    key = (torch.cuda.current_device(), _stream_role())
+    c = _COMPANIONS.get(key)
+    if c is None:
+        c = _COMPANIONS[key] = _register_stream(torch.cuda.Stream(), "companion:" + key[1])
+    return c
 
 
 def conv_out_size(size, k, stride, pad, dil, off=0):
@@ -423,6 +499,22 @@ class _ConvFn(Function):
         code = L.dtype_code(x)
         bf16 = code == L.NPP_BF16
         dx = dw = db = None
+        wslot, bslot = ctx.slots
+        # wgrad on the companion stream of this layer's stream, concurrently with dgrad (issued first so that it is
+        # already running when the dgrad kernel arrives); joined before this function returns
+        side = None
+        if (bf16 and ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and _state.get("wgrad_stream")
+                and _state.get("two_streams") and L._trace is None and L._prof is None):
+            side = _companion_stream()
+        if ctx.needs_input_grad[1] and side is not None:
+            dw = wslot if wslot is not None else torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
+            own = torch.cuda.current_stream()
+            side.wait_stream(own)
+            with torch.cuda.stream(side):
+                ws = _wgrad_workspace(x.device)
+                call("npp_conv2d_wgrad_ws", ref(view(x)), ref(view(dy)), fptr(dw), i32(cout), i32(cin), i32(kh), i32(kw),
+                     i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), fptr(ws), i64(ws.numel() * 4), stream(),
+                     work=ctx.work, keep=(x, dy, dw))
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if bf16:
@@ -431,8 +523,9 @@ class _ConvFn(Function):
             else:
                 call("npp_conv2d_direct_dgrad", ref(view(dy)), fptr(wmat), ref(view(dx)), i32(kh), i32(kw),
                      i32(stride), i32(pad), i32(dil), i32(hoff), i32(woff), i32(code), stream())
-        wslot, bslot = ctx.slots
-        if ctx.needs_input_grad[1]:
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        if ctx.needs_input_grad[1] and side is None:
             # wgrad accumulates (+=): into the parameter's own gradient slot when there is one, else into zeros
             dw = wslot if wslot is not None else torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=x.device)
             if bf16:

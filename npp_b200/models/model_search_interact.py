@@ -89,7 +89,8 @@ class MixedOp(nn.Module):
 
 def _weighted_node(ops, states, alphas, betas, base=None):
     """base + sum_j betas[j] * ops[j](states[j], alphas[j]) in one pass (:352-356, :648-654)."""
-    terms = [op(h, a) for op, h, a in zip(ops, states, alphas)]
+    # the MixedOps of one node are independent of each other: worker streams (functional.parallel_branches)
+    terms = F_.parallel_branches([((lambda op=op, h=h, a=a: op(h, a)), (h, a)) for op, h, a in zip(ops, states, alphas)])
     if base is None:
         return F_.mix(terms, betas)
     one = torch.ones(1, dtype=betas.dtype, device=betas.device)
