@@ -45,11 +45,11 @@ _state = {"dtype": torch.bfloat16, "sync_bn": None, "defer_bn_counters": None,
           # the SMs the other leaves idle (see TaskStreams below).  Measured on B200 (profiles/r02_bench_*_two_streams_*):
           # train 99.6 -> 90.4 ms, search 173.7 -> 159.1 ms, infer512 46.1 -> 41.3 ms per step
           "two_streams": os.environ.get("NPP_TWO_STREAMS", "1") != "0",
-          # NPP_WGRAD_STREAM=0 -> wgrad and dgrad of a convolution on one stream.  Default: the weight gradient of a
-          # dense convolution runs on a companion stream while the data gradient runs on the layer's own stream (both
-          # only read dY); the own stream waits for the companion before the backward node returns, so no tensor
-          # outlives its stream order.  Pays off where neither kernel fills the GPU (12^2 ... 48^2 stages)
-          "wgrad_stream": os.environ.get("NPP_WGRAD_STREAM", "1") != "0"}
+          # NPP_WGRAD_STREAM=1 -> the weight gradient of a dense convolution runs on a companion stream while the
+          # data gradient runs on the layer's own stream (both only read dY); the own stream waits for the companion
+          # before the backward node returns.  Measured with the two task streams already on: 89.18 vs 88.75 ms per
+          # train step (profiles/r02_wgrad_stream_ab.txt) -> off by default
+          "wgrad_stream": os.environ.get("NPP_WGRAD_STREAM", "0") == "1"}
 
 
 def set_compute_dtype(dtype):
@@ -199,7 +199,7 @@ class TaskStreams:
 
 
 _WORKERS = {}     # (device index, "main" | "side") -> [worker streams]
-_N_WORKERS = max(0, min(8, int(os.environ.get("NPP_BRANCH_STREAMS", "3"))))
+_N_WORKERS = max(0, min(8, int(os.environ.get("NPP_BRANCH_STREAMS", "6"))))
 
 
 def parallel_branches(fns):

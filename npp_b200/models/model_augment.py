@@ -16,6 +16,16 @@ from ..nn import BatchNorm2d, Conv2d, ReLU, Sequential, call_lazy
 from . import genotypes as gt
 from .operations import OPS, FactorizedReduce, ReLUConvBN
 
+# NPP_CELL_BRANCHES=1: the primitives of a cell whose inputs exist run concurrently on worker streams
+_CELL_BRANCHES = os.environ.get("NPP_CELL_BRANCHES", "0") == "1"
+
+
+def _preprocess(layers, inputs):
+    """The 1x1 preprocess layers of a cell (independent of each other)."""
+    if not _CELL_BRANCHES:
+        return [call_lazy(l, x) for l, x in zip(layers, inputs)]
+    return F_.parallel_branches([((lambda l=l, x=x: call_lazy(l, x)), x) for l, x in zip(layers, inputs)])
+
 BN_MOMENTUM = 0.1
 
 
@@ -181,11 +191,24 @@ class _StepCell(nn.Module):
 
         for k, p in enumerate(pre):
             emit(k, p, None)
-        for i in range(self._steps):
-            ja, jb = 2 * i, 2 * i + 1
-            a = call_lazy(self._ops[ja], handles[self._indices[ja]][ja])
-            b = call_lazy(self._ops[jb], handles[self._indices[jb]][jb])
-            emit(len(pre) + i, a, b)
+        if not _CELL_BRANCHES:
+            for i in range(self._steps):
+                ja, jb = 2 * i, 2 * i + 1
+                a = call_lazy(self._ops[ja], handles[self._indices[ja]][ja])
+                b = call_lazy(self._ops[jb], handles[self._indices[jb]][jb])
+                emit(len(pre) + i, a, b)
+        else:
+            # Wave schedule: every primitive whose input state exists runs now, each on its own worker stream
+            # (functional.parallel_branches); then the nodes whose two primitives are done are emitted in order.
+            done, nxt = {}, 0
+            while nxt < self._steps:
+                wave = [j for j in range(2 * self._steps) if j not in done and self._indices[j] < len(handles)]
+                res = F_.parallel_branches([((lambda j=j: call_lazy(self._ops[j], handles[self._indices[j]][j])),
+                                             handles[self._indices[j]][j]) for j in wave])
+                done.update(zip(wave, res))
+                while nxt < self._steps and 2 * nxt in done and 2 * nxt + 1 in done:
+                    emit(len(pre) + nxt, done[2 * nxt], done[2 * nxt + 1])
+                    nxt += 1
         outs = []
         for cid in range(len(concats)):
             hs = []
@@ -223,7 +246,7 @@ class Cell(_StepCell):
 
     def forward(self, s0, s1, out_raw=True, out_relu=False, n_out=None):
         """n_out = k: returns k handles on the cell output, one per consumer (see _run_fused)."""
-        return self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1)],
+        return self._run_fused(_preprocess((self.preprocess0, self.preprocess1), (s0, s1)),
                                [list(self._concat)], out_raw, out_relu, [n_out] if n_out else None)[0]
 
 
@@ -241,7 +264,7 @@ class Upsample(_StepCell):
                         wrap=lambda op, index: Sequential(op, Interpolate(scale_factor=2)) if index == 0 else op)
 
     def forward(self, s0, s1, out_raw=True, out_relu=False):
-        return self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1)],
+        return self._run_fused(_preprocess((self.preprocess0, self.preprocess1), (s0, s1)),
                                [list(self._concat)], out_raw, out_relu)[0]
 
 
@@ -278,8 +301,8 @@ class _FusionCell(_StepCell):
             states[0] = F_.interpolate(states[0], scale_factor=4)
             states[1] = F_.interpolate(states[1], scale_factor=2)
             return F_.cat(states[0:3]), F_.cat([states[i] for i in self._concat])
-        fea1, fea2 = self._run_fused([call_lazy(self.preprocess0, s0), call_lazy(self.preprocess1, s1),
-                                      call_lazy(self.preprocess2, s2)], [[0, 1, 2], list(self._concat)],
+        fea1, fea2 = self._run_fused(_preprocess((self.preprocess0, self.preprocess1, self.preprocess2),
+                                                  (s0, s1, s2)), [[0, 1, 2], list(self._concat)],
                                      out_raw, out_relu, list(n_out) if n_out else None)
         return fea1, fea2
 
