@@ -16,8 +16,10 @@ from ..nn import BatchNorm2d, Conv2d, ReLU, Sequential, call_lazy
 from . import genotypes as gt
 from .operations import OPS, FactorizedReduce, ReLUConvBN
 
-# NPP_CELL_BRANCHES=1: the primitives of a cell whose inputs exist run concurrently on worker streams
-_CELL_BRANCHES = os.environ.get("NPP_CELL_BRANCHES", "0") == "1"
+# NPP_CELL_BRANCHES=0: one primitive after the other.  Default: the primitives of a cell whose inputs exist run
+# concurrently on worker streams (train 88.34 -> 86.94 ms, infer512 40.99 -> 40.25 ms, profiles/r02_cell_branches_ab.txt);
+# without effect under SyncBN (functional.parallel_branches keeps the exchange order of a stream fixed)
+_CELL_BRANCHES = os.environ.get("NPP_CELL_BRANCHES", "1") != "0"
 
 
 def _preprocess(layers, inputs):
