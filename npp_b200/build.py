@@ -83,7 +83,7 @@ def build_test_binaries(verbose=False):
             outs.append(out)
             continue
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", src, "-o", out,
-               "-L", HERE, "-lnpp_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../../npp_b200"]
+               "-L", HERE, "-lnpp_b200", "-ldl", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../../npp_b200"]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -56,6 +56,8 @@ struct Geom {
   int n_blocks;                   // Cout blocks of BN
   int cout;
   int num_ptiles;                 // pixel tiles; total work items = num_ptiles * n_blocks
+  int k_last;                     // K16 steps of the last 64-channel block that hold real channels (1..4): the
+                                  // zero-filled rest of a partial block is not multiplied at all
 };
 
 template <int BN>
@@ -133,8 +135,10 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
   constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (the whole warp runs the
+    // loop converged and one elected lane issues: with `if (lane == 0)` around the loop the compiler wraps every
+    // TMA / MMA instruction, whose operands live in uniform registers, in a divergence "waterfall" loop)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
@@ -148,23 +152,26 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
           const int cw = w0 + taps.dw[t], ch = h0 + taps.dh[t], bt = taps.btap[t];
           for (int kc = 0; kc < g.kc_blocks; ++kc) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-            tma_load_4d(smem_a + stage * Cfg::A_BYTES, ma, full_bar + 8 * stage, kc * BK, cw, ch, n0);
-            tma_load_3d(smem_b + stage * Cfg::B_BYTES, &maps.b, full_bar + 8 * stage, kc * BK, bt,
-                        nb * BN);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+              tma_load_4d(smem_a + stage * Cfg::A_BYTES, ma, full_bar + 8 * stage, kc * BK, cw, ch, n0);
+              tma_load_3d(smem_b + stage * Cfg::B_BYTES, &maps.b, full_bar + 8 * stage, kc * BK, bt, nb * BN);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int kc = 0;  // 64-channel block index of the current k-block (the tap loop is the outer one)
       for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
@@ -174,15 +181,20 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
           tc_fence_after();
           const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES, 16, 1024);
+          const int ks = (kc + 1 == g.kc_blocks) ? g.k_last : BK / 16;
+          if (++kc == g.kc_blocks) kc = 0;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
+              if (k < ks) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar + 8 * stage);
+            if (kb == num_k - 1) umma_commit(tfull_bar + 8 * acc);
           }
-          umma_commit(empty_bar + 8 * stage);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * acc);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -426,15 +438,99 @@ __device__ __forceinline__ void epi_flush_stats(float (&acc_s)[SLABS][8], float 
                                                 float* __restrict__ stats, const int co0, const int cout, const int ew,
                                                 const int lane) {
   if (ew * 8 >= SLAB_COLS) return;  // warp-uniform
+  // Same-address float atomics from all CTAs arrive at the same moment and serialise in L2 (they were ~4 us of a
+  // 20 us launch): 16-byte vector reductions carry four channels per operation.
+  const bool vec = ((reinterpret_cast<uintptr_t>(stats) & 15u) == 0) && ((cout & 3) == 0);
 #pragma unroll
   for (int sl = 0; sl < SLABS; ++sl) {
+    float a[8], b[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float a = warp_sum(acc_s[sl][k]), b = warp_sum(acc_q[sl][k]);
-      const int co = co0 + sl * 64 + ew * 8 + k;
-      if (lane == 0 && co < cout) {
-        atomicAdd(stats + co, a);
-        atomicAdd(stats + cout + co, b);
+    for (int k = 0; k < 8; ++k) { a[k] = warp_sum(acc_s[sl][k]); b[k] = warp_sum(acc_q[sl][k]); }
+    const int co = co0 + sl * 64 + ew * 8;
+    if (lane == 0) {
+      if (vec && co + 8 <= cout) {
+        red_add_v4(stats + co, a[0], a[1], a[2], a[3]);
+        red_add_v4(stats + co + 4, a[4], a[5], a[6], a[7]);
+        red_add_v4(stats + cout + co, b[0], b[1], b[2], b[3]);
+        red_add_v4(stats + cout + co + 4, b[4], b[5], b[6], b[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (co + k < cout) {
+            atomicAdd(stats + co + k, a[k]);
+            atomicAdd(stats + cout + co + k, b[k]);
+          }
+      }
+    }
+  }
+}
+
+// conv3_kernel<32>: both 128-pixel halves of a tile in ONE round (a 32-column accumulator keeps only four of the
+// eight epilogue warps busy in epi_unit, and a tile would need two rounds of barriers / store waits).  Warp (q, hf)
+// drains rows q*32.. of half hf into staging buffer hf; two TMA stores; statistics: warp ew owns the 16-byte chunk
+// ew & 3 (8 channels) of buffer ew >> 2.
+__device__ __forceinline__ void epi_pair32(const uint32_t taddr, uint8_t* stg, const uint32_t stg_s,
+                                           const CUtensorMap* md, const int c_w, const int c_h, const int h_step,
+                                           const int c_n, const float* __restrict__ bias, const int cout,
+                                           const uint32_t release_bar, const bool want_stats, EpiMask mk,
+                                           float (&as)[8], float (&aq)[8], const int q, const int hf, const int ew,
+                                           const int lane, const int etid) {
+  const int row = q * 32 + lane;
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  // both staging buffers are rewritten: every earlier TMA store must have finished reading them
+  if (etid == 0) tma_store_wait_read<0>();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  tmem_ld_wait_regs(r);
+  uint8_t* my = stg + hf * (128 * 128);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // four 16-byte chunks (8 channels each)
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = __uint_as_float(r[j * 8 + e * 2]);
+      float v1 = __uint_as_float(r[j * 8 + e * 2 + 1]);
+      if (bias != nullptr) {
+        const int c0 = j * 8 + e * 2;
+        v0 += (c0 < cout) ? __ldg(bias + c0) : 0.f;
+        v1 += (c0 + 1 < cout) ? __ldg(bias + c0 + 1) : 0.f;
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      pk[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(my + row * 128 + ((j ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  tc_fence_before();  // every TMEM read of this thread has completed: the accumulator stage is free
+  mbar_arrive(release_bar);
+  fence_proxy_async_smem();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (etid == 0) {
+    tma_store_4d(md, stg_s, 0, c_w, c_h, c_n);
+    tma_store_4d(md, stg_s + 128 * 128, 0, c_w, c_h + h_step, c_n);
+    tma_store_commit();
+  }
+  if (want_stats) {
+    const int half = ew >> 2, chunk = ew & 3;
+    const uint8_t* src = stg + half * (128 * 128);
+    mk.p_off = half * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = lane * 4 + ((i + (lane >> 1)) & 3);
+      bool ok = true;
+      if (!mk.full) {
+        const int p = mk.p_off + rr;
+        const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
+        ok = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
+      }
+      const uint4 u = *reinterpret_cast<const uint4*>(src + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+      if (ok) {
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = __uint_as_float(uu[e] << 16), v1 = __uint_as_float(uu[e] & 0xffff0000u);
+          as[2 * e] += v0; aq[2 * e] = fmaf(v0, v0, aq[2 * e]);
+          as[2 * e + 1] += v1; aq[2 * e + 1] = fmaf(v1, v1, aq[2 * e + 1]);
+        }
       }
     }
   }
@@ -453,9 +549,9 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
   const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t smem_out = smem_base + STAGES * Cfg::STAGE_BYTES;
   const uint32_t bar_base = smem_out + Cfg::OUT_BYTES;
-  const uint32_t full_bar = bar_base;
-  const uint32_t empty_bar = bar_base + 8 * STAGES;
-  const uint32_t tfull_bar = bar_base + 16 * STAGES;
+  const uint32_t full_bar = bar_base;                 // 2 sets (one per MMA issuer warp, see conv3_kernel) x STAGES
+  const uint32_t empty_bar = bar_base + 16 * STAGES;
+  const uint32_t tfull_bar = bar_base + 24 * STAGES;
   const uint32_t tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -471,6 +567,7 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full_bar + 8 * i, 1);
+      mbar_init(full_bar + 8 * (STAGES + i), 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -498,10 +595,12 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
   constexpr int SLAB_COLS = BN >= 64 ? 64 : BN;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+      int it = 0;  // local tile counter: tile `it` belongs to MMA issuer it & 1
+      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step, ++it) {
+        const uint32_t full_t = full_bar + 8 * (it & 1) * STAGES;
         int pt = ptile;
         const int w0 = (pt % g.tiles_w) * g.tw;
         pt /= g.tiles_w;
@@ -512,39 +611,54 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
           const int cw = w0 + taps.dw[t], ch = h0 + taps.dh[t], bt = taps.btap[t];
           for (int kc = 0; kc < g.kc_blocks; ++kc) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-            tma_load_4d(smem_a + stage * Cfg::A_BYTES, ma, full_bar + 8 * stage, kc * BK, cw, ch, n0);
-            tma_load_3d(smem_b + stage * Cfg::B_BYTES, &maps.b, full_bar + 8 * stage, kc * BK, bt, nb * BN);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_t + 8 * stage, Cfg::STAGE_BYTES);
+              tma_load_4d(smem_a + stage * Cfg::A_BYTES, ma, full_t + 8 * stage, kc * BK, cw, ch, n0);
+              tma_load_3d(smem_b + stage * Cfg::B_BYTES, &maps.b, full_t + 8 * stage, kc * BK, bt, nb * BN);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // two MMA issuer warps alternating tiles (see conv3_kernel): warp 1 -> accumulator stage 0, warp 2 -> stage 1
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      const int which = warp - 1;
+      const int acc = which;
+      const uint32_t full_t = full_bar + 8 * which * STAGES;
+      const uint32_t tmem_d = tmem_base + acc * BN;
       int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
+      uint32_t bits = 0;  // parity of this issuer's next fill, one bit per ring stage
       uint32_t acc_phase = 0;
-      for (int ptile = pt_start; ptile < g.num_ptiles; ptile += pt_step) {
+      auto skip_tile = [&]() { stage = (stage + num_k) % STAGES; };
+      if (which) skip_tile();
+      for (int ptile = pt_start + which * pt_step; ptile < g.num_ptiles; ptile += 2 * pt_step) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        int kc = 0;  // 64-channel block index of the current k-block (the tap loop is the outer one)
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
+          mbar_wait(full_t + 8 * stage, (bits >> stage) & 1u);
+          bits ^= 1u << stage;
           tc_fence_after();
           const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES, 16, 1024);
+          const int ks = (kc + 1 == g.kc_blocks) ? g.k_last : BK / 16;
+          if (++kc == g.kc_blocks) kc = 0;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar + 8 * stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BK / 16; ++k)
+              if (k < ks) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar + 8 * stage);
+            if (kb == num_k - 1) umma_commit(tfull_bar + 8 * acc);
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0;
         }
-        umma_commit(tfull_bar + 8 * acc);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        skip_tile();  // the other issuer's tile
+        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -612,6 +726,21 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
 // Per (kernel column, 64-channel block): one box of (TH+2)*TW*128 B and three weight tiles feed 24 MMAs.
 // Activation boxes and weight tiles travel in separate mbarrier rings (different sizes, different reuse).
 // =================================================================================================
+#ifdef NPP_C3_PROF
+// Test-only build (tests/csrc/_bin/prof): where does conv3_kernel wait?  Cycle counters summed over all CTAs:
+// 0 producer total, 1 producer wait A-empty, 2 MMA total, 3 MMA wait A-full, 4 MMA wait B-full, 5 MMA wait TMEM-empty,
+// 6 epilogue total (thread 128), 7 epilogue wait TMEM-full, 8 tiles, 9 weight producer total, 10 weight producer wait,
+// 11 MMA issue blocks (8 tcgen05.mma each), 12 tcgen05.commit
+__device__ unsigned long long g_c3_prof[16];
+#define C3P_DECL(v) long long v = 0
+#define C3P_WAIT(v, stmt) do { const long long _t = clock64(); stmt; v += clock64() - _t; } while (0)
+#define C3P_ADD(i, v) atomicAdd(&g_c3_prof[i], (unsigned long long)(v))
+#else
+#define C3P_DECL(v)
+#define C3P_WAIT(v, stmt) stmt
+#define C3P_ADD(i, v)
+#endif
+
 struct C3Maps {
   CUtensorMap a;  // input: dims (C, W, H, N), box (64, tw, th + 2, 1)
   CUtensorMap b;  // weights: dims (K, 9, rows), box (64, 1, BN)
@@ -627,6 +756,8 @@ struct C3Geom {
   int sa, sb;            // ring depths (activation boxes, weight tiles)
   int flip;              // 0: fprop taps (x[h + r - 1][w + s - 1]); 1: dgrad taps (dy[h + 1 - r][w + 1 - s])
   int two_producers;     // weight tiles issued by a second producer thread (warp 3)
+  int k_last;            // K16 steps of the last 64-channel block that hold real channels (see Geom)
+  int wres;              // weights resident: all nine tap tiles of the (single) 64-channel block are loaded once per CTA
 };
 constexpr int kC3MaxSA = 4, kC3MaxSB = 8;
 constexpr int kC3OutBytes = 2 * 128 * 128;
@@ -645,10 +776,14 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
   const uint32_t smem_b = smem_a + g.sa * g.a_bytes;
   const uint32_t smem_out = smem_b + g.sb * B_BYTES;
   const uint32_t bar_base = smem_out + kC3OutBytes;
-  const uint32_t afull_bar = bar_base;                          // kC3MaxSA x 8 B
-  const uint32_t aempty_bar = afull_bar + 8 * kC3MaxSA;
-  const uint32_t bfull_bar = aempty_bar + 8 * kC3MaxSA;         // kC3MaxSB x 8 B
-  const uint32_t bempty_bar = bfull_bar + 8 * kC3MaxSB;
+  // "full" barriers exist twice, one set per MMA issuer warp (tiles alternate between two issuers, see below): every
+  // barrier then has ONE waiter that visits its phases in order — with a shared set, the issuer of tile i + 1 could
+  // poll a stage whose previous fill (tile i) has not landed yet and mistake the older completed phase of the same
+  // parity for its own
+  const uint32_t afull_bar = bar_base;                          // 2 x kC3MaxSA x 8 B
+  const uint32_t aempty_bar = afull_bar + 16 * kC3MaxSA;
+  const uint32_t bfull_bar = aempty_bar + 8 * kC3MaxSA;         // 2 x kC3MaxSB x 8 B
+  const uint32_t bempty_bar = bfull_bar + 16 * kC3MaxSB;
   const uint32_t tfull_bar = bempty_bar + 8 * kC3MaxSB;         // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
@@ -665,10 +800,12 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.sa; ++i) {
       mbar_init(afull_bar + 8 * i, 1);
+      mbar_init(afull_bar + 8 * (kC3MaxSA + i), 1);
       mbar_init(aempty_bar + 8 * i, 1);
     }
-    for (int i = 0; i < g.sb; ++i) {
+    for (int i = 0; i < (g.wres ? 1 : g.sb); ++i) {
       mbar_init(bfull_bar + 8 * i, 1);
+      mbar_init(bfull_bar + 8 * (kC3MaxSB + i), 1);
       mbar_init(bempty_bar + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -689,11 +826,21 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected lane)
+    {
       int as = 0, bs = 0;
       uint32_t ap = 0, bp = 0;
-      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+      C3P_DECL(p_wait); C3P_DECL(p_tiles);
+#ifdef NPP_C3_PROF
+      const long long p_t0 = clock64();
+#endif
+      int it = 0;  // local tile counter: tile `it` belongs to MMA issuer it & 1
+      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x, ++it) {
+#ifdef NPP_C3_PROF
+        ++p_tiles;
+#endif
+        const uint32_t afull_t = afull_bar + 8 * (it & 1) * kC3MaxSA;
+        const uint32_t bfull_t = bfull_bar + 8 * (it & 1) * kC3MaxSB;
         int pt = ptile;
         const int w0 = (pt % g.tiles_w) * g.tw;
         pt /= g.tiles_w;
@@ -702,83 +849,210 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
         for (int s = 0; s < 3; ++s) {
           const int cw = w0 + (g.flip ? 1 - s : s - 1);
           for (int kc = 0; kc < g.kc_blocks; ++kc) {
-            mbar_wait(aempty_bar + 8 * as, ap ^ 1);
-            mbar_arrive_expect_tx(afull_bar + 8 * as, g.a_bytes);
-            tma_load_4d(smem_a + as * g.a_bytes, &maps.a, afull_bar + 8 * as, kc * BK, cw, h0 - 1, n0);
+            C3P_WAIT(p_wait, mbar_wait(aempty_bar + 8 * as, ap ^ 1));
+            if (elect_one()) {
+              mbar_arrive_expect_tx(afull_t + 8 * as, g.a_bytes);
+              tma_load_4d(smem_a + as * g.a_bytes, &maps.a, afull_t + 8 * as, kc * BK, cw, h0 - 1, n0);
+            }
+            __syncwarp();
             if (++as == g.sa) { as = 0; ap ^= 1; }
-            if (g.two_producers) continue;  // the weight ring is fed by warp 3
+            if (g.two_producers || g.wres) continue;  // the weight tiles are fed by warp 3
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {
               mbar_wait(bempty_bar + 8 * bs, bp ^ 1);
-              mbar_arrive_expect_tx(bfull_bar + 8 * bs, B_BYTES);
-              tma_load_3d(smem_b + bs * B_BYTES, &maps.b, bfull_bar + 8 * bs, kc * BK, r * 3 + s, 0);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bfull_t + 8 * bs, B_BYTES);
+                tma_load_3d(smem_b + bs * B_BYTES, &maps.b, bfull_t + 8 * bs, kc * BK, r * 3 + s, 0);
+              }
+              __syncwarp();
               if (++bs == g.sb) { bs = 0; bp ^= 1; }
             }
           }
         }
       }
+#ifdef NPP_C3_PROF
+      if (lane == 0) { C3P_ADD(0, clock64() - p_t0); C3P_ADD(1, p_wait); C3P_ADD(8, p_tiles); }
+#endif
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ second TMA producer: weight tiles only, so
     // that the activation ring runs its full depth ahead instead of being throttled by the (shorter) weight ring
-    if (lane == 0 && g.two_producers) {
+    if (g.wres) {
+      // resident weights (Cin <= 64, small Cout): nine tap tiles, loaded once, one barrier
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bfull_bar, 9 * B_BYTES);
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) tma_load_3d(smem_b + t * B_BYTES, &maps.b, bfull_bar, 0, t, 0);
+      }
+      __syncwarp();
+    } else if (g.two_producers) {
       int bs = 0;
       uint32_t bp = 0;
-      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+      C3P_DECL(b_wait);
+#ifdef NPP_C3_PROF
+      const long long b_t0 = clock64();
+#endif
+      int it = 0;
+      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x, ++it) {
+        const uint32_t bfull_t = bfull_bar + 8 * (it & 1) * kC3MaxSB;
         for (int s = 0; s < 3; ++s) {
           for (int kc = 0; kc < g.kc_blocks; ++kc) {
 #pragma unroll 1
             for (int r = 0; r < 3; ++r) {
-              mbar_wait(bempty_bar + 8 * bs, bp ^ 1);
-              mbar_arrive_expect_tx(bfull_bar + 8 * bs, B_BYTES);
-              tma_load_3d(smem_b + bs * B_BYTES, &maps.b, bfull_bar + 8 * bs, kc * BK, r * 3 + s, 0);
+              C3P_WAIT(b_wait, mbar_wait(bempty_bar + 8 * bs, bp ^ 1));
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bfull_t + 8 * bs, B_BYTES);
+                tma_load_3d(smem_b + bs * B_BYTES, &maps.b, bfull_t + 8 * bs, kc * BK, r * 3 + s, 0);
+              }
+              __syncwarp();
               if (++bs == g.sb) { bs = 0; bp ^= 1; }
             }
           }
         }
       }
+#ifdef NPP_C3_PROF
+      if (lane == 0) { C3P_ADD(9, clock64() - b_t0); C3P_ADD(10, b_wait); }
+#endif
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers: TWO warps, alternating tiles
+    // (warp 1: tiles 0, 2, ... into accumulator stage 0; warp 2 — the TMEM allocator, idle otherwise — tiles 1, 3, ...
+    // into stage 1).  Each warp runs its loop converged and one elected lane issues.  Why two: the wait-cycle profile
+    // (tests/csrc/_bin/prof, profiles/r02_conv3_wait_profile.txt) showed the issuing thread itself as the bottleneck —
+    // ~330 cycles of scalar bookkeeping (mbarrier polls, descriptor arithmetic, elect, commits) per group of 8 MMAs
+    // that occupy the tensor pipe for 128-512 cycles; with two issuers one warp's bookkeeping hides behind the other
+    // warp's MMAs.  The rings are consumed strictly in tile order, so a warp simply skips the stages of the other
+    // warp's tile; every stage use still has exactly one committing thread.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int as = 0, bs = 0;
-      uint32_t ap = 0, bp = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      const int which = warp - 1;
+      const int acc = which;
       const int steps = 3 * g.kc_blocks;
-      for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
-        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 2 * BN;
-        for (int step = 0; step < steps; ++step) {
-          mbar_wait(afull_bar + 8 * as, ap);
-          tc_fence_after();
-          const uint32_t a_s = smem_a + as * g.a_bytes;
-#pragma unroll 1
-          for (int r = 0; r < 3; ++r) {
-            // vertical tap r reads the box `ro` image rows (ro * tw pixels = ro * tw * 128 bytes) further down
-            const int ro = g.flip ? 2 - r : r;
-            mbar_wait(bfull_bar + 8 * bs, bp);
-            tc_fence_after();
-            const uint64_t db = make_smem_desc_sw128(smem_b + bs * B_BYTES, 16, 1024);
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const uint64_t da = make_smem_desc_sw128(a_s + (ro * g.tw + m * 128) * 128, 16, 1024);
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_f16(tmem_d + m * BN, da + 2 * k, db + 2 * k, idesc, (step | r | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(bempty_bar + 8 * bs);
-            if (++bs == g.sb) { bs = 0; bp ^= 1; }
-          }
-          umma_commit(aempty_bar + 8 * as);
-          if (++as == g.sa) { as = 0; ap ^= 1; }
+      int as = 0, bs = 0;
+      uint32_t abits = 0, bbits = 0;  // parity of this issuer's next fill, one bit per ring stage
+      uint32_t acc_phase = 0;
+      const uint32_t afull_t = afull_bar + 8 * which * kC3MaxSA;
+      const uint32_t bfull_t = bfull_bar + 8 * which * kC3MaxSB;
+      auto skip_tile = [&]() {
+        as += steps;
+        while (as >= g.sa) as -= g.sa;
+        if (!g.wres) {
+          bs += 3 * steps;
+          while (bs >= g.sb) bs -= g.sb;
         }
-        umma_commit(tfull_bar + 8 * acc);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+      };
+      if (which) skip_tile();
+      C3P_DECL(m_wa); C3P_DECL(m_wb); C3P_DECL(m_wt); C3P_DECL(m_issue); C3P_DECL(m_commit);
+#ifdef NPP_C3_PROF
+      const long long m_t0 = clock64();
+#endif
+      if (g.wres) {
+        mbar_wait(bfull_bar, 0);
+        tc_fence_after();
       }
+      const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+      const uint32_t rstep = static_cast<uint32_t>(g.tw * 128) >> 4;  // one image row of the box, in descriptor units
+      for (int ptile = blockIdx.x + which * gridDim.x; ptile < g.num_ptiles; ptile += 2 * gridDim.x) {
+        C3P_WAIT(m_wt, mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1));
+        tc_fence_after();
+        for (int step = 0; step < steps; ++step) {
+          C3P_WAIT(m_wa, mbar_wait(afull_t + 8 * as, (abits >> as) & 1u));
+          abits ^= 1u << as;
+          tc_fence_after();
+          const uint64_t da00 = make_smem_desc_sw128(smem_a + as * g.a_bytes, 16, 1024);
+          if (g.wres) {
+            // one activation box (kernel column `step`) against the three resident weight tiles of that column:
+            // up to 24 MMAs back to back, one commit
+            const uint64_t db00 = make_smem_desc_sw128(smem_b + step * B_BYTES, 16, 1024);
+            if (elect_one()) {
+#ifdef NPP_C3_PROF
+              const long long i_t0 = clock64();
+#endif
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const uint64_t db = db00 + r * (3 * B_BYTES / 16);          // tap index r * 3 + step
+                // vertical tap r reads the box `ro` image rows (ro * tw pixels = ro * tw * 128 bytes) further down
+                const uint64_t dar = da00 + (g.flip ? 2 - r : r) * rstep;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  const uint64_t da = dar + m * (128 * 128 / 16);  // second pixel half: 128 rows of 128 bytes further
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    if (k < g.k_last) umma_f16(tmem_d + m * BN, da + 2 * k, db + 2 * k, idesc, (step | r | k) != 0 ? 1u : 0u);
+                }
+              }
+#ifdef NPP_C3_PROF
+              const long long i_t1 = clock64();
+#endif
+              umma_commit(aempty_bar + 8 * as);
+              if (step == steps - 1) umma_commit(tfull_bar + 8 * acc);
+#ifdef NPP_C3_PROF
+              m_issue += i_t1 - i_t0;
+              m_commit += clock64() - i_t1;
+#endif
+            }
+            __syncwarp();
+          } else {
+            // the three weight tiles (vertical taps) of this (kernel column, 64-channel block)
+            int bi[3];
+            {
+              int t = bs;
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                bi[r] = t;
+                C3P_WAIT(m_wb, mbar_wait(bfull_t + 8 * t, (bbits >> t) & 1u));
+                bbits ^= 1u << t;
+                if (++t == g.sb) t = 0;
+              }
+              bs = t;
+            }
+            tc_fence_after();
+            const int ks = (step % g.kc_blocks == g.kc_blocks - 1) ? g.k_last : BK / 16;
+            if (elect_one()) {
+#ifdef NPP_C3_PROF
+              const long long i_t0 = clock64();
+              long long i_c = 0;
+#endif
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const uint64_t db = make_smem_desc_sw128(smem_b + bi[r] * B_BYTES, 16, 1024);
+                const uint64_t dar = da00 + (g.flip ? 2 - r : r) * rstep;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  const uint64_t da = dar + m * (128 * 128 / 16);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    if (k < ks) umma_f16(tmem_d + m * BN, da + 2 * k, db + 2 * k, idesc, (step | r | k) != 0 ? 1u : 0u);
+                }
+#ifdef NPP_C3_PROF
+                const long long c_t0 = clock64();
+#endif
+                umma_commit(bempty_bar + 8 * bi[r]);   // the weight producer may refill this tile
+#ifdef NPP_C3_PROF
+                i_c += clock64() - c_t0;
+#endif
+              }
+#ifdef NPP_C3_PROF
+              const long long i_t1 = clock64();
+#endif
+              umma_commit(aempty_bar + 8 * as);
+              if (step == steps - 1) umma_commit(tfull_bar + 8 * acc);
+#ifdef NPP_C3_PROF
+              m_issue += i_t1 - i_t0 - i_c;
+              m_commit += clock64() - i_t1 + i_c;
+#endif
+            }
+            __syncwarp();
+          }
+          if (++as == g.sa) as = 0;
+        }
+        skip_tile();  // the other issuer's tile
+        acc_phase ^= 1;
+      }
+#ifdef NPP_C3_PROF
+      if (lane == 0) { C3P_ADD(2, clock64() - m_t0); C3P_ADD(3, m_wa); C3P_ADD(4, m_wb); C3P_ADD(5, m_wt); }
+      if (m_issue) { C3P_ADD(11, m_issue); C3P_ADD(12, m_commit); }
+#endif
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (eight warps)
@@ -794,6 +1068,10 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
     for (int sl = 0; sl < SLABS; ++sl)
 #pragma unroll
       for (int k = 0; k < 8; ++k) { acc_s[sl][k] = 0.f; acc_q[sl][k] = 0.f; }
+    C3P_DECL(e_wait);
+#ifdef NPP_C3_PROF
+    const long long e_t0 = clock64();
+#endif
     for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
       int pt = ptile;
       EpiMask mk;
@@ -803,8 +1081,16 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
       mk.h0 = (pt % g.tiles_h) * g.th;
       const int n0 = pt / g.tiles_h;
       mk.full = (mk.w0 + g.tw <= g.W) && (mk.h0 + g.th <= g.H);
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      C3P_WAIT(e_wait, mbar_wait(tfull_bar + 8 * acc, acc_phase));
       tc_fence_after();
+      if constexpr (BN == 32) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * 2 + hf) * BN);
+        epi_pair32(taddr, smem_gen + (smem_out - smem_base), smem_out, &maps.d, mk.w0, mk.h0, g.th >> 1, n0, bias,
+                   g.cout, tempty_bar + 8 * acc, stats != nullptr, mk, acc_s[0], acc_q[0], q, hf, ew, lane, etid);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
         mk.p_off = m * 128;
@@ -824,7 +1110,14 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (stats != nullptr) epi_flush_stats<SLABS, SLAB_COLS>(acc_s, acc_q, stats, 0, g.cout, ew, lane);
+#ifdef NPP_C3_PROF
+    if (etid == 0) { C3P_ADD(6, clock64() - e_t0); C3P_ADD(7, e_wait); }
+#endif
+    if constexpr (BN == 32) {
+      if (stats != nullptr) epi_flush_stats<SLABS, 64>(acc_s, acc_q, stats, 0, g.cout, ew & 3, lane);  // all 8 warps
+    } else {
+      if (stats != nullptr) epi_flush_stats<SLABS, SLAB_COLS>(acc_s, acc_q, stats, 0, g.cout, ew, lane);
+    }
     if (etid == 0) tma_store_wait_all<0>();
   }
 
@@ -921,7 +1214,7 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
 
   if (num_k > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      {  // converged warp, one elected lane issues (see conv_gemm_kernel)
         const CUtensorMap* mx = &maps.x[taps.map[tap]];
         const int dwx = taps.dw[tap], dhx = taps.dh[tap];
         // narrow layers (<= 64 output channels in this block): the second 64-channel dY slab would be all padding —
@@ -937,20 +1230,22 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
           const int h0 = (pt % g.tiles_h) * g.th;
           const int n0 = (pt / g.tiles_h) * g.tn;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * SLAB + Cfg::B_BYTES);
           const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
           const uint32_t sb = smem_b + stage * Cfg::B_BYTES;
-          for (int s = 0; s < a_slabs; ++s)
-            tma_load_4d(sa + s * SLAB, &maps.dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * SLAB + Cfg::B_BYTES);
+            for (int s = 0; s < a_slabs; ++s)
+              tma_load_4d(sa + s * SLAB, &maps.dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
 #pragma unroll
-          for (int s = 0; s < BN / 64; ++s)
-            tma_load_4d(sb + s * SLAB, mx, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + dwx,
-                        h0 + dhx, n0);
+            for (int s = 0; s < BN / 64; ++s)
+              tma_load_4d(sb + s * SLAB, mx, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + dwx, h0 + dhx, n0);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
@@ -960,15 +1255,18 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
           // MN-major SW128: 64-element MN slabs LBO apart, 8-row K groups SBO = 1024 B apart
           const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, SLAB, 1024);
           const uint64_t db = make_smem_desc_sw128(smem_b + stage * Cfg::B_BYTES, SLAB, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < Cfg::KP / 16; ++k) {
-            // 16 pixels (K) further = 16 rows x 128 B = 2048 B -> +128 in (addr>>4)
-            umma_f16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < Cfg::KP / 16; ++k) {
+              // 16 pixels (K) further = 16 rows x 128 B = 2048 B -> +128 in (addr>>4)
+              umma_f16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar + 8 * stage);
+            if (kb == num_k - 1) umma_commit(tfull_bar);
           }
-          umma_commit(empty_bar + 8 * stage);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar);
       }
     } else if (warp >= kEpiWarp0) {
       const int q = warp & 3;
@@ -1087,7 +1385,7 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   if (num_k > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      {  // converged warp, one elected lane issues (see conv_gemm_kernel)
         const int a_slabs = (g.cout - co_blk * 128 > 64) ? 2 : 1;  // see conv_wgrad_kernel
         int stage = 0;
         uint32_t phase = 0;
@@ -1098,20 +1396,22 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const int h0 = (pt % g.tiles_h) * g.th;
           const int n0 = pt / g.tiles_h;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * ASLAB + b_bytes);
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + A_BYTES;
-          for (int s = 0; s < a_slabs; ++s)
-            tma_load_4d(sa + s * ASLAB, &map_dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * ASLAB + b_bytes);
+            for (int s = 0; s < a_slabs; ++s)
+              tma_load_4d(sa + s * ASLAB, &map_dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
 #pragma unroll
-          for (int s = 0; s < BN / 64; ++s)
-            tma_load_4d(sb + s * g.bslab, &map_x, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + q - 1, h0 - 1,
-                        n0);
+            for (int s = 0; s < BN / 64; ++s)
+              tma_load_4d(sb + s * g.bslab, &map_x, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + q - 1, h0 - 1, n0);
+          }
+          __syncwarp();
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         int stage = 0;
         uint32_t phase = 0;
@@ -1122,18 +1422,23 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const uint32_t sb = sa + A_BYTES;
           // MN-major SW128: 64-channel slabs LBO apart, 8-pixel K groups SBO = 1024 B apart
           const uint64_t da = make_smem_desc_sw128(sa, ASLAB, 1024);
+          const uint64_t db0 = make_smem_desc_sw128(sb, g.bslab, 1024);
+          const uint32_t rstep = static_cast<uint32_t>(g.tw * 128) >> 4;
+          if (elect_one()) {
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            // vertical tap r reads the X tile r image rows (r * tw pixels = r * tw * 128 bytes) further down
-            const uint64_t db = make_smem_desc_sw128(sb + r * g.tw * 128, g.bslab, 1024);
+            for (int r = 0; r < 3; ++r) {
+              // vertical tap r reads the X tile r image rows (r * tw pixels = r * tw * 128 bytes) further down
+              const uint64_t db = db0 + r * rstep;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 64 pixels = 4 x K16; 16 pixels = 2048 B -> +128 in (addr >> 4)
-              umma_f16(tmem_base + r * BN, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)  // 64 pixels = 4 x K16; 16 pixels = 2048 B -> +128 in (addr >> 4)
+                umma_f16(tmem_base + r * BN, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar + 8 * stage);
+            if (kb == num_k - 1) umma_commit(tfull_bar);
           }
-          umma_commit(empty_bar + 8 * stage);
+          __syncwarp();
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar);
       }
     } else if (warp >= kEpiWarp0) {
       const int qw = warp & 3;
@@ -1435,6 +1740,7 @@ static int run_gemm(const npp_view4* a_views, int n_a, const npp_view4* d, const
   if (rc) return rc;
   g.num_taps = num_taps;
   g.kc_blocks = (int)cdiv64(wK, BK);
+  g.k_last = (int)cdiv64(wK - (int64_t)(g.kc_blocks - 1) * BK, 16);
   g.tw = t.tw; g.th = t.th; g.tn = t.tn;
   g.tiles_w = (int)cdiv64(ps.W, t.tw);
   g.tiles_h = (int)cdiv64(ps.H, t.th);
@@ -1499,6 +1805,7 @@ static int conv3_try(const npp_view4* a, const npp_view4* d, const void* wmat, i
   g.num_ptiles = (int)ptiles;
   g.W = d->w; g.H = d->h;
   g.kc_blocks = (int)cdiv64(wK, BK);
+  g.k_last = (int)cdiv64(wK - (int64_t)(g.kc_blocks - 1) * BK, 16);
   g.cout = wRows;
   g.flip = flip;
   g.two_producers = two_prod;
@@ -1506,11 +1813,21 @@ static int conv3_try(const npp_view4* a, const npp_view4* d, const void* wmat, i
   const int bn = pick_bn(wRows);
   const int b_bytes = bn * 128;
   const int avail = 227 * 1024 - kC3OutBytes - 1024 /*barriers*/ - 1024 /*alignment slack*/;
+  static const int wres_on = env_flag("NPP_CONV3_WRES", 1);
   g.sa = 3;
-  if (g.sa * g.a_bytes + 4 * b_bytes > avail) g.sa = 2;
-  g.sb = (avail - g.sa * g.a_bytes) / b_bytes;
-  if (g.sb > kC3MaxSB) g.sb = kC3MaxSB;
-  if (g.sb < 3) return NPP_E_UNSUPPORTED;
+  if (wres_on && g.kc_blocks == 1 && 9 * b_bytes + 3 * g.a_bytes <= avail) {
+    // Cin <= 64 and the nine tap tiles fit beside the activation ring: weights stay resident for the whole kernel
+    // (no weight ring, no per-tap barrier round trip, 4 instead of 13 tcgen05.commit per tile)
+    g.wres = 1;
+    g.sb = 9;
+    g.sa = (avail - 9 * b_bytes) / g.a_bytes;
+    if (g.sa > kC3MaxSA) g.sa = kC3MaxSA;
+  } else {
+    if (g.sa * g.a_bytes + 4 * b_bytes > avail) g.sa = 2;
+    g.sb = (avail - g.sa * g.a_bytes) / b_bytes;
+    if (g.sb > kC3MaxSB) g.sb = kC3MaxSB;
+    if (g.sb < 3) return NPP_E_UNSUPPORTED;
+  }
   const int smem = g.sa * g.a_bytes + g.sb * b_bytes + kC3OutBytes + 1024 + 1024;
   C3Maps maps;
   memset(&maps, 0, sizeof maps);
@@ -2017,3 +2334,14 @@ int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin
 
 }  // namespace tc
 }  // namespace npp
+
+#ifdef NPP_C3_PROF
+extern "C" int npp_debug_c3_prof(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, npp::tc::g_c3_prof, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(npp::tc::g_c3_prof, z, sizeof z);
+  }
+  return 0;
+}
+#endif

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
+#include <dlfcn.h>
 #include "../../include/npp_b200.h"
 
 
@@ -272,6 +273,24 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 10; ++i) npp_conv2d_wgrad(&vx, &vdy, dw_tc, c.cout, c.cin, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, 0);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("  wgrad(atomic) %.1f us\n", ms * 100);
+    // test-only profile build of the library (-DNPP_C3_PROF): where conv3_kernel's three roles wait
+    typedef int (*prof_fn)(unsigned long long*, int);
+    prof_fn prof = (prof_fn)dlsym(RTLD_DEFAULT, "npp_debug_c3_prof");
+    if (prof != nullptr) {
+      unsigned long long v[16];
+      prof(nullptr, 1);
+      for (int i = 0; i < 10; ++i) npp_conv2d_fwd(&vx, w, bptr, &vy_tc, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, stats, 0);
+      CK(cudaDeviceSynchronize());
+      prof(v, 1);
+      if (v[8]) {
+        const double t = (double)v[8];  // tiles over 10 launches
+        printf("  c3prof (cycles per 256-pixel tile, fprop+stats): producer total %.0f wait-empty %.0f | weights total %.0f wait %.0f | "
+               "mma total %.0f wait A %.0f wait B %.0f wait tmem %.0f issue %.0f commit %.0f | epilogue total %.0f wait acc %.0f | "
+               "tiles/launch %.0f\n",
+               v[0] / t, v[1] / t, v[9] / t, v[10] / t, v[2] / t, v[3] / t, v[4] / t, v[5] / t, v[11] / t, v[12] / t,
+               v[6] / t, v[7] / t, t / 10);
+      }
+    }
   }
   printf("[case %d] %s\n", idx, fails ? "FAILED" : "OK");
   return fails ? 1 : 0;
