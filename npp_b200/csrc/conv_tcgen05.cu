@@ -349,6 +349,25 @@ conv_gemm_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable
 // overlaps the wait, the accumulator is handed back to the MMA warp as soon as the last load has landed (before the
 // statistics of the last slab), and the statistics pass is spread over 256 threads (4 rows each instead of 8).
 // =================================================================================================
+#ifdef NPP_C3_PROF
+// Test-only build (tests/csrc/_bin/prof): where does conv3_kernel wait?  Cycle counters summed over all CTAs:
+// 0 producer total, 1 producer wait A-empty, 2 MMA total, 3 MMA wait A-full, 4 MMA wait B-full, 5 MMA wait TMEM-empty,
+// 6 epilogue total (thread 128), 7 epilogue wait TMEM-full, 8 tiles, 9 weight producer total, 10 weight producer wait,
+// 11 MMA issue blocks (8 tcgen05.mma each), 12 tcgen05.commit;
+// epilogue thread 128, per 128-row unit (epi_unit): 16 units, 17 wait for the staging slab (TMA store read), 18 first
+// barrier, 19 tcgen05.ld wait + convert + st.shared, 20 proxy fence + second barrier, 21 store issue, 22 statistics
+__device__ unsigned long long g_c3_prof[32];
+#define C3P_DECL(v) long long v = 0
+#define C3P_WAIT(v, stmt) do { const long long _t = clock64(); stmt; v += clock64() - _t; } while (0)
+#define C3P_ADD(i, v) atomicAdd(&g_c3_prof[i], (unsigned long long)(v))
+#define C3P_STAMP(t) const long long t = clock64()
+#else
+#define C3P_DECL(v)
+#define C3P_WAIT(v, stmt) stmt
+#define C3P_ADD(i, v)
+#define C3P_STAMP(t)
+#endif
+
 constexpr int kThreads2 = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 
 struct EpiMask {   // which rows of a 128-row unit are real pixels (statistics must skip padding rows)
@@ -371,10 +390,13 @@ __device__ __forceinline__ void epi_unit(const uint32_t taddr, uint8_t* stg, con
   const bool has_cols = hf * 32 < SLAB_COLS;  // warp-uniform
   const int row = q * 32 + lane;
   uint32_t r[32];
+  C3P_STAMP(e_t0);
   if (has_cols) tmem_ld_32x32(taddr, r);
   // the TMA store that last read this staging slab (two units ago) must have finished reading it
   if (etid == 0) tma_store_wait_read<1>();
+  C3P_STAMP(e_t1);
   asm volatile("bar.sync 1, 256;" ::: "memory");
+  C3P_STAMP(e_t2);
   if (has_cols) {
     tmem_ld_wait_regs(r);
 #pragma unroll
@@ -400,12 +422,15 @@ __device__ __forceinline__ void epi_unit(const uint32_t taddr, uint8_t* stg, con
     tc_fence_before();
     mbar_arrive(release_bar);
   }
+  C3P_STAMP(e_t3);
   fence_proxy_async_smem();
   asm volatile("bar.sync 1, 256;" ::: "memory");
+  C3P_STAMP(e_t4);
   if (etid == 0) {
     tma_store_4d(md, stg_s, co_base, c_w, c_h, c_n);
     tma_store_commit();
   }
+  C3P_STAMP(e_t5);
   if (want_stats && ew * 8 < SLAB_COLS) {
     // Epilogue warp ew owns the 16-byte chunk ew (8 channels) of every row; lane l adds up rows 4l..4l+3, visited
     // in a lane-skewed order so that the 8 lanes of an LDS.128 phase hit 8 different swizzle slots (bank groups).
@@ -420,16 +445,26 @@ __device__ __forceinline__ void epi_unit(const uint32_t taddr, uint8_t* stg, con
       }
       const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ew ^ (rr & 7)) << 4));
       if (ok) {
+        // packed fp32x2 adds / fmas (sm_100): the statistics are instruction-issue bound (~43 % of an epilogue unit)
         const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float v0 = __uint_as_float(uu[e] << 16), v1 = __uint_as_float(uu[e] & 0xffff0000u);
-          as[2 * e] += v0; aq[2 * e] = fmaf(v0, v0, aq[2 * e]);
-          as[2 * e + 1] += v1; aq[2 * e + 1] = fmaf(v1, v1, aq[2 * e + 1]);
+          const float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
+          const float2 s2 = __fadd2_rn(make_float2(as[2 * e], as[2 * e + 1]), v);
+          const float2 q2 = __ffma2_rn(v, v, make_float2(aq[2 * e], aq[2 * e + 1]));
+          as[2 * e] = s2.x; as[2 * e + 1] = s2.y;
+          aq[2 * e] = q2.x; aq[2 * e + 1] = q2.y;
         }
       }
     }
   }
+#ifdef NPP_C3_PROF
+  if (etid == 0) {
+    const long long e_t6 = clock64();
+    C3P_ADD(16, 1); C3P_ADD(17, e_t1 - e_t0); C3P_ADD(18, e_t2 - e_t1); C3P_ADD(19, e_t3 - e_t2);
+    C3P_ADD(20, e_t4 - e_t3); C3P_ADD(21, e_t5 - e_t4); C3P_ADD(22, e_t6 - e_t5);
+  }
+#endif
 }
 
 // fold the 32 row groups of a warp, then one atomic per (CTA, channel, moment)
@@ -524,12 +559,15 @@ __device__ __forceinline__ void epi_pair32(const uint32_t taddr, uint8_t* stg, c
       }
       const uint4 u = *reinterpret_cast<const uint4*>(src + rr * 128 + ((chunk ^ (rr & 7)) << 4));
       if (ok) {
+        // packed fp32x2 adds / fmas (sm_100): the statistics are instruction-issue bound (~43 % of an epilogue unit)
         const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float v0 = __uint_as_float(uu[e] << 16), v1 = __uint_as_float(uu[e] & 0xffff0000u);
-          as[2 * e] += v0; aq[2 * e] = fmaf(v0, v0, aq[2 * e]);
-          as[2 * e + 1] += v1; aq[2 * e + 1] = fmaf(v1, v1, aq[2 * e + 1]);
+          const float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
+          const float2 s2 = __fadd2_rn(make_float2(as[2 * e], as[2 * e + 1]), v);
+          const float2 q2 = __ffma2_rn(v, v, make_float2(aq[2 * e], aq[2 * e + 1]));
+          as[2 * e] = s2.x; as[2 * e + 1] = s2.y;
+          aq[2 * e] = q2.x; aq[2 * e + 1] = q2.y;
         }
       }
     }
@@ -726,21 +764,6 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
 // Per (kernel column, 64-channel block): one box of (TH+2)*TW*128 B and three weight tiles feed 24 MMAs.
 // Activation boxes and weight tiles travel in separate mbarrier rings (different sizes, different reuse).
 // =================================================================================================
-#ifdef NPP_C3_PROF
-// Test-only build (tests/csrc/_bin/prof): where does conv3_kernel wait?  Cycle counters summed over all CTAs:
-// 0 producer total, 1 producer wait A-empty, 2 MMA total, 3 MMA wait A-full, 4 MMA wait B-full, 5 MMA wait TMEM-empty,
-// 6 epilogue total (thread 128), 7 epilogue wait TMEM-full, 8 tiles, 9 weight producer total, 10 weight producer wait,
-// 11 MMA issue blocks (8 tcgen05.mma each), 12 tcgen05.commit
-__device__ unsigned long long g_c3_prof[16];
-#define C3P_DECL(v) long long v = 0
-#define C3P_WAIT(v, stmt) do { const long long _t = clock64(); stmt; v += clock64() - _t; } while (0)
-#define C3P_ADD(i, v) atomicAdd(&g_c3_prof[i], (unsigned long long)(v))
-#else
-#define C3P_DECL(v)
-#define C3P_WAIT(v, stmt) stmt
-#define C3P_ADD(i, v)
-#endif
-
 struct C3Maps {
   CUtensorMap a;  // input: dims (C, W, H, N), box (64, tw, th + 2, 1)
   CUtensorMap b;  // weights: dims (K, 9, rows), box (64, 1, BN)
@@ -1154,7 +1177,7 @@ struct WgradCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulators: one per MMA issuer warp (k-blocks alternate)
 };
 
 template <int BN>
@@ -1169,9 +1192,9 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t full_bar = bar_base;
-  const uint32_t empty_bar = bar_base + 8 * STAGES;
-  const uint32_t tfull_bar = bar_base + 16 * STAGES;
+  const uint32_t full_bar = bar_base;                 // 2 sets (one per MMA issuer warp) x STAGES
+  const uint32_t empty_bar = bar_base + 16 * STAGES;
+  const uint32_t tfull_bar = bar_base + 24 * STAGES;
   const uint32_t tmem_slot = tfull_bar + 8;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
@@ -1196,9 +1219,10 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full_bar + 8 * i, 1);
+      mbar_init(full_bar + 8 * (STAGES + i), 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
-    mbar_init(tfull_bar, 1);
+    mbar_init(tfull_bar, num_k >= 2 ? 2 : 1);  // one arrival per issuer warp that has work
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -1232,25 +1256,33 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_a + stage * Cfg::A_BYTES;
           const uint32_t sb = smem_b + stage * Cfg::B_BYTES;
+          const uint32_t fb = full_bar + 8 * (((p - p_begin) & 1) * STAGES + stage);  // k-block -> issuer (p - p_begin) & 1
           if (elect_one()) {
-            mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * SLAB + Cfg::B_BYTES);
+            mbar_arrive_expect_tx(fb, a_slabs * SLAB + Cfg::B_BYTES);
             for (int s = 0; s < a_slabs; ++s)
-              tma_load_4d(sa + s * SLAB, &maps.dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
+              tma_load_4d(sa + s * SLAB, &maps.dy, fb, co_blk * 128 + s * 64, w0, h0, n0);
 #pragma unroll
             for (int s = 0; s < BN / 64; ++s)
-              tma_load_4d(sb + s * SLAB, mx, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + dwx, h0 + dhx, n0);
+              tma_load_4d(sb + s * SLAB, mx, fb, ci_blk * BN + s * 64, w0 + dwx, h0 + dhx, n0);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
+      // Two MMA issuer warps (see conv3_kernel): k-blocks alternate, each issuer accumulates into its own TMEM
+      // accumulator (columns which * BN ..), the epilogue adds the two.  One full-barrier set per issuer.
       {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
+        const int which = warp - 1;
+        const uint32_t tmem_d = tmem_base + which * BN;
+        const uint32_t full_t = full_bar + 8 * which * STAGES;
+        int stage = which % STAGES;
+        uint32_t bits = 0;  // parity of this issuer's next fill, one bit per ring stage
+        const int last = ((num_k - 1 - which) & ~1) + which;  // this issuer's last k-block
+        for (int kb = which; kb < num_k; kb += 2) {
+          mbar_wait(full_t + 8 * stage, (bits >> stage) & 1u);
+          bits ^= 1u << stage;
           tc_fence_after();
           // MN-major SW128: 64-element MN slabs LBO apart, 8-row K groups SBO = 1024 B apart
           const uint64_t da = make_smem_desc_sw128(smem_a + stage * Cfg::A_BYTES, SLAB, 1024);
@@ -1259,13 +1291,13 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
 #pragma unroll
             for (int k = 0; k < Cfg::KP / 16; ++k) {
               // 16 pixels (K) further = 16 rows x 128 B = 2048 B -> +128 in (addr>>4)
-              umma_f16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(tmem_d, da + 128 * k, db + 128 * k, idesc, (kb >= 2 || k != 0) ? 1u : 0u);
             }
             umma_commit(empty_bar + 8 * stage);
-            if (kb == num_k - 1) umma_commit(tfull_bar);
+            if (kb == last) umma_commit(tfull_bar);
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage = (stage + 2) % STAGES;
         }
       }
     } else if (warp >= kEpiWarp0) {
@@ -1283,6 +1315,13 @@ conv_wgrad_kernel(const __grid_constant__ WMaps maps, const WGeom g, const TapTa
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c32 * 32, r);
         tmem_ld_wait();
+        if (num_k >= 2) {  // the second issuer's accumulator
+          uint32_t r2[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN + c32 * 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         if (part) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -1337,13 +1376,16 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                    const W3Geom g, float* __restrict__ dw, float* __restrict__ ws) {
   constexpr int A_BYTES = 2 * 64 * 128;  // two 64-channel slabs of dY, 64 pixels each
   constexpr int ASLAB = 64 * 128;
-  constexpr int TMEM_COLS = (3 * BN <= 256) ? 256 : 512;
+  // BN = 64: two MMA issuer warps (k-blocks alternate), each with its own set of three accumulators (2 x 192 columns);
+  // BN = 128: three accumulators already take 384 of the 512 columns -> one issuer
+  constexpr bool DUAL = (BN == 64);
+  constexpr int TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t full_bar = smem_base;            // 8 x 8 B
-  const uint32_t empty_bar = smem_base + 64;      // 8 x 8 B
-  const uint32_t tfull_bar = smem_base + 128;
-  const uint32_t tmem_slot = smem_base + 136;
+  const uint32_t full_bar = smem_base;            // 2 sets x 8 x 8 B
+  const uint32_t empty_bar = smem_base + 128;     // 8 x 8 B
+  const uint32_t tfull_bar = smem_base + 192;
+  const uint32_t tmem_slot = smem_base + 200;
   const uint32_t ring = smem_base + 1024;
   const uint32_t b_bytes = (BN / 64) * g.bslab;
   const uint32_t stage_bytes = A_BYTES + b_bytes;
@@ -1367,9 +1409,10 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
+      mbar_init(full_bar + 8 * (8 + i), 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
-    mbar_init(tfull_bar, 1);
+    mbar_init(tfull_bar, (DUAL && num_k >= 2) ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -1398,25 +1441,32 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + A_BYTES;
+          const uint32_t fb = full_bar + 8 * ((DUAL ? ((p - p_begin) & 1) : 0) * 8 + stage);
           if (elect_one()) {
-            mbar_arrive_expect_tx(full_bar + 8 * stage, a_slabs * ASLAB + b_bytes);
+            mbar_arrive_expect_tx(fb, a_slabs * ASLAB + b_bytes);
             for (int s = 0; s < a_slabs; ++s)
-              tma_load_4d(sa + s * ASLAB, &map_dy, full_bar + 8 * stage, co_blk * 128 + s * 64, w0, h0, n0);
+              tma_load_4d(sa + s * ASLAB, &map_dy, fb, co_blk * 128 + s * 64, w0, h0, n0);
 #pragma unroll
             for (int s = 0; s < BN / 64; ++s)
-              tma_load_4d(sb + s * g.bslab, &map_x, full_bar + 8 * stage, ci_blk * BN + s * 64, w0 + q - 1, h0 - 1, n0);
+              tma_load_4d(sb + s * g.bslab, &map_x, fb, ci_blk * BN + s * 64, w0 + q - 1, h0 - 1, n0);
           }
           __syncwarp();
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (DUAL && warp == 2)) {
       {
         constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
+        constexpr int NI = DUAL ? 2 : 1;  // issuer warps
+        const int which = warp - 1;
+        const uint32_t tmem_d = tmem_base + which * 3 * BN;
+        const uint32_t full_t = full_bar + 8 * which * 8;
+        int stage = which % g.stages;
+        uint32_t bits = 0;  // parity of this issuer's next fill, one bit per ring stage
+        const int last = NI == 2 ? ((num_k - 1 - which) & ~1) + which : num_k - 1;
+        for (int kb = which; kb < num_k; kb += NI) {
+          mbar_wait(full_t + 8 * stage, (bits >> stage) & 1u);
+          bits ^= 1u << stage;
           tc_fence_after();
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + A_BYTES;
@@ -1431,13 +1481,14 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               const uint64_t db = db0 + r * rstep;
 #pragma unroll
               for (int k = 0; k < 4; ++k)  // 64 pixels = 4 x K16; 16 pixels = 2048 B -> +128 in (addr >> 4)
-                umma_f16(tmem_base + r * BN, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_f16(tmem_d + r * BN, da + 128 * k, db + 128 * k, idesc, (kb >= NI || k != 0) ? 1u : 0u);
             }
             umma_commit(empty_bar + 8 * stage);
-            if (kb == num_k - 1) umma_commit(tfull_bar);
+            if (kb == last) umma_commit(tfull_bar);
           }
           __syncwarp();
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          stage += NI;
+          while (stage >= g.stages) stage -= g.stages;
         }
       }
     } else if (warp >= kEpiWarp0) {
@@ -1455,6 +1506,13 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + r * BN + c32 * 32, v);
           tmem_ld_wait();
+          if (DUAL && num_k >= 2) {  // the second issuer's accumulators
+            uint32_t v2[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + 3 * BN + r * BN + c32 * 32, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          }
           if (part) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -2337,9 +2395,9 @@ int pack_weight(const float* w32, void* w, void* wt, int cout, int taps, int cin
 
 #ifdef NPP_C3_PROF
 extern "C" int npp_debug_c3_prof(unsigned long long* out16, int reset) {
-  if (out16) cudaMemcpyFromSymbol(out16, npp::tc::g_c3_prof, sizeof(unsigned long long) * 16);
+  if (out16) cudaMemcpyFromSymbol(out16, npp::tc::g_c3_prof, sizeof(unsigned long long) * 32);
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[32] = {0};
     cudaMemcpyToSymbol(npp::tc::g_c3_prof, z, sizeof z);
   }
   return 0;

@@ -277,11 +277,17 @@ int main(int argc, char** argv) {
     typedef int (*prof_fn)(unsigned long long*, int);
     prof_fn prof = (prof_fn)dlsym(RTLD_DEFAULT, "npp_debug_c3_prof");
     if (prof != nullptr) {
-      unsigned long long v[16];
+      unsigned long long v[32];
       prof(nullptr, 1);
       for (int i = 0; i < 10; ++i) npp_conv2d_fwd(&vx, w, bptr, &vy_tc, c.k, c.k, c.stride, c.pad, c.dil, c.hoff, c.woff, stats, 0);
       CK(cudaDeviceSynchronize());
       prof(v, 1);
+      if (v[16]) {
+        const double u = (double)v[16];
+        printf("  epiprof (cycles per 128-row epilogue unit, fprop+stats, %.0f units/launch): staging wait %.0f | barrier 1 %.0f | "
+               "ld wait + convert + st.shared %.0f | fence + barrier 2 %.0f | store issue %.0f | statistics %.0f\n",
+               u / 10, v[17] / u, v[18] / u, v[19] / u, v[20] / u, v[21] / u, v[22] / u);
+      }
       if (v[8]) {
         const double t = (double)v[8];  // tiles over 10 launches
         printf("  c3prof (cycles per 256-pixel tile, fprop+stats): producer total %.0f wait-empty %.0f | weights total %.0f wait %.0f | "

@@ -10,7 +10,7 @@ grep -A1 "bench shape" gpurun_out/${tag}_conv_cases.log | grep -E "case|time"
 out=gpurun_out/${tag}_conv3_prof.txt
 : > $out
 export LD_LIBRARY_PATH=$PWD/tests/csrc/_bin/prof:$LD_LIBRARY_PATH
-for cs in 21 32 17 23; do
+for cs in 21 32 17 23 18 20; do
   timeout 90 tests/csrc/_bin/test_conv $cs 2>&1 | grep -v "PASS" >> $out
 done
 cat $out
