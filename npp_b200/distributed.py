@@ -135,6 +135,8 @@ def enable_sync_bn(group=True, peer=None):
         if old is not None:
             F_._state[key] = None
             old.close()
+    for old in (F_._state.pop("peer_comms", None) or {}).values():
+        old.close()
     F_._state["sync_bn"] = group if group else None
     if not group or not (dist.is_available() and dist.is_initialized()):
         return
@@ -147,9 +149,17 @@ def enable_sync_bn(group=True, peer=None):
             F_._state["peer_comm"] = PeerComm(pg)
             if F_._state.get("two_streams"):     # the second task stream issues its own sequence of exchanges
                 F_._state["peer_comm_side"] = PeerComm(pg)
+                # ... and so does every worker stream of functional.parallel_branches (branch j of a node always runs on
+                # worker j % n of its task stream's pool, the same on every rank): one communicator per stream role
+                comms = {}
+                for pool in ("main", "side"):
+                    for i in range(F_._N_WORKERS if F_._N_WORKERS >= 2 else 0):
+                        comms["worker:%s:%d" % (pool, i)] = PeerComm(pg)
+                F_._state["peer_comms"] = comms
         except Exception as exc:   # no peer access / IPC unavailable: the NCCL transport still works
             warnings.warn("SyncBN peer-memory exchange unavailable (%r): using NCCL all-reduces" % (exc,))
             F_._state["peer_comm"] = F_._state["peer_comm_side"] = None
+            F_._state["peer_comms"] = None
 
 
 def peer_comm():

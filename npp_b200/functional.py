@@ -207,11 +207,14 @@ def parallel_branches(fns):
     before returning the results (the MixedOps that feed one node of a search cell, model_search_interact.py:352-356:
     3-6 chains of ~50 small kernels each, nothing between them to share).  Inside a captured step they are parallel
     graph branches; autograd keeps every branch's backward on its worker stream.  Inputs the branches read must have
-    been produced on the current stream (they are marked for the workers via `inputs`); with SyncBN the branches stay
-    on one stream (the exchange sequence of a stream has to be the same on every rank AND per communicator).
+    been produced on the current stream (they are marked for the workers via `inputs`); with SyncBN every worker
+    stream has its own peer-memory communicator (distributed.enable_sync_bn) — branch j always runs on worker j % n, the
+    same on every rank, so each communicator sees the same exchange sequence everywhere; over NCCL the branches stay on
+    one stream.
     fns: list of (callable, inputs) pairs."""
     dev = torch.cuda.current_device() if torch.cuda.is_available() else None
-    if (not _state.get("two_streams") or _N_WORKERS < 2 or len(fns) < 2 or dev is None or _sync_group() is not None
+    if (not _state.get("two_streams") or _N_WORKERS < 2 or len(fns) < 2 or dev is None
+            or (_sync_group() is not None and not _state.get("peer_comms"))
             or not any(torch.is_tensor(t) and t.is_cuda for _, ins in fns for t in _flatten(ins))):
         return [fn() for fn, _ in fns]
     home = torch.cuda.current_stream()
@@ -801,9 +804,14 @@ def _allreduce_sum(t, t2=None):
     grp = None if g is True else g
     comm = _state.get("peer_comm")
     if comm is not None and t.is_cuda:
-        side = TaskStreams.side_stream_of(t.device.index)
-        if side is not None and _state.get("peer_comm_side") is not None and torch.cuda.current_stream() == side:
-            comm = _state["peer_comm_side"]     # exchanges of the second task stream: own sequence counter
+        # one communicator (= one device-side sequence counter) per stream that issues exchanges
+        role = _stream_role()
+        if role == "side" and _state.get("peer_comm_side") is not None:
+            comm = _state["peer_comm_side"]
+        elif role.startswith("worker:"):
+            comm = (_state.get("peer_comms") or {}).get(role)
+            if comm is None:
+                raise RuntimeError("SyncBN exchange on worker stream %r without a communicator" % role)
         comm.allreduce(t, t2)
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=grp)
