@@ -38,5 +38,7 @@ tot = sum((out["kernels"][k]["dram_read_bytes_per_launch"] + out["kernels"][k]["
           out["kernels"][k]["launches"] for k in gemm)
 out["conv_gemm"] = {"launches": n, "dram_bytes_per_launch": tot / max(n, 1), "kernels": gemm,
                     "source": "ncu per-launch metrics of one eager training step (batch 32 @384x384), " + src}
+out["source"] = ("ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum per launch over one eager step "
+                 "(tools/ncu_traffic.py, %s), %s" % (src, sys.argv[3] if len(sys.argv) > 3 else "build not named"))
 json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out["conv_gemm"]))
