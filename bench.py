@@ -528,12 +528,15 @@ def main():
             # DRAM traffic of the dominant kernel class: bytes per launch from the committed ncu per-launch capture of
             # the SAME kernels (profiles/roofline_traffic.json names the build it was taken from)
             traffic, traffic_src = None, None
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-                traffic = tj["conv_gemm"]["dram_bytes_per_launch"]
-                traffic_src = tj.get("source")
-            except Exception:
-                pass
+            if args.workload == "train":      # the capture is one eager step of THIS workload
+                try:
+                    tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+                    traffic = tj["conv_gemm"]["dram_bytes_per_launch"]
+                    traffic_src = tj.get("source") or tj["conv_gemm"].get("source")
+                except Exception:
+                    pass
+            else:
+                traffic_src = "not captured for this workload (profiles/roofline_traffic.json is the train step)"
             achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
             wg_tf = wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0
             kernels = {}
