@@ -12,6 +12,10 @@
 //   dgrad : dx[p] = [x[p] > 0] * sum_t dy[p + pad - t*dil] * w[t]            (stride 1; same kernel, flipped taps)
 //   wgrad : dw[c,t] += sum_p dy[p] * relu(x)[p*stride - pad + t*dil]         persistent CTAs keep the 9 x 8
 //           accumulators of their channel vector in registers over all their tiles, one atomic per (CTA, c, t).
+//
+// A block is CVL channel-vector lanes x 256 / CVL pixel lanes.  CVL = 8 (64 bf16 channels per block) for wide layers;
+// the search supernet runs its depthwise primitives on C / 4 = 16 or 32 channels (MixedOp, model_search_interact.py:
+// 39-74), where 8 lanes per pixel would leave 50-75 % of the threads without a channel vector: CVL = 4 / 2 there.
 #include "view.cuh"
 #include <stdlib.h>
 
@@ -20,7 +24,7 @@ namespace npp {
 struct DwTileGeom {
   int Hi, Wi, Ho, Wo, C, N;   // staged-tensor extents, produced-tensor extents
   int stride, dil, off_h, off_w;  // staged row of tap r for produced row h: h*stride + off + r*dil
-  int TW, TH, RPP, PPT;       // produced tile, rows per pass (32 / TW), pixels per thread
+  int TW, TH, RPP, PPT;       // produced tile, rows per pass (pixel lanes / TW), pixels per thread
   int IH, IW;                 // staged tile extents
   int tiles_w, tiles_h, cblocks, ntiles, slots;
 };
@@ -45,11 +49,11 @@ __device__ __forceinline__ uint4 relu_packed<__nv_bfloat16>(uint4 v) {
 }
 
 // stage the input tile of (n, th, tw, channel block) into shared memory (zero outside the tensor = zero padding)
-template <typename T>
+template <typename T, int CVL>
 __device__ __forceinline__ void dw_stage(uint4* tile, const DView<const T>& X, const DwTileGeom& g, int n, int ih0,
                                          int iw0, int c0, int cvn, bool relu) {
   constexpr int V = Pack<T>::N;
-  const int total = g.IH * g.IW * 8;
+  const int total = g.IH * g.IW * CVL;
   // four independent 16-byte loads in flight per thread before the first shared-memory store (the one-load-per-
   // iteration loop of the first version left the staging phase latency-bound)
   for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {
@@ -59,8 +63,8 @@ __device__ __forceinline__ void dw_stage(uint4* tile, const DView<const T>& X, c
       const int i = i0 + u * 256;
       v[u] = make_uint4(0u, 0u, 0u, 0u);
       if (i < total) {
-        const int cv = i & 7;
-        const int p = i >> 3;
+        const int cv = i % CVL;
+        const int p = i / CVL;
         const int pw = p % g.IW, ph = p / g.IW;
         const int h = ih0 + ph, w = iw0 + pw;
         if (cv < cvn && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi) v[u] = ldraw(X.at(n, h, w, c0 + cv * V));
@@ -74,7 +78,7 @@ __device__ __forceinline__ void dw_stage(uint4* tile, const DView<const T>& X, c
   }
 }
 
-template <typename T, bool BWD>
+template <typename T, bool BWD, int CVL>
 __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, const float* __restrict__ wgt,
                                                       const DView<T> Y, const DView<const T> M, const DwTileGeom g,
                                                       int relu_in) {
@@ -87,13 +91,13 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, co
   const int tw = b % g.tiles_w; b /= g.tiles_w;
   const int th = b % g.tiles_h;
   const int n = b / g.tiles_h;
-  const int c0 = cb * 8 * V;
+  const int c0 = cb * CVL * V;
   int cvn = (g.C - c0) / V;
-  if (cvn > 8) cvn = 8;
+  if (cvn > CVL) cvn = CVL;
   const int oh0 = th * g.TH, ow0 = tw * g.TW;
-  dw_stage<T>(tile, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn, !BWD && relu_in);
+  dw_stage<T, CVL>(tile, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn, !BWD && relu_in);
   __syncthreads();
-  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int cv = threadIdx.x % CVL, lane = threadIdx.x / CVL;
   if (cv >= cvn) return;
   const int c = c0 + cv * V;
   float wr[9][V];
@@ -118,13 +122,13 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, co
     float acc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.f;
-    const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+    const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * CVL + cv;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         float v[V];
-        Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+        Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * CVL], v);
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = fmaf(v[i], wr[r * 3 + q][i], acc[i]);
       }
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DView<const T> X, co
   }
 }
 
-template <typename T>
+template <typename T, int CVL>
 __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T> X, const DView<const T> DY,
                                                             float* __restrict__ dw, const DwTileGeom g, int relu_in) {
   pdl_wait();
@@ -147,10 +151,10 @@ __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T>
   uint4* tile = dw_tile_smem;
   const int cb = blockIdx.x % g.cblocks;
   const int slot = blockIdx.x / g.cblocks;
-  const int c0 = cb * 8 * V;
+  const int c0 = cb * CVL * V;
   int cvn = (g.C - c0) / V;
-  if (cvn > 8) cvn = 8;
-  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  if (cvn > CVL) cvn = CVL;
+  const int cv = threadIdx.x % CVL, lane = threadIdx.x / CVL;
   const int c = c0 + cv * V;
   const int pw = lane % g.TW, pr = lane / g.TW;
   float acc[9][V];
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T>
     const int n = b / g.tiles_h;
     const int oh0 = th * g.TH, ow0 = tw * g.TW;
     __syncthreads();  // the previous tile's readers are done
-    dw_stage<T>(tile, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn, relu_in != 0);
+    dw_stage<T, CVL>(tile, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn, relu_in != 0);
     __syncthreads();
     const int ow = ow0 + pw;
     if (cv < cvn && ow < g.Wo) {
@@ -180,13 +184,13 @@ __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T>
         if (k + 1 < g.PPT && ph + g.RPP < g.TH && oh + g.RPP < g.Ho) dnext = ldraw(DY.at(n, oh + g.RPP, ow, c));
         float d[V];
         Pack<T>::unpack(dcur, d);
-        const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+        const uint4* base = tile + ((ph * g.stride) * g.IW + pw * g.stride) * CVL + cv;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             float v[V];
-            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * CVL], v);
 #pragma unroll
             for (int i = 0; i < V; ++i) acc[r * 3 + q][i] = fmaf(d[i], v[i], acc[r * 3 + q][i]);
           }
@@ -201,12 +205,12 @@ __global__ void __launch_bounds__(256) dw_tile_wgrad_kernel(const DView<const T>
 #pragma unroll
     for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = acc[t][i];
     __syncthreads();
-    if (threadIdx.x < 8 * V) {
+    if (threadIdx.x < CVL * V) {
       const int cvj = threadIdx.x / V, ij = threadIdx.x % V;
       if (cvj < cvn) {
         float s = 0.f;
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) s += red[((l * 8) + cvj) * V + ij];
+        for (int l = 0; l < 256 / CVL; ++l) s += red[((l * CVL) + cvj) * V + ij];
         atomicAdd(dw + (int64_t)(c0 + threadIdx.x) * 9 + t, s);
       }
     }
@@ -229,15 +233,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename T>
+template <typename T, int CVL>
 __device__ __forceinline__ void dw_stage_async(uint4* tile, const DView<const T>& X, const DwTileGeom& g, int n, int ih0,
                                                int iw0, int c0, int cvn) {
   constexpr int V = Pack<T>::N;
-  const int total = g.IH * g.IW * 8;
+  const int total = g.IH * g.IW * CVL;
   const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
   for (int i = threadIdx.x; i < total; i += 256) {
-    const int cv = i & 7;
-    const int p = i >> 3;
+    const int cv = i % CVL;
+    const int p = i / CVL;
     const int pw = p % g.IW, ph = p / g.IW;
     const int h = ih0 + ph, w = iw0 + pw;
     const bool ok = cv < cvn && h >= 0 && h < g.Hi && w >= 0 && w < g.Wi;
@@ -245,9 +249,9 @@ __device__ __forceinline__ void dw_stage_async(uint4* tile, const DView<const T>
   }
 }
 // in-place ReLU of the elements this thread copied (visible to it after its own cp.async.wait_group)
-template <typename T>
+template <typename T, int CVL>
 __device__ __forceinline__ void dw_relu_own(uint4* tile, const DwTileGeom& g) {
-  const int total = g.IH * g.IW * 8;
+  const int total = g.IH * g.IW * CVL;
   for (int i = threadIdx.x; i < total; i += 256) tile[i] = relu_packed<T>(tile[i]);
 }
 
@@ -260,7 +264,7 @@ __device__ __forceinline__ void dw_tile_coords(const DwTileGeom& g, int tix, int
   ow0 = tw * g.TW;
 }
 
-template <typename T, bool BWD>
+template <typename T, bool BWD, int CVL>
 __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, const float* __restrict__ wgt,
                                                       const DView<T> Y, const DView<const T> M, const DwTileGeom g,
                                                       int relu_in, int tile_elems) {
@@ -269,10 +273,10 @@ __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, co
   extern __shared__ uint4 dw_tile_smem[];
   const int cb = blockIdx.x % g.cblocks;
   const int slot = blockIdx.x / g.cblocks;
-  const int c0 = cb * 8 * V;
+  const int c0 = cb * CVL * V;
   int cvn = (g.C - c0) / V;
-  if (cvn > 8) cvn = 8;
-  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  if (cvn > CVL) cvn = CVL;
+  const int cv = threadIdx.x % CVL, lane = threadIdx.x / CVL;
   const int c = c0 + cv * V;
   const int pw = lane % g.TW, pr = lane / g.TW;
   const bool cv_ok = cv < cvn;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, co
     int n, oh0, ow0;
     if (slot < g.ntiles) {
       dw_tile_coords(g, slot, n, oh0, ow0);
-      dw_stage_async<T>(dw_tile_smem, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn);
+      dw_stage_async<T, CVL>(dw_tile_smem, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn);
     }
     cp_async_commit();
   }
@@ -297,11 +301,11 @@ __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, co
     if (tix + g.slots < g.ntiles) {
       int n2, oh2, ow2;
       dw_tile_coords(g, tix + g.slots, n2, oh2, ow2);
-      dw_stage_async<T>(nxt, X, g, n2, oh2 * g.stride + g.off_h, ow2 * g.stride + g.off_w, c0, cvn);
+      dw_stage_async<T, CVL>(nxt, X, g, n2, oh2 * g.stride + g.off_h, ow2 * g.stride + g.off_w, c0, cvn);
     }
     cp_async_commit();       // (possibly empty) group: keeps the group count uniform
     cp_async_wait<1>();      // everything but the newest group has landed: tile `tix` is in `cur`
-    if (relu_stage) dw_relu_own<T>(cur, g);
+    if (relu_stage) dw_relu_own<T, CVL>(cur, g);
     __syncthreads();
     int n, oh0, ow0;
     dw_tile_coords(g, tix, n, oh0, ow0);
@@ -319,13 +323,13 @@ __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, co
         float acc[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        const uint4* base = cur + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+        const uint4* base = cur + ((ph * g.stride) * g.IW + pw * g.stride) * CVL + cv;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             float v[V];
-            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * CVL], v);
 #pragma unroll
             for (int i = 0; i < V; ++i) acc[i] = fmaf(v[i], wr[r * 3 + q][i], acc[i]);
           }
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(256) dw_pipe_kernel(const DView<const T> X, co
   cp_async_wait<0>();
 }
 
-template <typename T>
+template <typename T, int CVL>
 __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T> X, const DView<const T> DY,
                                                             float* __restrict__ dw, const DwTileGeom g, int relu_in,
                                                             int tile_elems) {
@@ -352,10 +356,10 @@ __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T>
   extern __shared__ uint4 dw_tile_smem[];
   const int cb = blockIdx.x % g.cblocks;
   const int slot = blockIdx.x / g.cblocks;
-  const int c0 = cb * 8 * V;
+  const int c0 = cb * CVL * V;
   int cvn = (g.C - c0) / V;
-  if (cvn > 8) cvn = 8;
-  const int cv = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  if (cvn > CVL) cvn = CVL;
+  const int cv = threadIdx.x % CVL, lane = threadIdx.x / CVL;
   const int c = c0 + cv * V;
   const int pw = lane % g.TW, pr = lane / g.TW;
   float acc[9][V];
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T>
     int n, oh0, ow0;
     if (slot < g.ntiles) {
       dw_tile_coords(g, slot, n, oh0, ow0);
-      dw_stage_async<T>(dw_tile_smem, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn);
+      dw_stage_async<T, CVL>(dw_tile_smem, X, g, n, oh0 * g.stride + g.off_h, ow0 * g.stride + g.off_w, c0, cvn);
     }
     cp_async_commit();
   }
@@ -378,11 +382,11 @@ __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T>
     if (tix + g.slots < g.ntiles) {
       int n2, oh2, ow2;
       dw_tile_coords(g, tix + g.slots, n2, oh2, ow2);
-      dw_stage_async<T>(nxt, X, g, n2, oh2 * g.stride + g.off_h, ow2 * g.stride + g.off_w, c0, cvn);
+      dw_stage_async<T, CVL>(nxt, X, g, n2, oh2 * g.stride + g.off_h, ow2 * g.stride + g.off_w, c0, cvn);
     }
     cp_async_commit();
     cp_async_wait<1>();
-    if (relu_in) dw_relu_own<T>(cur, g);
+    if (relu_in) dw_relu_own<T, CVL>(cur, g);
     __syncthreads();
     int n, oh0, ow0;
     dw_tile_coords(g, tix, n, oh0, ow0);
@@ -398,13 +402,13 @@ __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T>
         if (k + 1 < g.PPT && ph + g.RPP < g.TH && oh + g.RPP < g.Ho) dnext = ldraw(DY.at(n, oh + g.RPP, ow, c));
         float d[V];
         Pack<T>::unpack(dcur, d);
-        const uint4* base = cur + ((ph * g.stride) * g.IW + pw * g.stride) * 8 + cv;
+        const uint4* base = cur + ((ph * g.stride) * g.IW + pw * g.stride) * CVL + cv;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             float v[V];
-            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * 8], v);
+            Pack<T>::unpack(base[(r * g.dil * g.IW + q * g.dil) * CVL], v);
 #pragma unroll
             for (int i = 0; i < V; ++i) acc[r * 3 + q][i] = fmaf(d[i], v[i], acc[r * 3 + q][i]);
           }
@@ -421,12 +425,12 @@ __global__ void __launch_bounds__(256) dw_pipe_wgrad_kernel(const DView<const T>
 #pragma unroll
     for (int i = 0; i < V; ++i) red[threadIdx.x * V + i] = acc[t][i];
     __syncthreads();
-    if (threadIdx.x < 8 * V) {
+    if (threadIdx.x < CVL * V) {
       const int cvj = threadIdx.x / V, ij = threadIdx.x % V;
       if (cvj < cvn) {
         float s = 0.f;
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) s += red[((l * 8) + cvj) * V + ij];
+        for (int l = 0; l < 256 / CVL; ++l) s += red[((l * CVL) + cvj) * V + ij];
         atomicAdd(dw + (int64_t)(c0 + threadIdx.x) * 9 + t, s);
       }
     }
@@ -442,11 +446,18 @@ static int dw_pipe_enabled() {
   return v;
 }
 
+// Channel-vector lanes per pixel for a layer of C channels (V channels per 16-byte vector)
+static int dw_cvl(int C, int V) {
+  const int cv = (C + V - 1) / V;
+  return cv > 4 ? 8 : (cv > 2 ? 4 : 2);
+}
+
 // Tile geometry; returns false when the shape should stay on the gather kernels (stride-2 tiles that would not fit).
-static bool dw_tile_geom(DwTileGeom& g, int N, int Hi, int Wi, int Ho, int Wo, int C, int V, int stride, int dil,
+static bool dw_tile_geom(DwTileGeom& g, int N, int Hi, int Wi, int Ho, int Wo, int C, int V, int cvl, int stride, int dil,
                          int off_h, int off_w, size_t* smem) {
   g.N = N; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo; g.C = C;
   g.stride = stride; g.dil = dil; g.off_h = off_h; g.off_w = off_w;
+  const int lanes = 256 / cvl;  // pixel lanes of a block
   int best = 32;
   int64_t best_pad = -1;
   for (int tw = 32; tw >= 8; tw >>= 1) {
@@ -454,8 +465,8 @@ static bool dw_tile_geom(DwTileGeom& g, int N, int Hi, int Wi, int Ho, int Wo, i
     if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = tw; }
   }
   g.TW = best;
-  g.RPP = 32 / g.TW;
-  int th = 256 / g.TW;
+  g.RPP = lanes / g.TW;
+  int th = 8 * g.RPP;             // eight passes per tile: 256 / 512 / 1024 pixels for 8 / 4 / 2 vector lanes
   const int hround = (int)(cdiv64(Ho, g.RPP) * g.RPP);
   if (th > hround) th = hround;
   g.TH = th;
@@ -464,12 +475,12 @@ static bool dw_tile_geom(DwTileGeom& g, int N, int Hi, int Wi, int Ho, int Wo, i
   g.IW = (g.TW - 1) * stride + 2 * dil + 1;
   g.tiles_w = (int)cdiv64(Wo, g.TW);
   g.tiles_h = (int)cdiv64(Ho, g.TH);
-  g.cblocks = (int)cdiv64(C, 8 * V);
+  g.cblocks = (int)cdiv64(C, cvl * V);
   const int64_t ntiles = (int64_t)N * g.tiles_h * g.tiles_w;
   if (ntiles * g.cblocks > 0x7fffffff) return false;
   g.ntiles = (int)ntiles;
   g.slots = 1;
-  *smem = (size_t)g.IH * g.IW * 8 * 16;
+  *smem = (size_t)g.IH * g.IW * cvl * 16;
   if (*smem < (size_t)256 * V * 4) *smem = (size_t)256 * V * 4;
   return *smem <= 100 * 1024;
 }
@@ -503,29 +514,86 @@ static void dw_pipe_slots(DwTileGeom& g) {
   g.slots = slots;
 }
 
+template <typename T, int CVL>
+static int dw_fwd_launch(const npp_view4* x, const float* w, const npp_view4* y, DwTileGeom& g, size_t smem, int relu_in,
+                         cudaStream_t st) {
+  constexpr int TAG = sizeof(T) * 10 + CVL * 100;
+  const auto X = dview<const T>(x);
+  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
+    int rc = dw_set_smem2<TAG + 3>(dw_pipe_kernel<T, false, CVL>, "cudaFuncSetAttribute(dw_pipe_fwd)");
+    if (rc) return rc;
+    dw_pipe_slots(g);
+    NPP_LAUNCH((dw_pipe_kernel<T, false, CVL>), g.slots * g.cblocks, 256, 2 * smem, st, X, w, dview<T>(y), X, g, relu_in,
+                                                                              (int)(smem / 16));
+    NPP_CHECK_LAUNCH("dw_pipe_fwd");
+    return NPP_OK;
+  }
+  int rc = dw_set_smem<TAG + 0>(dw_tile_kernel<T, false, CVL>, "cudaFuncSetAttribute(dw_tile_fwd)");
+  if (rc) return rc;
+  NPP_LAUNCH((dw_tile_kernel<T, false, CVL>), g.ntiles * g.cblocks, 256, smem, st, X, w, dview<T>(y), X, g, relu_in);
+  NPP_CHECK_LAUNCH("dw_tile_fwd");
+  return NPP_OK;
+}
+
+template <typename T, int CVL>
+static int dw_dgrad_launch(const npp_view4* x, const float* w, const npp_view4* dy, const npp_view4* dx, DwTileGeom& g,
+                           size_t smem, int relu_in, cudaStream_t st) {
+  constexpr int TAG = sizeof(T) * 10 + CVL * 100;
+  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
+    int rc = dw_set_smem2<TAG + 4>(dw_pipe_kernel<T, true, CVL>, "cudaFuncSetAttribute(dw_pipe_dgrad)");
+    if (rc) return rc;
+    dw_pipe_slots(g);
+    NPP_LAUNCH((dw_pipe_kernel<T, true, CVL>), g.slots * g.cblocks, 256, 2 * smem, st, dview<const T>(dy), w, dview<T>(dx),
+                                                                             dview<const T>(x), g, relu_in, (int)(smem / 16));
+    NPP_CHECK_LAUNCH("dw_pipe_dgrad");
+    return NPP_OK;
+  }
+  int rc = dw_set_smem<TAG + 1>(dw_tile_kernel<T, true, CVL>, "cudaFuncSetAttribute(dw_tile_dgrad)");
+  if (rc) return rc;
+  NPP_LAUNCH((dw_tile_kernel<T, true, CVL>), g.ntiles * g.cblocks, 256, smem, st, dview<const T>(dy), w, dview<T>(dx),
+                                                                         dview<const T>(x), g, relu_in);
+  NPP_CHECK_LAUNCH("dw_tile_dgrad");
+  return NPP_OK;
+}
+
+template <typename T, int CVL>
+static int dw_wgrad_launch(const npp_view4* x, const npp_view4* dy, float* dw, DwTileGeom& g, size_t smem, int relu_in,
+                           cudaStream_t st) {
+  constexpr int TAG = sizeof(T) * 10 + CVL * 100;
+  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
+    int rc = dw_set_smem2<TAG + 5>(dw_pipe_wgrad_kernel<T, CVL>, "cudaFuncSetAttribute(dw_pipe_wgrad)");
+    if (rc) return rc;
+    dw_pipe_slots(g);
+    NPP_LAUNCH((dw_pipe_wgrad_kernel<T, CVL>), g.slots * g.cblocks, 256, 2 * smem, st, dview<const T>(x), dview<const T>(dy), dw,
+                                                                             g, relu_in, (int)(smem / 16));
+    NPP_CHECK_LAUNCH("dw_pipe_wgrad");
+    return NPP_OK;
+  }
+  int rc = dw_set_smem<TAG + 2>(dw_tile_wgrad_kernel<T, CVL>, "cudaFuncSetAttribute(dw_tile_wgrad)");
+  if (rc) return rc;
+  int slots = (2 * sm_count()) / g.cblocks;  // (4 per SM measured slower: twice the same-address atomics at the end)
+  if (slots < 1) slots = 1;
+  if (slots > g.ntiles) slots = g.ntiles;
+  g.slots = slots;
+  NPP_LAUNCH((dw_tile_wgrad_kernel<T, CVL>), slots * g.cblocks, 256, smem, st, dview<const T>(x), dview<const T>(dy), dw, g,
+                                                                             relu_in);
+  NPP_CHECK_LAUNCH("dw_tile_wgrad");
+  return NPP_OK;
+}
+
+#define NPP_DW_CVL(cvl, expr8, expr4, expr2) ((cvl) == 8 ? (expr8) : ((cvl) == 4 ? (expr4) : (expr2)))
+
 // returns NPP_E_UNSUPPORTED when the caller should use the gather kernels instead
 template <typename T>
 int dw_tile_fwd(const npp_view4* x, const float* w, const npp_view4* y, int stride, int pad, int dil, int relu_in,
                 cudaStream_t st) {
   DwTileGeom g;
   size_t smem;
-  if (!dw_tile_geom(g, y->n, x->h, x->w, y->h, y->w, y->c, Pack<T>::N, stride, dil, -pad, -pad, &smem))
+  const int cvl = dw_cvl(y->c, Pack<T>::N);
+  if (!dw_tile_geom(g, y->n, x->h, x->w, y->h, y->w, y->c, Pack<T>::N, cvl, stride, dil, -pad, -pad, &smem))
     return NPP_E_UNSUPPORTED;
-  const auto X = dview<const T>(x);
-  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
-    int rc = dw_set_smem2<sizeof(T) * 10 + 3>(dw_pipe_kernel<T, false>, "cudaFuncSetAttribute(dw_pipe_fwd)");
-    if (rc) return rc;
-    dw_pipe_slots(g);
-    NPP_LAUNCH((dw_pipe_kernel<T, false>), g.slots * g.cblocks, 256, 2 * smem, st, X, w, dview<T>(y), X, g, relu_in,
-                                                                         (int)(smem / 16));
-    NPP_CHECK_LAUNCH("dw_pipe_fwd");
-    return NPP_OK;
-  }
-  int rc = dw_set_smem<sizeof(T) * 10 + 0>(dw_tile_kernel<T, false>, "cudaFuncSetAttribute(dw_tile_fwd)");
-  if (rc) return rc;
-  NPP_LAUNCH((dw_tile_kernel<T, false>), g.ntiles * g.cblocks, 256, smem, st, X, w, dview<T>(y), X, g, relu_in);
-  NPP_CHECK_LAUNCH("dw_tile_fwd");
-  return NPP_OK;
+  return NPP_DW_CVL(cvl, (dw_fwd_launch<T, 8>(x, w, y, g, smem, relu_in, st)), (dw_fwd_launch<T, 4>(x, w, y, g, smem, relu_in, st)),
+                    (dw_fwd_launch<T, 2>(x, w, y, g, smem, relu_in, st)));
 }
 
 template <typename T>
@@ -534,24 +602,13 @@ int dw_tile_dgrad(const npp_view4* x, const float* w, const npp_view4* dy, const
   if (stride != 1) return NPP_E_UNSUPPORTED;
   DwTileGeom g;
   size_t smem;
+  const int cvl = dw_cvl(dx->c, Pack<T>::N);
   // dx[h] = sum_t dy[h + pad - t*dil] w[t] = sum_t' dy[h + pad - 2*dil + t'*dil] w[2 - t']
-  if (!dw_tile_geom(g, dx->n, dy->h, dy->w, dx->h, dx->w, dx->c, Pack<T>::N, 1, dil, pad - 2 * dil, pad - 2 * dil, &smem))
+  if (!dw_tile_geom(g, dx->n, dy->h, dy->w, dx->h, dx->w, dx->c, Pack<T>::N, cvl, 1, dil, pad - 2 * dil, pad - 2 * dil, &smem))
     return NPP_E_UNSUPPORTED;
-  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
-    int rc = dw_set_smem2<sizeof(T) * 10 + 4>(dw_pipe_kernel<T, true>, "cudaFuncSetAttribute(dw_pipe_dgrad)");
-    if (rc) return rc;
-    dw_pipe_slots(g);
-    NPP_LAUNCH((dw_pipe_kernel<T, true>), g.slots * g.cblocks, 256, 2 * smem, st, dview<const T>(dy), w, dview<T>(dx),
-                                                                        dview<const T>(x), g, relu_in, (int)(smem / 16));
-    NPP_CHECK_LAUNCH("dw_pipe_dgrad");
-    return NPP_OK;
-  }
-  int rc = dw_set_smem<sizeof(T) * 10 + 1>(dw_tile_kernel<T, true>, "cudaFuncSetAttribute(dw_tile_dgrad)");
-  if (rc) return rc;
-  NPP_LAUNCH((dw_tile_kernel<T, true>), g.ntiles * g.cblocks, 256, smem, st, dview<const T>(dy), w, dview<T>(dx),
-                                                                    dview<const T>(x), g, relu_in);
-  NPP_CHECK_LAUNCH("dw_tile_dgrad");
-  return NPP_OK;
+  return NPP_DW_CVL(cvl, (dw_dgrad_launch<T, 8>(x, w, dy, dx, g, smem, relu_in, st)),
+                    (dw_dgrad_launch<T, 4>(x, w, dy, dx, g, smem, relu_in, st)),
+                    (dw_dgrad_launch<T, 2>(x, w, dy, dx, g, smem, relu_in, st)));
 }
 
 template <typename T>
@@ -559,26 +616,12 @@ int dw_tile_wgrad(const npp_view4* x, const npp_view4* dy, float* dw, int stride
                   cudaStream_t st) {
   DwTileGeom g;
   size_t smem;
-  if (!dw_tile_geom(g, dy->n, x->h, x->w, dy->h, dy->w, dy->c, Pack<T>::N, stride, dil, -pad, -pad, &smem))
+  const int cvl = dw_cvl(dy->c, Pack<T>::N);
+  if (!dw_tile_geom(g, dy->n, x->h, x->w, dy->h, dy->w, dy->c, Pack<T>::N, cvl, stride, dil, -pad, -pad, &smem))
     return NPP_E_UNSUPPORTED;
-  if (dw_pipe_enabled() && 2 * smem <= 112 * 1024) {
-    int rc = dw_set_smem2<sizeof(T) * 10 + 5>(dw_pipe_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_pipe_wgrad)");
-    if (rc) return rc;
-    dw_pipe_slots(g);
-    NPP_LAUNCH((dw_pipe_wgrad_kernel<T>), g.slots * g.cblocks, 256, 2 * smem, st, dview<const T>(x), dview<const T>(dy), dw, g,
-                                                                        relu_in, (int)(smem / 16));
-    NPP_CHECK_LAUNCH("dw_pipe_wgrad");
-    return NPP_OK;
-  }
-  int rc = dw_set_smem<sizeof(T) * 10 + 2>(dw_tile_wgrad_kernel<T>, "cudaFuncSetAttribute(dw_tile_wgrad)");
-  if (rc) return rc;
-  int slots = (2 * sm_count()) / g.cblocks;  // (4 per SM measured slower: twice the same-address atomics at the end)
-  if (slots < 1) slots = 1;
-  if (slots > g.ntiles) slots = g.ntiles;
-  g.slots = slots;
-  NPP_LAUNCH((dw_tile_wgrad_kernel<T>), slots * g.cblocks, 256, smem, st, dview<const T>(x), dview<const T>(dy), dw, g, relu_in);
-  NPP_CHECK_LAUNCH("dw_tile_wgrad");
-  return NPP_OK;
+  return NPP_DW_CVL(cvl, (dw_wgrad_launch<T, 8>(x, dy, dw, g, smem, relu_in, st)),
+                    (dw_wgrad_launch<T, 4>(x, dy, dw, g, smem, relu_in, st)),
+                    (dw_wgrad_launch<T, 2>(x, dy, dw, g, smem, relu_in, st)));
 }
 
 template int dw_tile_fwd<float>(const npp_view4*, const float*, const npp_view4*, int, int, int, int, cudaStream_t);

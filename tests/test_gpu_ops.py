@@ -161,12 +161,14 @@ def test_maxpool_ties_route_to_first_max(dtype, lib_built):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 128, 96, 96, 2, 1), (2, 64, 48, 48, 4, 1), (3, 32, 24, 24, 2, 1),
                                    (2, 256, 12, 12, 4, 1), (2, 64, 48, 48, 2, 2), (2, 40, 23, 17, 2, 1),
-                                   (1, 72, 33, 50, 4, 2), (2, 32, 96, 96, 1, 1)],
+                                   (1, 72, 33, 50, 4, 2), (2, 32, 96, 96, 1, 1),
+                                   (2, 16, 96, 96, 2, 1), (3, 24, 30, 22, 4, 1), (2, 8, 40, 72, 2, 1)],
                          ids=lambda s: "n%dc%d_%dx%d_d%ds%d" % s)
 @pytest.mark.parametrize("relu_in", [0, 1])
 def test_depthwise_conv_vs_torch(shape, relu_in, dtype, lib_built):
     """Depthwise dilated 3x3 (DilConvS.net[1], operations.py:213) at the network's real shapes — the shared-memory
-    tiled kernels (multi-tile images, partial channel blocks, ragged tiles) and the gather fallback (stride 2) —
+    tiled kernels (multi-tile images, partial channel blocks, ragged tiles; 8 / 4 / 2 channel-vector lanes per pixel
+    for wide layers / the supernet's 32- and 16-channel MixedOp slices) and the gather fallback (stride 2) —
     forward, input gradient and weight gradient against torch's grouped convolution on the same rounded inputs."""
     import torch.nn.functional as TF
     from npp_b200 import functional as F_
