@@ -4,6 +4,7 @@ tag=${1:-r2prof}
 mkdir -p gpurun_out
 out=gpurun_out/${tag}_conv3_prof.txt
 : > $out
+[ -f tests/csrc/_bin/prof/libnpp_b200.so ] || { echo "no profile build (tools/build_conv_prof.sh)"; exit 0; }
 export LD_LIBRARY_PATH=$PWD/tests/csrc/_bin/prof:$LD_LIBRARY_PATH
 for cs in 21 32 17 23 24 25; do
   timeout 90 tests/csrc/_bin/test_conv $cs 2>&1 | grep -v "PASS" >> $out
