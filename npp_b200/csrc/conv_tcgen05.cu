@@ -574,8 +574,128 @@ __device__ __forceinline__ void epi_pair32(const uint32_t taddr, uint8_t* stg, c
   }
 }
 
+// ---- two-group epilogue (EPI2) ------------------------------------------------------------------------------
+// epi_unit marches all eight epilogue warps through one 128 x 64 unit in lockstep: per unit two 256-thread barriers,
+// the wait for the staging slab, the tcgen05.ld latency and the proxy fence sit on everybody's critical path (~540 of
+// the ~1470 cycles of a unit, profiles/r02_conv3_wait_profile.txt) while the issue slots are 75 % idle.  Here the warps
+// form two independent groups of four (one staging slab and one named barrier each) that work on DIFFERENT units —
+// alternate 64-channel slabs of a tile, the two pixel halves of a conv3 tile, or alternate tiles — so one group's
+// bubbles are filled by the other group's conversions and sums.  Warp q of a group drains rows q*32.. of the whole
+// slab (two tcgen05.ld of 32 columns) and owns the 16-byte chunks 2q, 2q+1 (16 channels) for the BatchNorm sums.
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int SLAB_COLS>
+__device__ __forceinline__ void epi_unit_grp(const uint32_t taddr, uint8_t* stg, const uint32_t stg_s,
+                                             const CUtensorMap* md, const int co_base, const int c_w, const int c_h,
+                                             const int c_n, const float* __restrict__ bias, const int cout,
+                                             const uint32_t release_bar, const bool want_stats, const EpiMask& mk,
+                                             float (&as)[SLAB_COLS / 4], float (&aq)[SLAB_COLS / 4], const int q,
+                                             const int lane, const int gtid, const int bar_id) {
+  constexpr int HALVES = SLAB_COLS / 32;  // tcgen05.ld rounds of 32 columns
+  const int row = q * 32 + lane;
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  // this group's previous TMA store must have finished reading the staging slab
+  if (gtid == 0) tma_store_wait_read<0>();
+  bar_sync_named(bar_id, 128);
+#pragma unroll
+  for (int hf = 0; hf < HALVES; ++hf) {
+    tmem_ld_wait_regs(r);
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float v0 = __uint_as_float(r[2 * e]);
+      float v1 = __uint_as_float(r[2 * e + 1]);
+      if (bias != nullptr) {
+        const int c0 = co_base + hf * 32 + 2 * e;
+        v0 += (c0 < cout) ? __ldg(bias + c0) : 0.f;
+        v1 += (c0 + 1 < cout) ? __ldg(bias + c0 + 1) : 0.f;
+      }
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      pk[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    if (hf + 1 < HALVES) tmem_ld_32x32(taddr + 32, r);  // the second half is in flight while the first is stored
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int chunk = hf * 4 + j;
+      *reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+          make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+  }
+  if (release_bar != 0u) {  // this thread's last TMEM read of the tile has completed
+    tc_fence_before();
+    mbar_arrive(release_bar);
+  }
+  fence_proxy_async_smem();
+  bar_sync_named(bar_id, 128);
+  if (gtid == 0) {
+    tma_store_4d(md, stg_s, co_base, c_w, c_h, c_n);
+    tma_store_commit();
+  }
+  if (want_stats) {
+    constexpr int NCH = SLAB_COLS / 32;  // 16-byte chunks per warp: 2 (64-column slab) or 1
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      const int chunk = NCH * q + cc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = lane * 4 + ((i + (lane >> 1)) & 3);  // lane-skewed: conflict-free LDS.128 (see epi_unit)
+        bool ok = true;
+        if (!mk.full) {
+          const int p = mk.p_off + rr;
+          const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
+          ok = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
+        }
+        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+        if (ok) {
+          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
+            const float2 s2 = __fadd2_rn(make_float2(as[cc * 8 + 2 * e], as[cc * 8 + 2 * e + 1]), v);
+            const float2 q2 = __ffma2_rn(v, v, make_float2(aq[cc * 8 + 2 * e], aq[cc * 8 + 2 * e + 1]));
+            as[cc * 8 + 2 * e] = s2.x; as[cc * 8 + 2 * e + 1] = s2.y;
+            aq[cc * 8 + 2 * e] = q2.x; aq[cc * 8 + 2 * e + 1] = q2.y;
+          }
+        }
+      }
+    }
+  }
+}
+
+// fold the 32 row groups of a warp; one 16-byte reduction per four channels (see epi_flush_stats)
+template <int NCH>
+__device__ __forceinline__ void epi_flush_grp(float (&as)[NCH * 8], float (&aq)[NCH * 8], float* __restrict__ stats,
+                                              const int co_slab, const int cout, const int q, const int lane) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(stats) & 15u) == 0) && ((cout & 3) == 0);
+#pragma unroll
+  for (int cc = 0; cc < NCH; ++cc) {
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = warp_sum(as[cc * 8 + k]); b[k] = warp_sum(aq[cc * 8 + k]); }
+    const int co = co_slab + (NCH * q + cc) * 8;
+    if (lane == 0) {
+      if (vec && co + 8 <= cout) {
+        red_add_v4(stats + co, a[0], a[1], a[2], a[3]);
+        red_add_v4(stats + co + 4, a[4], a[5], a[6], a[7]);
+        red_add_v4(stats + cout + co, b[0], b[1], b[2], b[3]);
+        red_add_v4(stats + cout + co + 4, b[4], b[5], b[6], b[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (co + k < cout) {
+            atomicAdd(stats + co + k, a[k]);
+            atomicAdd(stats + cout + co + k, b[k]);
+          }
+      }
+    }
+  }
+}
+
 // Same pipeline as conv_gemm_kernel (TMA producer warp, MMA warp, two TMEM accumulator stages), eight-warp epilogue.
-template <int BN>
+template <int BN, bool EPI2>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTable taps,
                   const float* __restrict__ bias, float* __restrict__ stats) {
@@ -610,7 +730,8 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 256);
+      // arrivals per tile: all eight epilogue warps, or (EPI2 with a single slab: the two groups alternate tiles) four
+      mbar_init(tempty_bar + 8 * i, (EPI2 && BN <= 64) ? 128 : 256);
     }
     fence_barrier_init();
   }
@@ -699,6 +820,68 @@ conv_gemm2_kernel(const __grid_constant__ Maps maps, const Geom g, const TapTabl
         acc_phase ^= 1;
       }
     }
+  } else if (warp >= 4 && EPI2) {
+    // ------------------------------------------------------------------ two-group epilogue (see epi_unit_grp)
+    const int ew = warp - 4, q = warp & 3, gi = ew >> 2;
+    const int gtid = threadIdx.x - 128 - gi * 128;
+    int nslab = (g.cout - nb * BN + 63) / 64;  // slabs of this CTA's channel block that hold real channels
+    if (nslab > SLABS) nslab = SLABS;
+    constexpr int GS = SLABS >= 2 ? SLABS / 2 : 1;  // slabs of a tile per group
+    constexpr int NCH = SLAB_COLS / 32;
+    uint8_t* stg = smem_gen + (smem_out - smem_base) + gi * (BM * 128);
+    const uint32_t stg_s = smem_out + gi * (BM * 128);
+    float gs_[GS][NCH * 8], gq_[GS][NCH * 8];
+#pragma unroll
+    for (int sl = 0; sl < GS; ++sl)
+#pragma unroll
+      for (int k = 0; k < NCH * 8; ++k) { gs_[sl][k] = 0.f; gq_[sl][k] = 0.f; }
+    // SLABS >= 2: both groups work on every tile (group gi: slabs gi, gi + 2); one slab: the groups alternate tiles
+    // (group gi <-> accumulator stage gi, like the MMA issuer warps)
+    constexpr bool ALT = SLABS < 2;
+    int acc = ALT ? gi : 0;
+    uint32_t acc_phase = 0;
+    for (int ptile = pt_start + (ALT ? gi * pt_step : 0); ptile < g.num_ptiles; ptile += (ALT ? 2 : 1) * pt_step) {
+      int pt = ptile;
+      EpiMask mk;
+      mk.tw = g.tw; mk.th = g.th; mk.W = g.W; mk.H = g.H; mk.N = g.N; mk.p_off = 0;
+      mk.w0 = (pt % g.tiles_w) * g.tw;
+      pt /= g.tiles_w;
+      mk.h0 = (pt % g.tiles_h) * g.th;
+      mk.n0 = (pt / g.tiles_h) * g.tn;
+      mk.full = (mk.w0 + g.tw <= g.W) && (mk.h0 + g.th <= g.H) && (mk.n0 + g.tn <= g.N);
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      bool released = false;
+#pragma unroll
+      for (int s2 = 0; s2 < GS; ++s2) {
+        const int slab = ALT ? 0 : gi + 2 * s2;
+        if (slab < nslab) {  // uniform across the group
+          const bool last = ALT || slab + 2 >= nslab;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN + slab * 64);
+          epi_unit_grp<SLAB_COLS>(taddr, stg, stg_s, &maps.d, nb * BN + slab * 64, mk.w0, mk.h0, mk.n0, bias, g.cout,
+                                  last ? tempty_bar + 8 * acc : 0u, stats != nullptr, mk, gs_[s2], gq_[s2], q, lane, gtid,
+                                  1 + gi);
+          released = released || last;
+        }
+      }
+      if (!released) {  // no slab of this tile belongs to the group: the accumulator stage is free as far as it goes
+        tc_fence_before();
+        mbar_arrive(tempty_bar + 8 * acc);
+      }
+      if (ALT) {
+        acc_phase ^= 1;
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    if (stats != nullptr) {
+#pragma unroll
+      for (int s2 = 0; s2 < GS; ++s2)
+        epi_flush_grp<NCH>(gs_[s2], gq_[s2], stats, nb * BN + (ALT ? 0 : gi + 2 * s2) * 64, g.cout, q, lane);
+    }
+    if (gtid == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     const int ew = warp - 4, q = warp & 3, hf = ew >> 2;
     const int etid = threadIdx.x - 128;
@@ -785,7 +968,7 @@ struct C3Geom {
 constexpr int kC3MaxSA = 4, kC3MaxSB = 8;
 constexpr int kC3OutBytes = 2 * 128 * 128;
 
-template <int BN>
+template <int BN, bool EPI2>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* __restrict__ bias,
              float* __restrict__ stats) {
@@ -1077,6 +1260,65 @@ conv3_kernel(const __grid_constant__ C3Maps maps, const C3Geom g, const float* _
       if (m_issue) { C3P_ADD(11, m_issue); C3P_ADD(12, m_commit); }
 #endif
     }
+  } else if (warp >= 4 && EPI2 && BN >= 64) {
+    // ------------------------------------------------------------------ two-group epilogue (see epi_unit_grp):
+    // BN = 64: group gi drains pixel half gi of every tile; BN = 128: group gi drains slab gi of both pixel halves
+    const int ew = warp - 4, q = warp & 3, gi = ew >> 2;
+    const int gtid = threadIdx.x - 128 - gi * 128;
+    int nslab = (g.cout + 63) / 64;
+    if (nslab > SLABS) nslab = SLABS;
+    uint8_t* stg = smem_gen + (smem_out - smem_base) + gi * (128 * 128);
+    const uint32_t stg_s = smem_out + gi * (128 * 128);
+    float gs_[16], gq_[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { gs_[k] = 0.f; gq_[k] = 0.f; }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    C3P_DECL(e_wait);
+#ifdef NPP_C3_PROF
+    const long long e_t0 = clock64();
+#endif
+    for (int ptile = blockIdx.x; ptile < g.num_ptiles; ptile += gridDim.x) {
+      int pt = ptile;
+      EpiMask mk;
+      mk.tw = g.tw; mk.th = g.th; mk.W = g.W; mk.H = g.H; mk.N = 1; mk.n0 = 0;
+      mk.w0 = (pt % g.tiles_w) * g.tw;
+      pt /= g.tiles_w;
+      mk.h0 = (pt % g.tiles_h) * g.th;
+      const int n0 = pt / g.tiles_h;
+      mk.full = (mk.w0 + g.tw <= g.W) && (mk.h0 + g.th <= g.H);
+      C3P_WAIT(e_wait, mbar_wait(tfull_bar + 8 * acc, acc_phase));
+      tc_fence_after();
+      if constexpr (SLABS == 1) {
+        const int m = gi;
+        mk.p_off = m * 128;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * 2 + m) * BN);
+        epi_unit_grp<64>(taddr, stg, stg_s, &maps.d, 0, mk.w0, mk.h0 + m * (g.th >> 1), n0, bias, g.cout,
+                         tempty_bar + 8 * acc, stats != nullptr, mk, gs_, gq_, q, lane, gtid, 1 + gi);
+      } else {
+        const int slab = gi;
+        if (slab < nslab) {  // uniform across the group
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            mk.p_off = m * 128;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>((acc * 2 + m) * BN + slab * 64);
+            epi_unit_grp<64>(taddr, stg, stg_s, &maps.d, slab * 64, mk.w0, mk.h0 + m * (g.th >> 1), n0, bias, g.cout,
+                             m == 1 ? tempty_bar + 8 * acc : 0u, stats != nullptr, mk, gs_, gq_, q, lane, gtid, 1 + gi);
+          }
+        } else {
+          tc_fence_before();
+          mbar_arrive(tempty_bar + 8 * acc);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+#ifdef NPP_C3_PROF
+    if (gtid == 0 && gi == 0) { C3P_ADD(6, clock64() - e_t0); C3P_ADD(7, e_wait); }
+#endif
+    if (stats != nullptr) epi_flush_grp<2>(gs_, gq_, stats, (SLABS == 1 ? 0 : gi) * 64, g.cout, q, lane);
+    if (gtid == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (eight warps)
     const int ew = warp - 4, q = warp & 3, hf = ew >> 2;
@@ -1733,14 +1975,21 @@ static int launch_fprop(const Maps& maps, const Geom& g, const TapTable& taps, c
   if (per_nb > g.num_ptiles) per_nb = g.num_ptiles;
   const int grid = per_nb * g.n_blocks;
   static const int epi8 = env_flag("NPP_CONV_EPI8", 1);
+  static const int epi2 = env_flag("NPP_CONV_EPI2", 1);
   if (epi8) {
     static bool attr2_set = false;
     if (!attr2_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm2_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_gemm2_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_gemm2)", e); return NPP_E_CUDA; }
       attr2_set = true;
     }
-    NPP_LAUNCH((conv_gemm2_kernel<BN>), grid, kThreads2, Cfg::SMEM, st, maps, g, taps, bias, stats);
+    if (epi2) {
+      NPP_LAUNCH((conv_gemm2_kernel<BN, true>), grid, kThreads2, Cfg::SMEM, st, maps, g, taps, bias, stats);
+    } else {
+      NPP_LAUNCH((conv_gemm2_kernel<BN, false>), grid, kThreads2, Cfg::SMEM, st, maps, g, taps, bias, stats);
+    }
     NPP_CHECK_LAUNCH("conv_gemm2_kernel");
     return NPP_OK;
   }
@@ -1820,14 +2069,23 @@ static int run_gemm(const npp_view4* a_views, int n_a, const npp_view4* d, const
 template <int BN>
 static int launch_conv3(const C3Maps& maps, const C3Geom& g, int smem, const float* bias, float* stats, cudaStream_t st) {
   static bool attr_set = false;
+  // two-group epilogue: measured a gain for the generic kernel with statistics (1x1 128 -> 128 @ 96^2: 41.3 -> 37.2 us,
+  // 1024 -> 512: 292 -> 268 us) but not here (3x3 128 -> 128: 68.5 -> 70.5 us), profiles/r02_epi2_ab.txt: off for conv3
+  static const int epi2 = env_flag("NPP_CONV3_EPI2", 0);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv3)", e); return NPP_E_CUDA; }
     attr_set = true;
   }
   int grid = sm_count();
   if (grid > g.num_ptiles) grid = g.num_ptiles;
-  NPP_LAUNCH((conv3_kernel<BN>), grid, kThreads2, smem, st, maps, g, bias, stats);
+  if (epi2) {
+    NPP_LAUNCH((conv3_kernel<BN, true>), grid, kThreads2, smem, st, maps, g, bias, stats);
+  } else {
+    NPP_LAUNCH((conv3_kernel<BN, false>), grid, kThreads2, smem, st, maps, g, bias, stats);
+  }
   NPP_CHECK_LAUNCH("conv3_kernel");
   return NPP_OK;
 }
