@@ -378,6 +378,60 @@ struct EpiMask {   // which rows of a 128-row unit are real pixels (statistics m
   bool full;
 };
 
+// BatchNorm sums of one 16-byte chunk (8 channels) of a staging slab: lane l adds up rows 4l..4l+3, visited in a
+// lane-skewed order so that the 8 lanes of an LDS.128 phase hit 8 different swizzle slots.  All four loads are issued
+// before the first use and rows outside the tensor are masked by a select, not a branch (the first version branched
+// per row, which serialised the four shared-memory round trips: ~620 cycles per unit).
+template <bool MASKED>
+__device__ __forceinline__ void epi_chunk_sums_t(const uint8_t* __restrict__ stg, const int chunk, const int lane,
+                                                 const EpiMask& mk, float* __restrict__ as, float* __restrict__ aq) {
+  uint4 u[4];
+  bool ok[4];
+  uint32_t ad[4];
+  const uint32_t stg_a = smem_u32(stg);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = lane * 4 + ((i + (lane >> 1)) & 3);
+    ad[i] = stg_a + rr * 128 + ((chunk ^ (rr & 7)) << 4);
+    ok[i] = true;
+    if (MASKED) {
+      const int p = mk.p_off + rr;
+      const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
+      ok[i] = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
+    }
+  }
+  // one statement: the four loads are issued back to back into four distinct register quads (left to itself the
+  // compiler recycles one quad and serialises load -> use -> load)
+  asm volatile(
+      "ld.shared.v4.u32 {%0, %1, %2, %3}, [%16];\n\t"
+      "ld.shared.v4.u32 {%4, %5, %6, %7}, [%17];\n\t"
+      "ld.shared.v4.u32 {%8, %9, %10, %11}, [%18];\n\t"
+      "ld.shared.v4.u32 {%12, %13, %14, %15}, [%19];"
+      : "=r"(u[0].x), "=r"(u[0].y), "=r"(u[0].z), "=r"(u[0].w), "=r"(u[1].x), "=r"(u[1].y), "=r"(u[1].z), "=r"(u[1].w),
+        "=r"(u[2].x), "=r"(u[2].y), "=r"(u[2].z), "=r"(u[2].w), "=r"(u[3].x), "=r"(u[3].y), "=r"(u[3].z), "=r"(u[3].w)
+      : "r"(ad[0]), "r"(ad[1]), "r"(ad[2]), "r"(ad[3])
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t uu[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
+      if (MASKED && !ok[i]) v = make_float2(0.f, 0.f);
+      const float2 s2 = __fadd2_rn(make_float2(as[2 * e], as[2 * e + 1]), v);
+      const float2 q2 = __ffma2_rn(v, v, make_float2(aq[2 * e], aq[2 * e + 1]));
+      as[2 * e] = s2.x; as[2 * e + 1] = s2.y;
+      aq[2 * e] = q2.x; aq[2 * e + 1] = q2.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_chunk_sums(const uint8_t* __restrict__ stg, const int chunk, const int lane,
+                                               const EpiMask& mk, float* __restrict__ as, float* __restrict__ aq) {
+  if (mk.full) epi_chunk_sums_t<false>(stg, chunk, lane, mk, as, aq);   // uniform across the CTA
+  else epi_chunk_sums_t<true>(stg, chunk, lane, mk, as, aq);
+}
+
 // One unit = 128 rows (TMEM lanes) x one 64-column slab (SLAB_COLS = 32 for the BN = 32 kernels) of the accumulator:
 // TMEM -> (+bias) -> bf16 -> swizzled staging slab -> TMA store; BatchNorm sums of the rounded values.
 template <int SLAB_COLS>
@@ -432,31 +486,8 @@ __device__ __forceinline__ void epi_unit(const uint32_t taddr, uint8_t* stg, con
   }
   C3P_STAMP(e_t5);
   if (want_stats && ew * 8 < SLAB_COLS) {
-    // Epilogue warp ew owns the 16-byte chunk ew (8 channels) of every row; lane l adds up rows 4l..4l+3, visited
-    // in a lane-skewed order so that the 8 lanes of an LDS.128 phase hit 8 different swizzle slots (bank groups).
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = lane * 4 + ((i + (lane >> 1)) & 3);
-      bool ok = true;
-      if (!mk.full) {
-        const int p = mk.p_off + rr;
-        const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
-        ok = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
-      }
-      const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ew ^ (rr & 7)) << 4));
-      if (ok) {
-        // packed fp32x2 adds / fmas (sm_100): the statistics are instruction-issue bound (~43 % of an epilogue unit)
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
-          const float2 s2 = __fadd2_rn(make_float2(as[2 * e], as[2 * e + 1]), v);
-          const float2 q2 = __ffma2_rn(v, v, make_float2(aq[2 * e], aq[2 * e + 1]));
-          as[2 * e] = s2.x; as[2 * e + 1] = s2.y;
-          aq[2 * e] = q2.x; aq[2 * e + 1] = q2.y;
-        }
-      }
-    }
+    // epilogue warp ew owns the 16-byte chunk ew (8 channels) of every row
+    epi_chunk_sums(stg, ew, lane, mk, as, aq);
   }
 #ifdef NPP_C3_PROF
   if (etid == 0) {
@@ -546,31 +577,8 @@ __device__ __forceinline__ void epi_pair32(const uint32_t taddr, uint8_t* stg, c
   }
   if (want_stats) {
     const int half = ew >> 2, chunk = ew & 3;
-    const uint8_t* src = stg + half * (128 * 128);
     mk.p_off = half * 128;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = lane * 4 + ((i + (lane >> 1)) & 3);
-      bool ok = true;
-      if (!mk.full) {
-        const int p = mk.p_off + rr;
-        const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
-        ok = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
-      }
-      const uint4 u = *reinterpret_cast<const uint4*>(src + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-      if (ok) {
-        // packed fp32x2 adds / fmas (sm_100): the statistics are instruction-issue bound (~43 % of an epilogue unit)
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
-          const float2 s2 = __fadd2_rn(make_float2(as[2 * e], as[2 * e + 1]), v);
-          const float2 q2 = __ffma2_rn(v, v, make_float2(aq[2 * e], aq[2 * e + 1]));
-          as[2 * e] = s2.x; as[2 * e + 1] = s2.y;
-          aq[2 * e] = q2.x; aq[2 * e + 1] = q2.y;
-        }
-      }
-    }
+    epi_chunk_sums(stg + half * (128 * 128), chunk, lane, mk, as, aq);
   }
 }
 
@@ -637,31 +645,7 @@ __device__ __forceinline__ void epi_unit_grp(const uint32_t taddr, uint8_t* stg,
   if (want_stats) {
     constexpr int NCH = SLAB_COLS / 32;  // 16-byte chunks per warp: 2 (64-column slab) or 1
 #pragma unroll
-    for (int cc = 0; cc < NCH; ++cc) {
-      const int chunk = NCH * q + cc;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = lane * 4 + ((i + (lane >> 1)) & 3);  // lane-skewed: conflict-free LDS.128 (see epi_unit)
-        bool ok = true;
-        if (!mk.full) {
-          const int p = mk.p_off + rr;
-          const int pw = p % mk.tw, ph = (p / mk.tw) % mk.th, pn = p / (mk.tw * mk.th);
-          ok = (mk.w0 + pw < mk.W) && (mk.h0 + ph < mk.H) && (mk.n0 + pn < mk.N);
-        }
-        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-        if (ok) {
-          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 v = make_float2(__uint_as_float(uu[e] << 16), __uint_as_float(uu[e] & 0xffff0000u));
-            const float2 s2 = __fadd2_rn(make_float2(as[cc * 8 + 2 * e], as[cc * 8 + 2 * e + 1]), v);
-            const float2 q2 = __ffma2_rn(v, v, make_float2(aq[cc * 8 + 2 * e], aq[cc * 8 + 2 * e + 1]));
-            as[cc * 8 + 2 * e] = s2.x; as[cc * 8 + 2 * e + 1] = s2.y;
-            aq[cc * 8 + 2 * e] = q2.x; aq[cc * 8 + 2 * e + 1] = q2.y;
-          }
-        }
-      }
-    }
+    for (int cc = 0; cc < NCH; ++cc) epi_chunk_sums(stg, NCH * q + cc, lane, mk, as + cc * 8, aq + cc * 8);
   }
 }
 
