@@ -2123,7 +2123,9 @@ static int conv3_try(const npp_view4* a, const npp_view4* d, const void* wmat, i
     g.sa = (avail - 9 * b_bytes) / g.a_bytes;
     if (g.sa > kC3MaxSA) g.sa = kC3MaxSA;
   } else {
-    if (g.sa * g.a_bytes + 4 * b_bytes > avail) g.sa = 2;
+    static const int sa_env = env_flag("NPP_CONV3_SA", 0);  // experiments: activation ring depth (the weight ring gets the rest)
+    if (sa_env >= 2 && sa_env <= kC3MaxSA && sa_env * g.a_bytes + 3 * b_bytes <= avail) g.sa = sa_env;
+    else if (g.sa * g.a_bytes + 4 * b_bytes > avail) g.sa = 2;
     g.sb = (avail - g.sa * g.a_bytes) / b_bytes;
     if (g.sb > kC3MaxSB) g.sb = kC3MaxSB;
     if (g.sb < 3) return NPP_E_UNSUPPORTED;
