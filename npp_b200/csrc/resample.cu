@@ -133,13 +133,64 @@ static int bilinear_bwd_t(const npp_view4* dy, const npp_view4* dx, Axis ah, Axi
 //     dx[n, h, w, c]  = sum_ho wh(ho, h) * T[n, ho, w, c]          (pass 2)
 // reads dY once, touches 2s+1 candidates per axis instead of (2s+1)^2, and keeps the same tap arithmetic
 // (bilinear_taps / bilinear_range); only the summation order differs from the gather form (fp32 rounding).
+// First pass of the separable backward with all candidate loads in flight: the loop form below tests every candidate
+// and loads inside the branch, so the (up to 2 / scale) contributing dY vectors of an input column arrive one L2 round
+// trip after the other.  Here the candidate window is a fixed MAXC columns from a tight lower bound, every load is
+// issued unconditionally (clamped address), the tap test only decides the weight (0 outside).  Same tap arithmetic.
+template <typename T, int MAXC>
+static int bilinear_bwd_sep_w_batched(const npp_view4* dy, float* tmp, int Wi, Axis aw, cudaStream_t st) {
+  constexpr int V = Pack<T>::N;
+  const auto DY = dview<const T>(dy);
+  const int Ho = dy->h, Wo = dy->w, C = dy->c;
+  const float inv = 1.f / aw.scale, off = aw.align ? 0.f : 0.5f;
+  return foreach_vec<V>(dy->n, Ho, Wi, C, st, "bilinear_bwd_sep(w, batched)", [=] __device__(int n, int ho, int w, int c) {
+    // taps of wo reach w only if src(wo) is in (w - 1, w + 1): wo > ((w - 1) + off) / scale - off  (one column of slack
+    // for fp rounding; the weights below are exact whatever the window)
+    int lo = (int)floorf(((float)w - 1.f + off) * inv - off) - 1;
+    if (lo < 0) lo = 0;
+    if (lo > Wo - MAXC) lo = max(Wo - MAXC, 0);
+    uint4 q[MAXC];
+    float ww[MAXC];
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int wo = min(lo + j, Wo - 1);
+      q[j] = ldraw(DY.at(n, ho, wo, c));
+      int w0, w1;
+      float lw0, lw1;
+      bilinear_taps(aw, wo, w0, w1, lw0, lw1);
+      ww[j] = (lo + j < Wo) ? ((w0 == w ? lw0 : 0.f) + (w1 == w ? lw1 : 0.f)) : 0.f;
+    }
+    float g[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      float d[V];
+      Pack<T>::unpack(q[j], d);
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] = fmaf(ww[j], d[i], g[i]);
+    }
+    float* tp = tmp + (((int64_t)n * Ho + ho) * Wi + w) * C + c;
+#pragma unroll
+    for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(tp + i) = make_float4(g[i], g[i + 1], g[i + 2], g[i + 3]);
+  });
+}
+
 template <typename T>
 static int bilinear_bwd_sep_t(const npp_view4* dy, const npp_view4* dx, float* tmp, Axis ah, Axis aw, cudaStream_t st) {
   constexpr int V = Pack<T>::N;
   const auto DY = dview<const T>(dy);
   const auto DX = dview<T>(dx);
   const int Ho = dy->h, Wi = dx->w, C = dx->c;
-  int rc = foreach_vec<V>(dy->n, Ho, Wi, C, st, "bilinear_bwd_sep(w)", [=] __device__(int n, int ho, int w, int c) {
+  static const int batched = []() { const char* e = getenv("NPP_BILINEAR_BWD_BATCHED"); return (e && *e) ? atoi(e) : 1; }();
+  int rc;
+  // window = 2 / scale + 4 columns: x2 up-sampling -> 8 (scale >= 0.45 incl. align_corners 47/95), x4 -> 13
+  if (batched && aw.scale >= 0.45f && aw.scale <= 1.f && dy->w >= 8)
+    rc = bilinear_bwd_sep_w_batched<T, 8>(dy, tmp, Wi, aw, st);
+  else if (batched && aw.scale >= 0.2f && aw.scale < 0.45f && dy->w >= 13)
+    rc = bilinear_bwd_sep_w_batched<T, 13>(dy, tmp, Wi, aw, st);
+  else
+  rc = foreach_vec<V>(dy->n, Ho, Wi, C, st, "bilinear_bwd_sep(w)", [=] __device__(int n, int ho, int w, int c) {
     float g[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) g[i] = 0.f;
