@@ -182,7 +182,9 @@ static int bilinear_bwd_sep_t(const npp_view4* dy, const npp_view4* dx, float* t
   const auto DY = dview<const T>(dy);
   const auto DX = dview<T>(dx);
   const int Ho = dy->h, Wi = dx->w, C = dx->c;
-  static const int batched = []() { const char* e = getenv("NPP_BILINEAR_BWD_BATCHED"); return (e && *e) ? atoi(e) : 1; }();
+  // measured: 83.42 ms per train step with the batched first pass against 82.92 ms without (profiles/r02_bilinear_ab.txt):
+  // the extra registers cost more occupancy than the overlapped loads win -> off by default
+  static const int batched = []() { const char* e = getenv("NPP_BILINEAR_BWD_BATCHED"); return (e && *e) ? atoi(e) : 0; }();
   int rc;
   // window = 2 / scale + 4 columns: x2 up-sampling -> 8 (scale >= 0.45 incl. align_corners 47/95), x4 -> 13
   if (batched && aw.scale >= 0.45f && aw.scale <= 1.f && dy->w >= 8)
